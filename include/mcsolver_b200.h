@@ -1,0 +1,177 @@
+/* mcsolver_b200.h - C ABI of libmcsolver_b200.so, the B200-native Monte Carlo engine.
+ *
+ * Drop-in boundary: the reference's native engines are three CPython extension
+ * modules exporting one function each,
+ *     heisenberglib.MCMainFunction   /root/reference/mcsolver/heisenbergLib.c:478
+ *     xylib.MCMainFunction           /root/reference/mcsolver/xyLib.c:413
+ *     isinglib.MCMainFunction        /root/reference/mcsolver/isingLib.c:259
+ * called from mcMain.py:119-124 (Ising) and mcMain.py:239-248 (XY/Heisenberg).  The shims
+ * mcsolver_b200/lib/{isinglib,xylib,heisenberglib}.py expose the same MCMainFunction(*args)
+ * and bind the entry points below through ctypes.  Plain pointers and sizes only; every
+ * function returns 0 on success and a non-zero mcg_status otherwise, with a thread-local
+ * message available from mcg_last_error() (the reference signals no errors at all and
+ * segfaults on bad input: heisenbergLib.c:504 ignores PyArg_ParseTuple's result).
+ *
+ * There is no CPU fallback: if no CUDA device is usable every entry point fails with
+ * MCG_ERR_CUDA.
+ */
+#ifndef MCSOLVER_B200_H
+#define MCSOLVER_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define MCG_API __attribute__((visibility("default")))
+#else
+#define MCG_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    MCG_OK = 0,
+    MCG_ERR_ARG = 1,      /* invalid argument (bad index, bad size, NULL, unsupported combination) */
+    MCG_ERR_CUDA = 2,     /* CUDA runtime failure / no device */
+    MCG_ERR_ALLOC = 3,
+    MCG_ERR_STATE = 4,    /* call sequence error (e.g. results before any measurement) */
+    MCG_ERR_NCCL = 5
+} mcg_status;
+
+typedef struct mcg_system mcg_system; /* opaque: tables + replica states resident in HBM */
+
+/* models: the reference's three engines */
+#define MCG_ISING 1       /* isingLib.c      */
+#define MCG_XY 2          /* xyLib.c         */
+#define MCG_HEISENBERG 3  /* heisenbergLib.c */
+
+/* update algorithms (first positional argument of MCMainFunction, mcMain.py:107-108,147-148) */
+#define MCG_METROPOLIS 0  /* localUpdate: heisenbergLib.c:441, xyLib.c:382, isingLib.c:238 */
+#define MCG_WOLFF 1       /* blockUpdate: heisenbergLib.c:373, xyLib.c:319, isingLib.c:202 */
+
+/* Per-site tables: exactly the payload of one MCMainFunction call (SURVEY 8b "Signature").
+ * O(n): heisenbergLib.c:504-585.  Ising: isingLib.c:277-335 (D, tri, groups unused; J has one
+ * number per link instead of nine).  All couplings are in units of kT_table (the reference
+ * passes everything pre-divided by T, mcMain.py:21-31); per-replica beta[] (mcg_config) scales
+ * them further, so tables may also be left unscaled and beta[r] = 1/T_r used instead. */
+typedef struct {
+    int32_t model;            /* MCG_ISING | MCG_XY | MCG_HEISENBERG */
+    int32_t N;                /* totOrbs */
+    int32_t maxL;             /* maxNLinking */
+    const double *S;          /* [N]   initSpin: signed spin length (Ising: the +-S configuration) */
+    const double *D;          /* [N*3] initD (x,y,z as parsed); NULL = 0 */
+    const int32_t *nlink;     /* [N] */
+    const double *J;          /* O(n): [N*maxL*9] xx,yy,zz,xy,xz,yz,yx,zx,zy ; Ising: [N*maxL] */
+    const int32_t *nbr;       /* [N*maxL] linkedOrb, -1 padded */
+    int32_t nTri;             /* number of triangle circuits */
+    const int32_t *tri;       /* [nTri*3] localCircuits */
+    int32_t nLat;             /* number of correlated pairs */
+    const int32_t *pairs;     /* [nLat*2] corrOrbPair */
+    int32_t nG, maxG;         /* nOrbGroup, maxOrbGroupSize */
+    const int32_t *groups;    /* [nG*maxG] orbGroupList, -1 padded */
+    int32_t nR, nC;           /* block-spin sites, cluster size */
+    const int32_t *rOrb;      /* [nR] */
+    const int32_t *rCl;       /* [nR*nC] rOrbCluster */
+    const int32_t *rNbr;      /* [nR*maxL] linkedOrb_rnorm */
+    int32_t ignoreOffDiag;    /* ignoreNonDiagonalJ: use only Jxx,Jyy,Jzz (heisenbergLib.c:592-593) */
+} mcg_tables;
+
+/* Compact translation-invariant lattice: what a parameter file holds (fileio.py:10-22) and what
+ * Lattice.py:155-284 expands into one Python object per orbital.  The engine expands it on the
+ * device instead (structured path: neighbour indices are computed, not stored). */
+typedef struct {
+    int32_t src, tgt;         /* orbital indices inside the cell */
+    int32_t d[3];             /* overLat: target cell = source cell + d (periodic) */
+    double J[9];              /* xx,yy,zz,xy,xz,yz,yx,zx,zy (Ising: J[0]) - Lattice.py:127-137 */
+} mcg_bond;
+
+typedef struct {
+    int32_t model;
+    int32_t L[3];             /* supercell Lx,Ly,Lz ; site id = ((x*Ly+y)*Lz+z)*norb+o (Lattice.py:171-184) */
+    int32_t norb;
+    const double *S;          /* [norb] */
+    const double *D;          /* [norb*3]; NULL = 0 */
+    int32_t nbond;
+    const mcg_bond *bonds;
+    int32_t pair_s, pair_t;   /* correlated pair: orbital pair_s in cell, pair_t in cell+pair_d */
+    int32_t pair_d[3];
+    int32_t ncircuit;         /* triangles per cell */
+    const int32_t *circuits;  /* [ncircuit*3*4]: per vertex (orb, dx, dy, dz) - Lattice.py:223-234 */
+} mcg_lattice_desc;
+
+typedef struct {
+    int32_t precision;        /* 32: fp32 spin state and arithmetic; 64: fp64 (parity level 1) */
+    int32_t nReplica;         /* independent (T,H) points / PT replicas resident on this GPU */
+    const double *beta;       /* [nReplica] multiplies J and D;  NULL = 1.0 (tables pre-scaled) */
+    const double *field;      /* [nReplica] h (units of the table energies; multiplied by beta) */
+    uint64_t seed;            /* Philox key */
+    int32_t replica_offset;   /* global index of local replica 0 (keeps RNG streams GPU-count independent) */
+    int32_t device;           /* CUDA device ordinal, -1 = current */
+} mcg_config;
+
+MCG_API const char *mcg_last_error(void);
+MCG_API int mcg_version(void);
+MCG_API int mcg_device_count(int *count);
+
+/* ---- system life cycle ---- */
+MCG_API int mcg_create_tables(const mcg_tables *t, const mcg_config *cfg, mcg_system **out);
+MCG_API int mcg_create_lattice(const mcg_lattice_desc *d, const mcg_config *cfg, mcg_system **out);
+MCG_API int mcg_destroy(mcg_system *sys);
+MCG_API int mcg_num_colours(const mcg_system *sys, int *ncolours);
+MCG_API int mcg_colour_order(const mcg_system *sys, int32_t *order /*[N] site ids, colour-major*/);
+MCG_API int mcg_set_params(mcg_system *sys, const double *beta, const double *field); /* per replica */
+
+/* ---- state ---- */
+/* initial state of establishLattice (heisenbergLib.c:157-172): normalise((S,0,0)+flunc*n)*|S| */
+MCG_API int mcg_init_spins(mcg_system *sys, double flunc);
+MCG_API int mcg_set_spins(mcg_system *sys, int replica, const double *spins /* O(n):[N*3]  Ising:[N] */);
+MCG_API int mcg_get_spins(mcg_system *sys, int replica, double *spins);
+
+/* ---- parity level 1: energy of the resident configuration, fp64 accumulation ----
+ * getCorrEnergy / getOnsiteEnergy (heisenbergLib.c:238-253, xyLib.c:191-204, isingLib.c:121-127,232).
+ * Etot = sum_i ebond_i/2 + sum_i eonsite_i, in beta*E units of the replica.  Per-site arrays may be NULL. */
+MCG_API int mcg_energy(mcg_system *sys, int replica, double *Etot, double *ebond_site, double *eonsite_site);
+
+/* ---- updates ---- */
+/* nsweeps colour-class Metropolis sweeps (each site attempted once per sweep with probability
+ * pAttempt); one attempt = localUpdate (heisenbergLib.c:441-473 / xyLib.c:382-409 / isingLib.c:238-254) */
+MCG_API int mcg_metropolis_sweeps(mcg_system *sys, int64_t nsweeps, double pAttempt);
+/* nsteps Wolff single-cluster updates (blockUpdate) by bond activation + union-find labelling */
+MCG_API int mcg_wolff_steps(mcg_system *sys, int64_t nsteps);
+
+/* ---- measurement (heisenbergLib.c:661-831 definitions) ---- */
+MCG_API int mcg_measure(mcg_system *sys);              /* accumulate one "sweep" worth of observables */
+MCG_API int mcg_reset_measurements(mcg_system *sys);
+/* O(n): out[27] = tuple slots 0..26 of heisenbergLib.c:853-881 ; Ising: out[10] = isingLib.c:435-446.
+ * groupOut [(nG+2)*(nG+1)] = slot 28 (may be NULL). */
+MCG_API int mcg_results(mcg_system *sys, int replica, double *out, double *groupOut);
+MCG_API int mcg_counters(mcg_system *sys, int replica, int64_t *attempts, int64_t *accepted, int64_t *cluster_sites);
+
+/* ---- the whole MCMainFunction loop on the resident system ----
+ * thermalise nthermal intervals, then nsweep x (ninterval updates + measurement).
+ * Metropolis: ninterval >= N -> round(ninterval/N) sweeps per interval, else one sweep with
+ * attempt probability ninterval/N.  Wolff: ninterval cluster updates per interval.
+ * frames: NULL or [nReplica][spinFrame][N*3] (Ising [N]) host buffer (slot 27 / 10). */
+MCG_API int mcg_run(mcg_system *sys, int algorithm, int64_t nthermal, int64_t nsweep, int64_t ninterval, int spinFrame,
+            double *frames);
+
+/* ---- one-shot legacy entry points: one call = one MCMainFunction call ---- */
+MCG_API int mcg_run_on(const mcg_tables *t, int algorithm, int64_t nthermal, int64_t nsweep, int64_t ninterval, double flunc,
+               double h, int spinFrame, uint64_t seed, int precision, double out27[27], double *frames,
+               double *groupOut);
+MCG_API int mcg_run_ising(const mcg_tables *t, int algorithm, int64_t nthermal, int64_t nsweep, int64_t ninterval, double h,
+                  int spinFrame, uint64_t seed, int precision, double out10[10], double *frames);
+
+/* ---- parallel tempering (new capability): replica ladder, temperature-label swaps ---- */
+/* Exchange attempt between neighbouring temperatures of the ladder held by this system (single
+ * GPU) - energies come from the last measurement/energy evaluation. parity = 0/1 (even/odd pairs). */
+MCG_API int mcg_pt_swap_local(mcg_system *sys, int parity, uint64_t step);
+/* Multi-GPU: energies[] of ALL replicas of the ladder (allgathered by the host layer over NCCL) */
+MCG_API int mcg_pt_energies(mcg_system *sys, double *energies_local /*[nReplica]*/);
+MCG_API int mcg_pt_apply(mcg_system *sys, const double *beta_local, const double *field_local);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCSOLVER_B200_H */

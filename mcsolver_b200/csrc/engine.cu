@@ -1,0 +1,584 @@
+// libmcsolver_b200: host side of the engine and the C ABI of include/mcsolver_b200.h.
+//
+// Generic (table-driven) path: the legacy MCMainFunction payload (per-site link tables) is
+// coloured greedily from its own bond list, reordered colour-major, its exchange tensors and
+// (|S|, D) site classes deduplicated into small tables, and everything is made resident in HBM.
+// The structured path (structured.cu) takes a compact lattice descriptor instead.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <numeric>
+
+#include "kernels_wolff.cuh"
+#include "structured.hpp"
+
+namespace mcg {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string &m) { g_last_error = m; }
+
+template <typename F> static int guarded(F &&f) {
+    try {
+        f();
+        return MCG_OK;
+    } catch (const Error &e) {
+        set_last_error(e.what());
+        return e.code;
+    } catch (const std::bad_alloc &) {
+        set_last_error("host allocation failed");
+        return MCG_ERR_ALLOC;
+    } catch (const std::exception &e) {
+        set_last_error(e.what());
+        return MCG_ERR_ARG;
+    }
+}
+
+template <typename T> static T *dalloc(size_t n) {
+    T *p = nullptr;
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+    if (e != cudaSuccess) throw Error(MCG_ERR_ALLOC, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    return p;
+}
+template <typename T> static T *dupload(const std::vector<T> &v) {
+    T *p = dalloc<T>(v.size());
+    if (!v.empty()) MCG_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return p;
+}
+template <typename real> static void *dupload_real(const std::vector<double> &v) {
+    std::vector<real> t(v.begin(), v.end());
+    return dupload<real>(t);
+}
+
+static void select_device(const mcg_config *cfg, mcg_system *s) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        throw Error(MCG_ERR_CUDA, std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    int dev = cfg->device;
+    if (dev < 0) MCG_CUDA(cudaGetDevice(&dev));
+    MCG_REQUIRE(dev < n, "device ordinal out of range");
+    MCG_CUDA(cudaSetDevice(dev));
+    s->device = dev;
+}
+
+static GenArgs gen_args(const mcg_system *s) {
+    GenArgs a;
+    a.N = s->N; a.maxL = s->maxL; a.R = s->R; a.nJ = s->nJ; a.ncls = s->ncls;
+    a.nbrp = s->d_nbrp; a.jtype = s->d_jtype; a.Jtab = s->d_Jtab; a.cls = s->d_cls; a.clsS = s->d_clsS; a.clsD = s->d_clsD;
+    a.site_of = s->d_site_of; a.spin = s->d_spin; a.beta = s->d_beta; a.field = s->d_field; a.cnt = s->d_cnt;
+    a.key.k0 = (uint32_t)s->seed; a.key.k1 = (uint32_t)(s->seed >> 32);
+    a.replica0 = s->replica0;
+    return a;
+}
+
+// dispatch on (components, precision, full-tensor) -> f.template operator()<NC, real, FULLJ>()
+template <typename F> static void dispatch(const mcg_system *s, F &&f) {
+    bool d = s->prec == 64, fj = s->fullJ;
+    switch (s->NC) {
+    case 1: d ? f.template operator()<1, double, false>() : f.template operator()<1, float, false>(); break;
+    case 2:
+        if (d) fj ? f.template operator()<2, double, true>() : f.template operator()<2, double, false>();
+        else fj ? f.template operator()<2, float, true>() : f.template operator()<2, float, false>();
+        break;
+    default:
+        if (d) fj ? f.template operator()<3, double, true>() : f.template operator()<3, double, false>();
+        else fj ? f.template operator()<3, float, true>() : f.template operator()<3, float, false>();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// system construction from per-site tables
+// ---------------------------------------------------------------------------------------------
+static void greedy_colouring(int N, int maxL, const int32_t *nlink, const int32_t *nbr, std::vector<int> &colour, int &C) {
+    // symmetric adjacency in CSR form (the reference's tables are symmetric: J on the source,
+    // J^T on the target, Lattice.py:260-262; we do not rely on it for race freedom)
+    std::vector<int> deg(N + 1, 0);
+    for (int i = 0; i < N; i++)
+        for (int k = 0; k < nlink[i]; k++) {
+            int j = nbr[(size_t)i * maxL + k];
+            if (j == i) continue;
+            deg[i + 1]++; deg[j + 1]++;
+        }
+    for (int i = 0; i < N; i++) deg[i + 1] += deg[i];
+    std::vector<int> adj(deg[N]), fill(deg.begin(), deg.end() - 1);
+    for (int i = 0; i < N; i++)
+        for (int k = 0; k < nlink[i]; k++) {
+            int j = nbr[(size_t)i * maxL + k];
+            if (j == i) continue;
+            adj[fill[i]++] = j; adj[fill[j]++] = i;
+        }
+    colour.assign(N, -1);
+    C = 0;
+    std::vector<int> mark;   // mark[c] == i  <=> colour c used by a neighbour of i
+    for (int i = 0; i < N; i++) {
+        for (int e = deg[i]; e < deg[i + 1]; e++) {
+            int c = colour[adj[e]];
+            if (c >= 0) { if ((int)mark.size() <= c) mark.resize(c + 1, -1); mark[c] = i; }
+        }
+        int c = 0;
+        while (c < (int)mark.size() && mark[c] == i) c++;
+        colour[i] = c;
+        C = std::max(C, c + 1);
+    }
+    for (int i = 0; i < N; i++)   // validation: "no two same-colour sites linked"
+        for (int e = deg[i]; e < deg[i + 1]; e++)
+            if (colour[adj[e]] == colour[i]) throw Error(MCG_ERR_STATE, "internal: colouring is not proper");
+}
+
+static void validate_tables(const mcg_tables *t) {
+    MCG_REQUIRE(t, "tables is NULL");
+    MCG_REQUIRE(t->model >= 1 && t->model <= 3, "model must be 1 (Ising), 2 (XY) or 3 (Heisenberg)");
+    MCG_REQUIRE(t->N > 0, "N must be positive");
+    MCG_REQUIRE(t->maxL >= 0, "maxL must be non-negative");
+    MCG_REQUIRE(t->S && t->nlink && (t->maxL == 0 || (t->J && t->nbr)), "S/nlink/J/nbr must not be NULL");
+    MCG_REQUIRE(t->nLat > 0 && t->pairs, "at least one correlated pair is required (nLat>0)");
+    for (int i = 0; i < t->N; i++) {
+        MCG_REQUIRE(t->nlink[i] >= 0 && t->nlink[i] <= t->maxL, "nlink[i] out of range");
+        for (int k = 0; k < t->nlink[i]; k++) {
+            int j = t->nbr[(size_t)i * t->maxL + k];
+            MCG_REQUIRE(j >= 0 && j < t->N, "linkedOrb index out of range");
+        }
+    }
+    for (int j = 0; j < 2 * t->nLat; j++) MCG_REQUIRE(t->pairs[j] >= 0 && t->pairs[j] < t->N, "corrOrbPair index out of range");
+    MCG_REQUIRE(t->nTri >= 0 && (t->nTri == 0 || t->tri), "tri is NULL");
+    for (int j = 0; j < 3 * t->nTri; j++) MCG_REQUIRE(t->tri[j] >= 0 && t->tri[j] < t->N, "localCircuits index out of range");
+}
+
+static void alloc_replica_state(mcg_system *s, const mcg_config *cfg) {
+    s->beta_host.assign(s->R, 1.0);
+    s->field_host.assign(s->R, 0.0);
+    if (cfg->beta) s->beta_host.assign(cfg->beta, cfg->beta + s->R);
+    if (cfg->field) s->field_host.assign(cfg->field, cfg->field + s->R);
+    s->d_beta = dupload(s->beta_host);
+    s->d_field = dupload(s->field_host);
+    s->d_sums = dalloc<double>((size_t)s->R * NSUM);
+    s->d_acc = dalloc<double>((size_t)s->R * NACC);
+    s->d_cnt = dalloc<unsigned long long>((size_t)s->R * NCNT);
+    MCG_CUDA(cudaMemset(s->d_sums, 0, sizeof(double) * s->R * NSUM));
+    MCG_CUDA(cudaMemset(s->d_acc, 0, sizeof(double) * s->R * NACC));
+    MCG_CUDA(cudaMemset(s->d_cnt, 0, sizeof(unsigned long long) * s->R * NCNT));
+}
+
+static mcg_system *create_from_tables(const mcg_tables *t, const mcg_config *cfg) {
+    validate_tables(t);
+    MCG_REQUIRE(cfg, "config is NULL");
+    MCG_REQUIRE(cfg->precision == 32 || cfg->precision == 64, "precision must be 32 or 64");
+    MCG_REQUIRE(cfg->nReplica >= 1, "nReplica must be >= 1");
+    std::unique_ptr<mcg_system> sys(new mcg_system());
+    mcg_system *s = sys.get();
+    select_device(cfg, s);
+    s->model = t->model; s->NC = t->model; s->prec = cfg->precision; s->R = cfg->nReplica;
+    s->N = t->N; s->maxL = std::max(1, (int)t->maxL);
+    s->seed = cfg->seed; s->replica0 = (uint32_t)cfg->replica_offset;
+    const int N = s->N, maxL = t->maxL, JW = t->model == 1 ? 1 : 9;
+    s->fullJ = t->model != 1 && !t->ignoreOffDiag;
+
+    std::vector<int> colour;
+    greedy_colouring(N, maxL, t->nlink, t->nbr, colour, s->C);
+    // colour-major permutation (stable: reference id order inside a class)
+    s->colourStart.assign(s->C + 1, 0);
+    for (int i = 0; i < N; i++) s->colourStart[colour[i] + 1]++;
+    for (int c = 0; c < s->C; c++) s->colourStart[c + 1] += s->colourStart[c];
+    s->site_of.resize(N); s->pos_of.resize(N);
+    {
+        std::vector<int> fill(s->colourStart.begin(), s->colourStart.end() - 1);
+        for (int i = 0; i < N; i++) { int p = fill[colour[i]]++; s->site_of[p] = i; s->pos_of[i] = p; }
+    }
+    // deduplicate exchange tensors (index 0 = zero tensor for padding) and (|S|, D) site classes
+    std::map<std::vector<double>, int> jmap, cmap;
+    std::vector<double> Jtab(JW, 0.0), clsS, clsD;
+    jmap[std::vector<double>(JW, 0.0)] = 0;
+    std::vector<int32_t> nbrp((size_t)s->maxL * N);
+    std::vector<uint16_t> jtype((size_t)s->maxL * N, 0), cls(N);
+    for (int p = 0; p < N; p++) {
+        int i = s->site_of[p];
+        for (int k = 0; k < s->maxL; k++) {
+            size_t o = (size_t)k * N + p;
+            if (k >= t->nlink[i]) { nbrp[o] = p; jtype[o] = 0; continue; }
+            nbrp[o] = s->pos_of[t->nbr[(size_t)i * maxL + k]];
+            std::vector<double> J(t->J + ((size_t)i * maxL + k) * JW, t->J + ((size_t)i * maxL + k) * JW + JW);
+            if (t->model != 1 && t->ignoreOffDiag) for (int c = 3; c < 9; c++) J[c] = 0.0;
+            auto it = jmap.find(J);
+            if (it == jmap.end()) {
+                MCG_REQUIRE(jmap.size() < 65535, "more than 65535 distinct exchange tensors");
+                it = jmap.emplace(J, (int)jmap.size()).first;
+                Jtab.insert(Jtab.end(), J.begin(), J.end());
+            }
+            jtype[o] = (uint16_t)it->second;
+        }
+        std::vector<double> key = {std::fabs(t->S[i]), t->D ? t->D[3 * i] : 0.0, t->D ? t->D[3 * i + 1] : 0.0,
+                                   t->D ? t->D[3 * i + 2] : 0.0};
+        if (t->model == 1) key[1] = key[2] = key[3] = 0.0;
+        auto ic = cmap.find(key);
+        if (ic == cmap.end()) {
+            MCG_REQUIRE(cmap.size() < 65535, "more than 65535 distinct (S,D) site classes");
+            ic = cmap.emplace(key, (int)cmap.size()).first;
+            clsS.push_back(key[0]);
+            clsD.insert(clsD.end(), key.begin() + 1, key.end());
+        }
+        cls[p] = (uint16_t)ic->second;
+    }
+    s->nJ = (int)jmap.size(); s->ncls = (int)cmap.size();
+    s->S_host.assign(t->S, t->S + N);
+    std::vector<double> signS(N);
+    for (int p = 0; p < N; p++) signS[p] = t->S[s->site_of[p]];
+    // measurement tables in storage positions
+    s->nLat = t->nLat; s->nTri = t->model == 3 ? t->nTri : 0;
+    std::vector<int32_t> pairs(2 * (size_t)t->nLat), tri(3 * (size_t)s->nTri), mi(N, 0), mj(N, 0);
+    s->selfPairs = true;
+    for (int j = 0; j < t->nLat; j++) {
+        pairs[2 * j] = s->pos_of[t->pairs[2 * j]]; pairs[2 * j + 1] = s->pos_of[t->pairs[2 * j + 1]];
+        mi[pairs[2 * j]]++; mj[pairs[2 * j + 1]]++;
+        if (pairs[2 * j] != pairs[2 * j + 1]) s->selfPairs = false;
+    }
+    for (int j = 0; j < 3 * s->nTri; j++) tri[j] = s->pos_of[t->tri[j]];
+    s->nG = t->nG; s->maxG = t->maxG; s->nR = t->nR; s->nC = t->nC;
+
+    s->d_nbrp = dupload(nbrp); s->d_jtype = dupload(jtype); s->d_cls = dupload(cls);
+    s->d_site_of = dupload(s->site_of); s->d_pos_of = dupload(s->pos_of);
+    s->d_pairs = dupload(pairs); s->d_tri = dupload(tri); s->d_mi = dupload(mi); s->d_mj = dupload(mj);
+    s->d_signS = dupload(signS);
+    if (s->prec == 64) { s->d_Jtab = dupload_real<double>(Jtab); s->d_clsS = dupload_real<double>(clsS); s->d_clsD = dupload_real<double>(clsD); }
+    else { s->d_Jtab = dupload_real<float>(Jtab); s->d_clsS = dupload_real<float>(clsS); s->d_clsD = dupload_real<float>(clsD); }
+    MCG_CUDA(cudaMalloc(&s->d_spin, (size_t)s->R * s->NC * N * s->real_size()));
+    s->d_scratch = dalloc<double>(3 * (size_t)N);
+    alloc_replica_state(s, cfg);
+    MCG_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    return sys.release();
+}
+
+static dim3 grid_for(int n, int R) { return dim3((unsigned)((n + 255) / 256), (unsigned)R, 1); }
+
+static void init_spins(mcg_system *s, double flunc) {
+    if (s->structured) { structured_init_spins(s, flunc); return; }
+    GenArgs a = gen_args(s);
+    dispatch(s, [&]<int NC, typename real, bool FJ>() {
+        k_init_generic<NC, real><<<grid_for(s->N, s->R), 256, 0, s->stream>>>(a, s->d_signS, flunc);
+    });
+    MCG_CUDA(cudaGetLastError());
+}
+
+static void set_spins(mcg_system *s, int r, const double *spins) {
+    MCG_REQUIRE(r >= 0 && r < s->R && spins, "bad replica index or NULL spins");
+    if (s->structured) { structured_set_spins(s, r, spins); return; }
+    size_t n = (size_t)s->N * (s->NC == 1 ? 1 : 3);
+    MCG_CUDA(cudaMemcpyAsync(s->d_scratch, spins, n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    GenArgs a = gen_args(s);
+    dispatch(s, [&]<int NC, typename real, bool FJ>() {
+        k_scatter_frame<NC, real><<<grid_for(s->N, 1), 256, 0, s->stream>>>(a, r, s->d_scratch);
+    });
+    MCG_CUDA(cudaGetLastError());
+    MCG_CUDA(cudaStreamSynchronize(s->stream));
+}
+
+static void get_spins(mcg_system *s, int r, double *spins) {
+    MCG_REQUIRE(r >= 0 && r < s->R && spins, "bad replica index or NULL spins");
+    if (s->structured) { structured_get_spins(s, r, spins); return; }
+    size_t n = (size_t)s->N * (s->NC == 1 ? 1 : 3);
+    GenArgs a = gen_args(s);
+    dispatch(s, [&]<int NC, typename real, bool FJ>() {
+        k_gather_frame<NC, real><<<grid_for(s->N, 1), 256, 0, s->stream>>>(a, r, s->d_scratch);
+    });
+    MCG_CUDA(cudaGetLastError());
+    MCG_CUDA(cudaMemcpyAsync(spins, s->d_scratch, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    MCG_CUDA(cudaStreamSynchronize(s->stream));
+}
+
+// raw per-sweep sums of the resident configuration (all replicas) into d_sums
+static void launch_measure_sums(mcg_system *s, int siteRep, double *eb, double *eo) {
+    if (s->structured) { structured_measure_sums(s); return; }
+    GenArgs a = gen_args(s);
+    dispatch(s, [&]<int NC, typename real, bool FJ>() {
+        k_measure_generic<NC, real, FJ><<<grid_for(s->N, s->R), 256, 0, s->stream>>>(a, s->d_mi, s->d_mj, s->d_sums, siteRep, eb, eo);
+        k_pairs_generic<NC, real><<<grid_for(s->nLat, s->R), 256, 0, s->stream>>>(s->N, s->nLat, s->d_pairs, s->d_spin, s->d_sums);
+        if constexpr (NC == 3)
+            if (s->nTri > 0) k_topo_generic<real><<<grid_for(s->nTri, s->R), 256, 0, s->stream>>>(a, s->nTri, s->d_tri, s->d_sums);
+    });
+    MCG_CUDA(cudaGetLastError());
+}
+
+static void measure(mcg_system *s) {
+    launch_measure_sums(s, -1, nullptr, nullptr);
+    k_finalize_sweep<<<(s->R + 63) / 64, 64, 0, s->stream>>>(s->model, s->R, s->N, s->nLat, s->d_sums, s->d_acc);
+    MCG_CUDA(cudaGetLastError());
+}
+
+static void energy(mcg_system *s, int r, double *Etot, double *eb, double *eo) {
+    MCG_REQUIRE(r >= 0 && r < s->R, "bad replica index");
+    MCG_REQUIRE((eb == nullptr) == (eo == nullptr), "per-site energy arrays must both be given or both be NULL");
+    MCG_REQUIRE(!(s->structured && eb), "per-site energies are only available on table-built systems");
+    MCG_CUDA(cudaMemsetAsync(s->d_sums, 0, sizeof(double) * s->R * NSUM, s->stream));
+    double *deb = eb ? s->d_scratch : nullptr, *deo = eb ? s->d_scratch + s->N : nullptr;
+    launch_measure_sums(s, r, deb, deo);
+    double E = 0;
+    MCG_CUDA(cudaMemcpyAsync(&E, s->d_sums + (size_t)r * NSUM + SUM_E, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    if (eb) {
+        MCG_CUDA(cudaMemcpyAsync(eb, deb, sizeof(double) * s->N, cudaMemcpyDeviceToHost, s->stream));
+        MCG_CUDA(cudaMemcpyAsync(eo, deo, sizeof(double) * s->N, cudaMemcpyDeviceToHost, s->stream));
+    }
+    MCG_CUDA(cudaMemsetAsync(s->d_sums, 0, sizeof(double) * s->R * NSUM, s->stream));
+    MCG_CUDA(cudaStreamSynchronize(s->stream));
+    if (Etot) *Etot = E;
+}
+
+static void metropolis_sweeps(mcg_system *s, int64_t n, double pAtt) {
+    MCG_REQUIRE(n >= 0, "negative sweep count");
+    MCG_REQUIRE(pAtt > 0.0 && pAtt <= 1.0, "pAttempt must be in (0,1]");
+    if (s->structured) { structured_sweeps(s, n, pAtt, false); return; }
+    GenArgs a = gen_args(s);
+    for (int64_t it = 0; it < n; it++) {
+        for (int c = 0; c < s->C; c++) {
+            int cb = s->colourStart[c], ce = s->colourStart[c + 1];
+            if (ce == cb) continue;
+            dispatch(s, [&]<int NC, typename real, bool FJ>() {
+                k_metro_generic<NC, real, FJ><<<grid_for(ce - cb, s->R), 256, 0, s->stream>>>(a, cb, ce, s->sweepCtr, (real)pAtt);
+            });
+        }
+        s->sweepCtr++;
+    }
+    MCG_CUDA(cudaGetLastError());
+}
+
+static void wolff_steps(mcg_system *s, int64_t n) {
+    MCG_REQUIRE(n >= 0, "negative step count");
+    MCG_REQUIRE(!s->structured, "Wolff updates need a table-built system in this version");
+    if (!s->d_parent) {
+        s->d_parent = dalloc<int32_t>((size_t)s->R * s->N);
+        MCG_CUDA(cudaMalloc(&s->d_proj, (size_t)s->R * s->N * s->real_size()));
+        s->d_wres = dalloc<double>(2 * (size_t)s->R);
+    }
+    GenArgs a = gen_args(s);
+    WolffArgs w;
+    w.parent = s->d_parent; w.proj = s->d_proj; w.wres = s->d_wres; w.pos_of = s->d_pos_of;
+    dim3 g = grid_for(s->N, s->R);
+    for (int64_t it = 0; it < n; it++) {
+        w.step = s->wolffCtr++;
+        dispatch(s, [&]<int NC, typename real, bool FJ>() {
+            k_wolff_init<NC, real><<<g, 256, 0, s->stream>>>(a, w);
+            k_wolff_bonds<NC, real, FJ><<<g, 256, 0, s->stream>>>(a, w);
+            k_wolff_flatten<<<g, 256, 0, s->stream>>>(s->N, s->d_parent);
+            k_wolff_residual<NC, real, FJ><<<g, 256, 0, s->stream>>>(a, w);
+            k_wolff_flip<NC, real><<<g, 256, 0, s->stream>>>(a, w);
+        });
+    }
+    MCG_CUDA(cudaGetLastError());
+}
+
+static void capture_frame(mcg_system *s, int r, double *dst) {
+    // synchronous: frames are rare (spinFrame per run) and the staging buffer is reused
+    get_spins(s, r, dst);
+}
+
+static void run(mcg_system *s, int algorithm, int64_t nthermal, int64_t nsweep, int64_t ninterval, int spinFrame, double *frames) {
+    MCG_REQUIRE(algorithm == MCG_METROPOLIS || algorithm == MCG_WOLFF, "algorithm must be 0 (Metropolis) or 1 (Wolff)");
+    MCG_REQUIRE(nthermal >= 0 && nsweep >= 1 && ninterval >= 0, "need nthermal>=0, nsweep>=1, ninterval>=0");
+    MCG_REQUIRE(spinFrame >= 0 && (spinFrame == 0 || frames), "frames buffer is NULL");
+    int64_t nsub = 1;
+    double pAtt = 1.0;
+    if (algorithm == MCG_METROPOLIS) {
+        if (ninterval >= s->N) nsub = (ninterval + s->N / 2) / s->N;
+        else if (ninterval > 0) pAtt = (double)ninterval / (double)s->N;
+        else nsub = 0;
+    }
+    auto updates = [&](int64_t intervals) {
+        if (algorithm == MCG_METROPOLIS) { if (nsub > 0) metropolis_sweeps(s, intervals * nsub, pAtt); }
+        else wolff_steps(s, intervals * ninterval);
+    };
+    updates(nthermal);
+    int64_t per = nsweep, iFrame = 0;
+    if (spinFrame > 0) per = std::max<int64_t>(1, nsweep / spinFrame);
+    size_t fsz = (size_t)s->N * (s->NC == 1 ? 1 : 3);
+    for (int64_t i = 0; i < nsweep; i++) {
+        updates(1);
+        if (spinFrame > 0 && i % per == 0 && iFrame < spinFrame) {   // heisenbergLib.c:664-675, capped
+            for (int r = 0; r < s->R; r++) capture_frame(s, r, frames + ((size_t)r * spinFrame + iFrame) * fsz);
+            iFrame++;
+        }
+        measure(s);
+        if ((i & 255) == 255) MCG_CUDA(cudaStreamSynchronize(s->stream));   // bound the launch queue
+    }
+    MCG_CUDA(cudaStreamSynchronize(s->stream));
+}
+
+static void results(mcg_system *s, int r, double *out, double *groupOut) {
+    MCG_REQUIRE(r >= 0 && r < s->R && out, "bad replica index or NULL out");
+    double A[NACC];
+    MCG_CUDA(cudaStreamSynchronize(s->stream));
+    MCG_CUDA(cudaMemcpy(A, s->d_acc + (size_t)r * NACC, sizeof(A), cudaMemcpyDeviceToHost));
+    double ns = A[ACC_NMEAS];
+    if (!(ns > 0)) throw Error(MCG_ERR_STATE, "no measurement has been accumulated yet");
+    double U4 = (A[ACC_M2] / ns) * (A[ACC_M2] / ns) / (A[ACC_M4] / ns);                     // heisenbergLib.c:833
+    double autoCorr = A[ACC_MDOTM] / ns - (A[ACC_MTOT] / ns) * (A[ACC_MTOT] / ns);          // :834
+    if (s->model == MCG_ISING) {   // isingLib.c:435-446
+        out[0] = A[ACC_SI] / ns; out[1] = A[ACC_SJ] / ns; out[2] = A[ACC_SIJ] / ns; out[3] = autoCorr;
+        out[4] = A[ACC_E] / ns; out[5] = A[ACC_E2] / ns; out[6] = A[ACC_ER] / ns; out[7] = A[ACC_E2R] / ns;
+        out[8] = U4; out[9] = A[ACC_STOT] / ns / s->nLat;
+        return;
+    }
+    for (int c = 0; c < 3; c++) { out[c] = A[ACC_SI + c] / ns; out[3 + c] = A[ACC_SJ + c] / ns; }
+    out[6] = A[ACC_SIJ] / ns; out[7] = autoCorr; out[8] = A[ACC_E] / ns; out[9] = A[ACC_E2] / ns; out[10] = U4;
+    for (int c = 0; c < 3; c++) { out[11 + c] = A[ACC_SIR + c] / ns; out[14 + c] = A[ACC_SJR + c] / ns; }
+    out[17] = A[ACC_SIJR] / ns; out[18] = A[ACC_ER] / ns; out[19] = A[ACC_E2R] / ns;
+    out[20] = A[ACC_SIZ] / ns; out[21] = A[ACC_SJZ] / ns; out[22] = A[ACC_STZ] / ns;
+    out[23] = A[ACC_SIH] / ns; out[24] = A[ACC_SJH] / ns; out[25] = A[ACC_STH] / ns;
+    out[26] = A[ACC_Q] / ns;
+    if (groupOut) for (int i = 0; i < (s->nG + 2) * (s->nG + 1); i++) groupOut[i] = 0.0;
+}
+
+}  // namespace mcg
+
+mcg_system::~mcg_system() {
+    cudaSetDevice(device);
+    void *bufs[] = {d_nbrp, d_site_of, d_pos_of, d_pairs, d_tri, d_mi, d_mj, d_jtype, d_cls, d_Jtab, d_clsS, d_clsD, d_spin,
+                    d_signS, d_beta, d_field, d_sums, d_acc, d_cnt, d_scratch, d_parent, d_proj, d_wres};
+    for (void *b : bufs) if (b) cudaFree(b);
+    if (st) mcg::structured_destroy(st);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace mcg;
+
+extern "C" {
+
+MCG_API const char *mcg_last_error(void) { return g_last_error.c_str(); }
+MCG_API int mcg_version(void) { return 100; }
+
+MCG_API int mcg_device_count(int *count) {
+    return guarded([&] {
+        MCG_REQUIRE(count, "count is NULL");
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess) throw Error(MCG_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+        *count = n;
+    });
+}
+
+MCG_API int mcg_create_tables(const mcg_tables *t, const mcg_config *cfg, mcg_system **out) {
+    return guarded([&] {
+        MCG_REQUIRE(out, "out is NULL");
+        *out = create_from_tables(t, cfg);
+    });
+}
+
+MCG_API int mcg_create_lattice(const mcg_lattice_desc *d, const mcg_config *cfg, mcg_system **out) {
+    return guarded([&] {
+        MCG_REQUIRE(out, "out is NULL");
+        MCG_REQUIRE(d && cfg, "descriptor/config is NULL");
+        MCG_REQUIRE(cfg->precision == 32 || cfg->precision == 64, "precision must be 32 or 64");
+        MCG_REQUIRE(cfg->nReplica >= 1, "nReplica must be >= 1");
+        std::unique_ptr<mcg_system> sys(new mcg_system());
+        select_device(cfg, sys.get());
+        sys->prec = cfg->precision; sys->R = cfg->nReplica; sys->seed = cfg->seed; sys->replica0 = (uint32_t)cfg->replica_offset;
+        structured_create(sys.get(), d);
+        alloc_replica_state(sys.get(), cfg);
+        MCG_CUDA(cudaStreamCreateWithFlags(&sys->stream, cudaStreamNonBlocking));
+        *out = sys.release();
+    });
+}
+
+MCG_API int mcg_destroy(mcg_system *sys) {
+    return guarded([&] { delete sys; });
+}
+
+#define SYS_GUARD(body)                         \
+    return guarded([&] {                        \
+        MCG_REQUIRE(sys, "system is NULL");     \
+        MCG_CUDA(cudaSetDevice(sys->device));   \
+        body;                                   \
+    })
+
+MCG_API int mcg_num_colours(const mcg_system *sys, int *ncolours) {
+    return guarded([&] { MCG_REQUIRE(sys && ncolours, "NULL argument"); *ncolours = sys->C; });
+}
+
+MCG_API int mcg_colour_order(const mcg_system *sys, int32_t *order) {
+    return guarded([&] {
+        MCG_REQUIRE(sys && order, "NULL argument");
+        if (sys->structured) structured_colour_order(sys, order);
+        else std::copy(sys->site_of.begin(), sys->site_of.end(), order);
+    });
+}
+
+MCG_API int mcg_set_params(mcg_system *sys, const double *beta, const double *field) {
+    SYS_GUARD({
+        if (beta) sys->beta_host.assign(beta, beta + sys->R);
+        if (field) sys->field_host.assign(field, field + sys->R);
+        MCG_CUDA(cudaMemcpyAsync(sys->d_beta, sys->beta_host.data(), sizeof(double) * sys->R, cudaMemcpyHostToDevice, sys->stream));
+        MCG_CUDA(cudaMemcpyAsync(sys->d_field, sys->field_host.data(), sizeof(double) * sys->R, cudaMemcpyHostToDevice, sys->stream));
+        MCG_CUDA(cudaStreamSynchronize(sys->stream));
+    });
+}
+
+MCG_API int mcg_init_spins(mcg_system *sys, double flunc) { SYS_GUARD(init_spins(sys, flunc)); }
+MCG_API int mcg_set_spins(mcg_system *sys, int replica, const double *spins) { SYS_GUARD(set_spins(sys, replica, spins)); }
+MCG_API int mcg_get_spins(mcg_system *sys, int replica, double *spins) { SYS_GUARD(get_spins(sys, replica, spins)); }
+MCG_API int mcg_energy(mcg_system *sys, int replica, double *Etot, double *eb, double *eo) { SYS_GUARD(energy(sys, replica, Etot, eb, eo)); }
+
+MCG_API int mcg_metropolis_sweeps(mcg_system *sys, int64_t nsweeps, double pAttempt) {
+    SYS_GUARD({ metropolis_sweeps(sys, nsweeps, pAttempt); MCG_CUDA(cudaStreamSynchronize(sys->stream)); });
+}
+MCG_API int mcg_wolff_steps(mcg_system *sys, int64_t nsteps) {
+    SYS_GUARD({ wolff_steps(sys, nsteps); MCG_CUDA(cudaStreamSynchronize(sys->stream)); });
+}
+MCG_API int mcg_measure(mcg_system *sys) {
+    SYS_GUARD({ measure(sys); MCG_CUDA(cudaStreamSynchronize(sys->stream)); });
+}
+MCG_API int mcg_reset_measurements(mcg_system *sys) {
+    SYS_GUARD({
+        MCG_CUDA(cudaMemsetAsync(sys->d_acc, 0, sizeof(double) * sys->R * NACC, sys->stream));
+        MCG_CUDA(cudaMemsetAsync(sys->d_sums, 0, sizeof(double) * sys->R * NSUM, sys->stream));
+        MCG_CUDA(cudaMemsetAsync(sys->d_cnt, 0, sizeof(unsigned long long) * sys->R * NCNT, sys->stream));
+        MCG_CUDA(cudaStreamSynchronize(sys->stream));
+    });
+}
+MCG_API int mcg_results(mcg_system *sys, int replica, double *out, double *groupOut) { SYS_GUARD(results(sys, replica, out, groupOut)); }
+
+MCG_API int mcg_counters(mcg_system *sys, int replica, int64_t *attempts, int64_t *accepted, int64_t *cluster_sites) {
+    SYS_GUARD({
+        MCG_REQUIRE(replica >= 0 && replica < sys->R, "bad replica index");
+        unsigned long long c[NCNT];
+        MCG_CUDA(cudaStreamSynchronize(sys->stream));
+        MCG_CUDA(cudaMemcpy(c, sys->d_cnt + (size_t)replica * NCNT, sizeof(c), cudaMemcpyDeviceToHost));
+        if (attempts) *attempts = (int64_t)c[CNT_ATTEMPT];
+        if (accepted) *accepted = (int64_t)c[CNT_ACCEPT];
+        if (cluster_sites) *cluster_sites = (int64_t)c[CNT_CLUSTER];
+    });
+}
+
+MCG_API int mcg_run(mcg_system *sys, int algorithm, int64_t nthermal, int64_t nsweep, int64_t ninterval, int spinFrame, double *frames) {
+    SYS_GUARD(run(sys, algorithm, nthermal, nsweep, ninterval, spinFrame, frames));
+}
+
+static int run_legacy(const mcg_tables *t, int model_expected_ising, int algorithm, int64_t nthermal, int64_t nsweep,
+                      int64_t ninterval, double flunc, double h, int spinFrame, uint64_t seed, int precision, double *out,
+                      double *frames, double *groupOut) {
+    return guarded([&] {
+        MCG_REQUIRE(t && out, "NULL argument");
+        MCG_REQUIRE((t->model == MCG_ISING) == (model_expected_ising != 0), "wrong entry point for this model");
+        mcg_config cfg;
+        std::memset(&cfg, 0, sizeof cfg);
+        double beta = 1.0;
+        cfg.precision = precision; cfg.nReplica = 1; cfg.beta = &beta; cfg.field = &h; cfg.seed = seed; cfg.device = -1;
+        std::unique_ptr<mcg_system> sys(create_from_tables(t, &cfg));
+        init_spins(sys.get(), flunc);
+        run(sys.get(), algorithm, nthermal, nsweep, ninterval, spinFrame, frames);
+        results(sys.get(), 0, out, groupOut);
+    });
+}
+
+MCG_API int mcg_run_on(const mcg_tables *t, int algorithm, int64_t nthermal, int64_t nsweep, int64_t ninterval, double flunc, double h,
+               int spinFrame, uint64_t seed, int precision, double out27[27], double *frames, double *groupOut) {
+    return run_legacy(t, 0, algorithm, nthermal, nsweep, ninterval, flunc, h, spinFrame, seed, precision, out27, frames, groupOut);
+}
+
+MCG_API int mcg_run_ising(const mcg_tables *t, int algorithm, int64_t nthermal, int64_t nsweep, int64_t ninterval, double h, int spinFrame,
+                  uint64_t seed, int precision, double out10[10], double *frames) {
+    return run_legacy(t, 1, algorithm, nthermal, nsweep, ninterval, 0.0, h, spinFrame, seed, precision, out10, frames, nullptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,15 @@
+// Structured (descriptor-driven) path: entry points used by engine.cu; implemented in structured.cu.
+#pragma once
+#include "system.hpp"
+
+namespace mcg {
+void structured_create(mcg_system *s, const mcg_lattice_desc *d);
+void structured_destroy(StructuredSystem *st);
+void structured_init_spins(mcg_system *s, double flunc);
+void structured_set_spins(mcg_system *s, int r, const double *spins);
+void structured_get_spins(mcg_system *s, int r, double *spins);
+void structured_measure_sums(mcg_system *s);
+// n colour sweeps; fusedMeasure: the last sweep also produces the raw measurement sums in d_sums
+void structured_sweeps(mcg_system *s, int64_t n, double pAtt, bool fusedMeasure);
+void structured_colour_order(const mcg_system *s, int32_t *order);
+}  // namespace mcg

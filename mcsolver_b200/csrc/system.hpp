@@ -1,0 +1,71 @@
+// Host-side description of a resident simulation (tables + replica states in HBM).
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <vector>
+
+#include "common.cuh"
+
+namespace mcg {
+
+// POD handed to the generic (table-driven) kernels by value.
+struct GenArgs {
+    int N, maxL, R;
+    int nJ, ncls;
+    const int32_t *nbrp;        // [maxL][N] neighbour storage positions (pad: self)
+    const uint16_t *jtype;      // [maxL][N] index into Jtab (0 = zero tensor)
+    const void *Jtab;           // [nJ][9] (Ising [nJ][1]) real
+    const uint16_t *cls;        // [N] site class
+    const void *clsS;           // [ncls] |S| real
+    const void *clsD;           // [ncls][3] real
+    const int32_t *site_of;     // [N] storage position -> reference site id
+    void *spin;                 // [R][NC][N] real
+    const double *beta;         // [R]
+    const double *field;        // [R]
+    unsigned long long *cnt;    // [R][NCNT]
+    RngKey key;
+    uint32_t replica0;
+};
+
+struct StructuredSystem;  // structured.cu
+
+}  // namespace mcg
+
+struct mcg_system {
+    int model = 0, NC = 0, prec = 64, R = 1;
+    int N = 0, maxL = 0;
+    bool fullJ = false;
+    bool structured = false;
+    int device = 0;
+    uint64_t seed = 1;
+    uint32_t replica0 = 0;
+    uint64_t sweepCtr = 0;       // Metropolis sweep counter (Philox counter word)
+    uint64_t wolffCtr = 0;       // Wolff step counter
+    // colouring
+    int C = 0;
+    std::vector<int> colourStart;        // [C+1] in storage positions
+    std::vector<int32_t> site_of, pos_of;  // permutation
+    std::vector<double> S_host;          // [N] signed S in reference order
+    // measurement tables
+    int nLat = 0, nTri = 0, nG = 0, maxG = 0, nR = 0, nC = 0;
+    bool selfPairs = false;
+    // device buffers (generic path)
+    int32_t *d_nbrp = nullptr, *d_site_of = nullptr, *d_pos_of = nullptr, *d_pairs = nullptr, *d_tri = nullptr;
+    int32_t *d_mi = nullptr, *d_mj = nullptr;
+    uint16_t *d_jtype = nullptr, *d_cls = nullptr;
+    void *d_Jtab = nullptr, *d_clsS = nullptr, *d_clsD = nullptr, *d_spin = nullptr;
+    double *d_signS = nullptr;           // [N] signed S (storage order) for init
+    int nJ = 0, ncls = 0;
+    double *d_beta = nullptr, *d_field = nullptr, *d_sums = nullptr, *d_acc = nullptr;
+    unsigned long long *d_cnt = nullptr;
+    double *d_scratch = nullptr;         // [2N] per-site energies / frame staging (3N)
+    // wolff
+    int32_t *d_parent = nullptr;         // [R][N]
+    void *d_proj = nullptr;              // [R][N] real
+    double *d_wres = nullptr;            // [R][2] residual, cluster size
+    std::vector<double> beta_host, field_host;
+    cudaStream_t stream = nullptr;
+    mcg::StructuredSystem *st = nullptr;   // structured (descriptor) path state, owned
+    size_t real_size() const { return prec == 32 ? 4 : 8; }
+    ~mcg_system();
+};
