@@ -59,7 +59,7 @@ def make_tables():
              ("cri3", (4, 4, 1), 35.0, 3, 0.0), ("cri3", (2, 2, 1), 35.0, 3, 0.0), ("cri3", (3, 3, 1), 35.0, 3, 0.0),
              ("square", (6, 4, 1), 0.9, 2, 0.0), ("square", (2, 2, 1), 2.2, 1, 0.1), ("square", (1, 4, 1), 2.2, 1, 0.1),
              ("square", (5, 3, 1), 2.2, 1, 0.0), ("cubic", (4, 4, 4), 1.4, 3, 0.0), ("cubic", (2, 4, 6), 4.4, 1, 0.0),
-             ("cubic", (3, 3, 3), 1.4, 3, 0.0), ("aniso", (4, 4, 2), 0.7, 3, 0.3), ("aniso", (3, 2, 1), 0.7, 2, 0.3)]
+             ("cubic", (3, 3, 3), 1.4, 3, 0.0), ("aniso", (4, 4, 2), 0.7, 3, 0.3), ("aniso", (3, 4, 1), 0.7, 2, 0.3)]
     out = []
     for name, L, T, model, h in cases:
         a = _ref_args(spec_of(name, L), T, model, h=h)
