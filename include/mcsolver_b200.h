@@ -137,6 +137,10 @@ MCG_API int mcg_energy(mcg_system *sys, int replica, double *Etot, double *ebond
 /* nsweeps colour-class Metropolis sweeps (each site attempted once per sweep with probability
  * pAttempt); one attempt = localUpdate (heisenbergLib.c:441-473 / xyLib.c:382-409 / isingLib.c:238-254) */
 MCG_API int mcg_metropolis_sweeps(mcg_system *sys, int64_t nsweeps, double pAttempt);
+/* Same as mcg_metropolis_sweeps, bracketed by CUDA events on the stream the kernels are launched on;
+ * with_measure != 0 also produces and accumulates the per-sweep measurements after every sweep
+ * (fused into the colour passes on structured systems).  elapsed_ms = device time of the region. */
+MCG_API int mcg_timed_sweeps(mcg_system *sys, int64_t nsweeps, double pAttempt, int with_measure, double *elapsed_ms);
 /* nsteps Wolff single-cluster updates (blockUpdate) by bond activation + union-find labelling */
 MCG_API int mcg_wolff_steps(mcg_system *sys, int64_t nsteps);
 

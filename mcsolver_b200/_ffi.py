@@ -57,6 +57,7 @@ SIGNATURES = {
     "mcg_get_spins": (_i, [_vp, _i, _vp]),
     "mcg_energy": (_i, [_vp, _i, _vp, _vp, _vp]),
     "mcg_metropolis_sweeps": (_i, [_vp, _i64, _d]),
+    "mcg_timed_sweeps": (_i, [_vp, _i64, _d, _i, _vp]),
     "mcg_wolff_steps": (_i, [_vp, _i64]),
     "mcg_measure": (_i, [_vp]),
     "mcg_reset_measurements": (_i, [_vp]),

@@ -135,6 +135,15 @@ __device__ __forceinline__ void add_field(real (&H)[3], const real *__restrict__
     }
 }
 
+// on-site energy  sum_a D_a s_a^2 - h s_axis   (getOnsiteEnergy heisenbergLib.c:249-253, xyLib.c:200-204)
+template <int NC, typename real>
+__device__ __forceinline__ real onsite_energy(const real (&s)[3], const real *__restrict__ D, real beta, real hf) {
+    if (NC == 1) return -hf * s[0];
+    real e = D[0] * s[0] * s[0] + D[1] * s[1] * s[1];
+    if (NC == 3) e += D[2] * s[2] * s[2];
+    return beta * e - hf * (NC == 3 ? s[2] : s[0]);
+}
+
 // n.J.n for the Wolff bond weight (heisenbergLib.c:355: diagonalDot(ref,ref,J))
 template <int NC, typename real, bool FULLJ>
 __device__ __forceinline__ real quad_form(const real *__restrict__ J, const real (&a)[3], const real (&b)[3]) {

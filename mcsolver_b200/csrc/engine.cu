@@ -386,17 +386,23 @@ static void run(mcg_system *s, int algorithm, int64_t nthermal, int64_t nsweep, 
         if (algorithm == MCG_METROPOLIS) { if (nsub > 0) metropolis_sweeps(s, intervals * nsub, pAtt); }
         else wolff_steps(s, intervals * ninterval);
     };
+    // structured Metropolis: the measurement sums are produced by the last sweep of the interval itself
+    const bool fused = s->structured && algorithm == MCG_METROPOLIS && nsub > 0;
     updates(nthermal);
     int64_t per = nsweep, iFrame = 0;
     if (spinFrame > 0) per = std::max<int64_t>(1, nsweep / spinFrame);
     size_t fsz = (size_t)s->N * (s->NC == 1 ? 1 : 3);
     for (int64_t i = 0; i < nsweep; i++) {
-        updates(1);
+        if (fused) structured_sweeps(s, nsub, pAtt, true);
+        else updates(1);
         if (spinFrame > 0 && i % per == 0 && iFrame < spinFrame) {   // heisenbergLib.c:664-675, capped
             for (int r = 0; r < s->R; r++) capture_frame(s, r, frames + ((size_t)r * spinFrame + iFrame) * fsz);
             iFrame++;
         }
-        measure(s);
+        if (fused) {
+            k_finalize_sweep<<<(s->R + 63) / 64, 64, 0, s->stream>>>(s->model, s->R, s->N, s->nLat, s->d_sums, s->d_acc);
+            MCG_CUDA(cudaGetLastError());
+        } else measure(s);
         if ((i & 255) == 255) MCG_CUDA(cudaStreamSynchronize(s->stream));   // bound the launch queue
     }
     MCG_CUDA(cudaStreamSynchronize(s->stream));
@@ -485,11 +491,11 @@ MCG_API int mcg_destroy(mcg_system *sys) {
     return guarded([&] { delete sys; });
 }
 
-#define SYS_GUARD(body)                         \
+#define SYS_GUARD(...)                          \
     return guarded([&] {                        \
         MCG_REQUIRE(sys, "system is NULL");     \
         MCG_CUDA(cudaSetDevice(sys->device));   \
-        body;                                   \
+        __VA_ARGS__;                            \
     })
 
 MCG_API int mcg_num_colours(const mcg_system *sys, int *ncolours) {
@@ -521,6 +527,35 @@ MCG_API int mcg_energy(mcg_system *sys, int replica, double *Etot, double *eb, d
 
 MCG_API int mcg_metropolis_sweeps(mcg_system *sys, int64_t nsweeps, double pAttempt) {
     SYS_GUARD({ metropolis_sweeps(sys, nsweeps, pAttempt); MCG_CUDA(cudaStreamSynchronize(sys->stream)); });
+}
+MCG_API int mcg_timed_sweeps(mcg_system *sys, int64_t nsweeps, double pAttempt, int with_measure, double *elapsed_ms) {
+    SYS_GUARD({
+        MCG_REQUIRE(elapsed_ms, "elapsed_ms is NULL");
+        cudaEvent_t e0, e1;
+        MCG_CUDA(cudaEventCreate(&e0));
+        MCG_CUDA(cudaEventCreate(&e1));
+        MCG_CUDA(cudaStreamSynchronize(sys->stream));
+        MCG_CUDA(cudaEventRecord(e0, sys->stream));
+        if (!with_measure) metropolis_sweeps(sys, nsweeps, pAttempt);
+        else
+            for (int64_t i = 0; i < nsweeps; i++) {
+                if (sys->structured) {
+                    structured_sweeps(sys, 1, pAttempt, true);
+                    k_finalize_sweep<<<(sys->R + 63) / 64, 64, 0, sys->stream>>>(sys->model, sys->R, sys->N, sys->nLat, sys->d_sums, sys->d_acc);
+                } else {
+                    metropolis_sweeps(sys, 1, pAttempt);
+                    measure(sys);
+                }
+            }
+        MCG_CUDA(cudaEventRecord(e1, sys->stream));
+        MCG_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        MCG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        MCG_CUDA(cudaGetLastError());
+        *elapsed_ms = ms;
+    });
 }
 MCG_API int mcg_wolff_steps(mcg_system *sys, int64_t nsteps) {
     SYS_GUARD({ wolff_steps(sys, nsteps); MCG_CUDA(cudaStreamSynchronize(sys->stream)); });

@@ -39,15 +39,6 @@ __device__ __forceinline__ void local_field(const GenArgs &a, const real *__rest
     }
 }
 
-// on-site energy  sum_a D_a s_a^2 - h s_axis   (getOnsiteEnergy heisenbergLib.c:249-253, xyLib.c:200-204)
-template <int NC, typename real>
-__device__ __forceinline__ real onsite_energy(const real (&s)[3], const real *__restrict__ D, real beta, real hf) {
-    if (NC == 1) return -hf * s[0];
-    real e = D[0] * s[0] * s[0] + D[1] * s[1] * s[1];
-    if (NC == 3) e += D[2] * s[2] * s[2];
-    return beta * e - hf * (NC == 3 ? s[2] : s[0]);
-}
-
 // ---------------------------------------------------------------------------------------------
 // one colour class of a Metropolis sweep
 // ---------------------------------------------------------------------------------------------

@@ -1,12 +1,740 @@
+// Structured path: translation-invariant lattices given as bond templates + supercell dims.
+//
+// What it replaces: the reference expands a parameter file into one Python object per orbital
+// (Lattice.py:155-284), flattens that into O(N*maxL*9) Python floats (mcMain.py:150-223) and the
+// C engine chases pointers through 264-byte AoS structs (heisenbergLib.c:129-151).  Here the
+// lattice stays a descriptor: the engine finds the smallest colouring period (px,py,pz) such that
+// colour(x,y,z,o) = f(x%px, y%py, z%pz, o) is a proper colouring of the bond graph, splits the
+// lattice into nclass = px*py*pz*norb sublattice "classes", and stores every class as a dense
+// [Xd][Yd][Zd] array (Xd=Lx/px ...), structure-of-arrays per spin component.  The neighbour of cell
+// (X,Y,Z) of class q through link k is cell (X+cX, Y+cY, Z+cZ) of class q'(q,k): indices are
+// computed, not stored; the per-class link table and exchange tensors live in shared memory.
+// One colour per launch; classes of a colour are interleaved in block order so that the L2 serves
+// the repeated neighbour reads and HBM traffic stays at (own read + own write + neighbour read).
+//
+// Per-sweep measurements (M, E) are fused into the colour passes: every site's final spin is known
+// when its own colour is processed, and a bond's final energy is known when its later-coloured end
+// is processed (both ends final), so  E = sum_i [ s'_i . H_i(lower colours) + onsite(s'_i) ].
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
 #include "structured.hpp"
+
 namespace mcg {
-struct StructuredSystem { int dummy; };
-void structured_create(mcg_system *, const mcg_lattice_desc *) { throw Error(MCG_ERR_ARG, "structured path not built yet"); }
-void structured_destroy(StructuredSystem *st) { delete st; }
-void structured_init_spins(mcg_system *, double) {}
-void structured_set_spins(mcg_system *, int, const double *) {}
-void structured_get_spins(mcg_system *, int, double *) {}
-void structured_measure_sums(mcg_system *) {}
-void structured_sweeps(mcg_system *, int64_t, double, bool) {}
-void structured_colour_order(const mcg_system *, int32_t *) {}
+
+constexpr int MAXLINK = 32;
+
+struct SLinkD {
+    int qn;          // neighbour class
+    int cX, cY;      // coarse offsets, already reduced to [0,Xd) / [0,Yd)
+    int cZ;          // coarse Z offset in (-Zd/2, Zd/2]
+    int low;         // neighbour class has a lower colour (its spins are final in this sweep)
+    int self;        // link to the site itself (supercell dimension 1)
+};
+struct SClassD {
+    int a, b, c, o, colour, nlink, lowmode, pad;
+    double S, D[3];
+};
+
+struct StructuredSystem {
+    int L[3], p[3], Xd, Yd, Zd, ncellc, nclass, norb, V;
+    int nrows;
+    bool hasSelf = false, selfPairs = false;
+    int pair_s, pair_t, pair_d[3];
+    int ncircuit = 0;
+    std::vector<int> circuits;           // [ncircuit][3][4] internal axes
+    std::vector<SClassD> classes;        // sorted by colour
+    std::vector<int> classOf;            // [(a*py+b)*pz+c)*norb+o] -> class index
+    std::vector<int> colourClassStart;   // [C+1]
+    SClassD *d_classes = nullptr;
+    SLinkD *d_links = nullptr;
+    void *d_J = nullptr;
+    int *d_classOf = nullptr, *d_circuits = nullptr;
+    double *d_classSums = nullptr;       // [R][nclass][4]
+    double *d_stage = nullptr;           // [3N] host<->device staging, allocated on demand
+};
+
+struct StructArgs {
+    int Xd, Yd, Zd, Zc, ncellc, nclass, nrows, N;
+    int px, py, pz, norb, Lx, Ly, Lz;
+    const SClassD *classes;
+    const SLinkD *links;
+    const void *J;
+    const int *classOf;
+    void *spin;
+    const double *beta, *field;
+    unsigned long long *cnt;
+    double *classSums;
+    RngKey key;
+    uint32_t replica0;
+};
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+template <typename real, int V> struct Vec;
+template <> struct Vec<float, 4> { typedef float4 type; };
+template <> struct Vec<float, 1> { typedef float type; };
+template <> struct Vec<double, 2> { typedef double2 type; };
+template <> struct Vec<double, 1> { typedef double type; };
+
+template <typename real, int V> __device__ __forceinline__ void vload(const real *__restrict__ p, real (&o)[V]) {
+    typedef typename Vec<real, V>::type VT;
+    VT v = *reinterpret_cast<const VT *>(p);
+    const real *e = reinterpret_cast<const real *>(&v);
+#pragma unroll
+    for (int i = 0; i < V; i++) o[i] = e[i];
+}
+template <typename real, int V> __device__ __forceinline__ void vstore(real *__restrict__ p, const real (&o)[V]) {
+    typedef typename Vec<real, V>::type VT;
+    VT v;
+    real *e = reinterpret_cast<real *>(&v);
+#pragma unroll
+    for (int i = 0; i < V; i++) e[i] = o[i];
+    *reinterpret_cast<VT *>(p) = v;
+}
+
+// V consecutive cells of a neighbour row, shifted by cZ cells with periodic wrap
+template <typename real, int V>
+__device__ __forceinline__ void load_shifted(const real *__restrict__ row, int Z0, int cZ, int Zd, real (&o)[V]) {
+    if (cZ == 0) {
+        vload<real, V>(row + Z0, o);
+    } else if (V > 1 && cZ == -1) {
+        real t[V];
+        vload<real, V>(row + Z0, t);
+        int zl = Z0 == 0 ? Zd - 1 : Z0 - 1;
+        o[0] = row[zl];
+#pragma unroll
+        for (int i = 1; i < V; i++) o[i] = t[i - 1];
+    } else if (V > 1 && cZ == 1) {
+        real t[V];
+        vload<real, V>(row + Z0, t);
+        int zr = Z0 + V >= Zd ? 0 : Z0 + V;
+#pragma unroll
+        for (int i = 0; i < V - 1; i++) o[i] = t[i + 1];
+        o[V - 1] = row[zr];
+    } else {
+#pragma unroll
+        for (int i = 0; i < V; i++) {
+            int z = Z0 + i + cZ;
+            if (z < 0) z += Zd;
+            if (z >= Zd) z -= Zd;
+            o[i] = row[z];
+        }
+    }
+}
+
+__device__ __forceinline__ int struct_pos(const StructArgs &a, int x, int y, int z, int o) {
+    int ca = x % a.px, cb = y % a.py, cc = z % a.pz;
+    int q = a.classOf[((ca * a.py + cb) * a.pz + cc) * a.norb + o];
+    return ((q * a.Xd + x / a.px) * a.Yd + y / a.py) * a.Zd + z / a.pz;
+}
+__device__ __forceinline__ int struct_site_id(const StructArgs &a, int p) {
+    int q = p / a.ncellc, cell = p - q * a.ncellc;
+    int Z = cell % a.Zd, Y = (cell / a.Zd) % a.Yd, X = cell / (a.Zd * a.Yd);
+    const SClassD &c = a.classes[q];
+    int x = X * a.px + c.a, y = Y * a.py + c.b, z = Z * a.pz + c.c;
+    return ((x * a.Ly + y) * a.Lz + z) * a.norb + c.o;
+}
+
+// MODE 0: update only   1: update + fused measurement   2: measurement only (no update)
+template <int NC, typename real, bool FULLJ, int MODE, int V>
+__global__ void __launch_bounds__(256) k_struct(StructArgs a, int q0, int nqc, int rowsPerBlock, int nrb, uint64_t sweep,
+                                                real pAtt) {
+    constexpr int JW = NC == 1 ? 1 : 9;
+    __shared__ SLinkD sl[MAXLINK];
+    __shared__ real sJ[MAXLINK * JW];
+    __shared__ SClassD sc;
+    __shared__ double red[4 * 32];
+    const int bid = blockIdx.x;
+    const int j = bid % nqc, tq = bid / nqc, rb = tq % nrb, r = tq / nrb;
+    const int q = q0 + j;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    if (tid == 0) sc = a.classes[q];
+    for (int i = tid; i < MAXLINK; i += blockDim.x * blockDim.y) sl[i] = a.links[q * MAXLINK + i];
+    for (int i = tid; i < MAXLINK * JW; i += blockDim.x * blockDim.y) sJ[i] = ((const real *)a.J)[(size_t)q * MAXLINK * JW + i];
+    __syncthreads();
+    const int nlink = sc.nlink, lowmode = sc.lowmode;
+    const real S = (real)fabs(sc.S);
+    const real D[3] = {(real)sc.D[0], (real)sc.D[1], (real)sc.D[2]};
+    const real beta = (real)a.beta[r], hf = (real)(a.beta[r] * a.field[r]);
+    real *sp = (real *)a.spin + (size_t)r * NC * a.N;
+    const int idStrideZ = a.pz * a.norb;
+    real accM[3] = {0, 0, 0}, accE = 0;
+    int natt = 0, nacc = 0;
+
+    const int rowEnd = min(a.nrows, (rb + 1) * rowsPerBlock);
+    for (int row = rb * rowsPerBlock + threadIdx.y; row < rowEnd; row += blockDim.y) {
+        const int X = row / a.Yd, Y = row - X * a.Yd;
+        const int rowBase = ((q * a.Xd + X) * a.Yd + Y) * a.Zd;
+        const int x = X * a.px + sc.a, y = Y * a.py + sc.b;
+        for (int zc = threadIdx.x; zc < a.Zc; zc += blockDim.x) {
+            const int Z0 = zc * V;
+            real s[3][V], H[3][V], Hl[3][V];
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int v = 0; v < V; v++) { s[c][v] = 0; H[c][v] = 0; Hl[c][v] = 0; }
+#pragma unroll
+            for (int c = 0; c < NC; c++) vload<real, V>(sp + (size_t)c * a.N + rowBase + Z0, s[c]);
+            for (int k = 0; k < nlink; k++) {
+                const SLinkD L = sl[k];
+                int Xn = X + L.cX; if (Xn >= a.Xd) Xn -= a.Xd;
+                int Yn = Y + L.cY; if (Yn >= a.Yd) Yn -= a.Yd;
+                const int nb = ((L.qn * a.Xd + Xn) * a.Yd + Yn) * a.Zd;
+                real t[3][V];
+#pragma unroll
+                for (int c = 0; c < NC; c++) load_shifted<real, V>(sp + (size_t)c * a.N + nb, Z0, L.cZ, a.Zd, t[c]);
+                const real *Jk = sJ + k * JW;
+                const bool lowk = MODE == 1 && lowmode == 2 && L.low;
+#pragma unroll
+                for (int v = 0; v < V; v++) {
+                    real tv[3] = {t[0][v], NC >= 2 ? t[1][v] : real(0), NC == 3 ? t[2][v] : real(0)};
+                    real Hv[3] = {0, 0, 0};
+                    add_field<NC, real, FULLJ>(Hv, Jk, tv);
+                    H[0][v] += Hv[0]; H[1][v] += Hv[1]; H[2][v] += Hv[2];
+                    if (lowk) { Hl[0][v] += Hv[0]; Hl[1][v] += Hv[1]; Hl[2][v] += Hv[2]; }
+                }
+            }
+            const uint32_t id0 = (uint32_t)(((x * a.Ly + y) * a.Lz + (Z0 * a.pz + sc.c)) * a.norb + sc.o);
+#pragma unroll
+            for (int v = 0; v < V; v++) {
+                real sv[3] = {s[0][v], s[1][v], s[2][v]};
+                const real Hv[3] = {H[0][v], H[1][v], H[2][v]};
+                if (MODE != 2) {
+                    uint32_t w[4];
+                    rng4(a.key, a.replica0 + r, STREAM_METRO, 0, sweep, id0 + (uint32_t)(v * idStrideZ), w);
+                    if (!(pAtt < real(1)) || u01<real>(w[3]) < pAtt) {
+                        natt++;
+                        if (NC == 1) {
+                            real corr = real(2) * (beta * sv[0] * Hv[0] - hf * sv[0]);      // isingLib.c:242
+                            if (corr >= real(0) || r_exp<real>(corr) > u01<real>(w[2])) { sv[0] = -sv[0]; nacc++; }
+                        } else {
+                            real n[3];
+                            random_dir<NC, real>(w[0], w[1], n);
+                            real s1n = real(-2) * (sv[0] * n[0] + sv[1] * n[1] + (NC == 3 ? sv[2] * n[2] : real(0)));
+                            real tr[3] = {n[0] * s1n, n[1] * s1n, NC == 3 ? n[2] * s1n : real(0)};
+                            real dE = tr[0] * Hv[0] + tr[1] * Hv[1] + (NC == 3 ? tr[2] * Hv[2] : real(0));
+                            real t1[3] = {sv[0] + tr[0], sv[1] + tr[1], sv[2] + tr[2]};
+                            real dOn = D[0] * (t1[0] * t1[0] - sv[0] * sv[0]) + D[1] * (t1[1] * t1[1] - sv[1] * sv[1]);
+                            if (NC == 3) dOn += D[2] * (t1[2] * t1[2] - sv[2] * sv[2]);
+                            dE = beta * (dE + dOn) - hf * (NC == 3 ? tr[2] : tr[0]);
+                            if (dE <= real(0) || r_exp<real>(-dE) > u01<real>(w[2])) {       // heisenbergLib.c:461
+                                if (sizeof(real) == 4) {
+                                    real f = S * r_rsqrt<real>(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]);
+                                    t1[0] *= f; t1[1] *= f; t1[2] *= f;
+                                }
+                                sv[0] = t1[0]; sv[1] = t1[1]; sv[2] = t1[2];
+                                nacc++;
+                            }
+                        }
+                    }
+                    s[0][v] = sv[0]; s[1][v] = sv[1]; s[2][v] = sv[2];
+                }
+                if (MODE != 0) {
+                    accM[0] += sv[0]; accM[1] += sv[1]; accM[2] += sv[2];
+                    real eb;
+                    if (MODE == 2) {
+                        eb = real(0.5) * (sv[0] * Hv[0] + sv[1] * Hv[1] + sv[2] * Hv[2]);
+                    } else if (lowmode == 1) {
+                        eb = sv[0] * Hv[0] + sv[1] * Hv[1] + sv[2] * Hv[2];
+                    } else if (lowmode == 2) {
+                        eb = sv[0] * Hl[0][v] + sv[1] * Hl[1][v] + sv[2] * Hl[2][v];
+                    } else {
+                        eb = real(0);
+                    }
+                    accE += beta * eb + onsite_energy<NC, real>(sv, D, beta, hf);
+                }
+            }
+            if (MODE != 2) {
+#pragma unroll
+                for (int c = 0; c < NC; c++) vstore<real, V>(sp + (size_t)c * a.N + rowBase + Z0, s[c]);
+            }
+        }
+    }
+    if (MODE != 2) {
+        natt = __reduce_add_sync(0xffffffffu, natt);
+        nacc = __reduce_add_sync(0xffffffffu, nacc);
+        if ((tid & 31) == 0 && natt) {
+            atomicAdd(a.cnt + (size_t)r * NCNT + CNT_ATTEMPT, (unsigned long long)natt);
+            atomicAdd(a.cnt + (size_t)r * NCNT + CNT_ACCEPT, (unsigned long long)nacc);
+        }
+    }
+    if (MODE != 0) {
+        double v[4] = {(double)accM[0], (double)accM[1], (double)accM[2], (double)accE};
+        // block_accumulate indexes warps by threadIdx.x: flatten first
+        int lane = tid & 31, w = tid >> 5, nw = (blockDim.x * blockDim.y + 31) >> 5;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            double sum = warp_sum(v[i]);
+            if (lane == 0) red[i * 32 + w] = sum;
+        }
+        __syncthreads();
+        if (w == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                double sum = lane < nw ? red[i * 32 + lane] : 0.0;
+                sum = warp_sum(sum);
+                if (lane == 0 && sum != 0.0) atomicAdd(a.classSums + ((size_t)r * a.nclass + q) * 4 + i, sum);
+            }
+        }
+    }
+}
+
+// classSums -> the raw per-sweep sums the common finalize kernel consumes; clears classSums
+__global__ void k_struct_fold(StructArgs a, int R, int pair_s, int pair_t, int selfPairs, double nLat, double *sums) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    double *s = sums + (size_t)r * NSUM;
+    for (int q = 0; q < a.nclass; q++) {
+        double *c = a.classSums + ((size_t)r * a.nclass + q) * 4;
+        const SClassD &cl = a.classes[q];
+        for (int k = 0; k < 3; k++) {
+            s[SUM_TOT + k] += c[k];
+            if (cl.o == pair_s) s[SUM_SI + k] += c[k];
+            if (cl.o == pair_t) s[SUM_SJ + k] += c[k];
+        }
+        s[SUM_E] += c[3];
+        if (selfPairs && cl.o == pair_s) s[SUM_SIJ] += cl.S * cl.S * (nLat / (a.nclass / a.norb));
+        c[0] = c[1] = c[2] = c[3] = 0.0;
+    }
+}
+
+template <int NC, typename real>
+__global__ void __launch_bounds__(256) k_struct_pairs(StructArgs a, int ps, int pt, int d0, int d1, int d2, double *sums) {
+    __shared__ double smem[32];
+    int r = blockIdx.y;
+    int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    double v[1] = {0.0};
+    int ncell = a.Lx * a.Ly * a.Lz;
+    if (cell < ncell) {
+        int z = cell % a.Lz, y = (cell / a.Lz) % a.Ly, x = cell / (a.Lz * a.Ly);
+        int pi = struct_pos(a, x, y, z, ps);
+        int pj = struct_pos(a, (x + d0 + a.Lx) % a.Lx, (y + d1 + a.Ly) % a.Ly, (z + d2 + a.Lz) % a.Lz, pt);
+        const real *sp = (const real *)a.spin + (size_t)r * NC * a.N;
+        for (int c = 0; c < NC; c++) v[0] += (double)sp[(size_t)c * a.N + pi] * (double)sp[(size_t)c * a.N + pj];
+    }
+    block_accumulate<1>(v, sums + (size_t)r * NSUM + SUM_SIJ, smem);
+}
+
+// signed_area(): defined in kernels_generic.cuh for the table path; same formula here
+__device__ __forceinline__ double signed_area_s(const double (&s1)[3], const double (&s2)[3], const double (&s3)[3], double l1,
+                                                double l2, double l3) {
+    double s1s2 = (s1[0] * s2[0] + s1[1] * s2[1] + s1[2] * s2[2]) / l1 / l2;
+    double s2s3 = (s2[0] * s3[0] + s2[1] * s3[1] + s2[2] * s3[2]) / l2 / l3;
+    double s3s1 = (s3[0] * s1[0] + s3[1] * s1[1] + s3[2] * s1[2]) / l3 / l1;
+    double cx = s2[1] * s3[2] - s2[2] * s3[1], cy = s2[2] * s3[0] - s2[0] * s3[2], cz = s2[0] * s3[1] - s2[1] * s3[0];
+    double re = 1 + s1s2 + s2s3 + s3s1;
+    double im = (s1[0] * cx + s1[1] * cy + s1[2] * cz) / l1 / l2 / l3;
+    if (fabs(re) < 1e-6) return im > 0 ? MCG_REF_PI : -MCG_REF_PI;   // heisenbergLib.c:122-125
+    return 2 * atan(im / re);
+}
+
+template <typename real>
+__global__ void __launch_bounds__(256) k_struct_topo(StructArgs a, int ncirc, const int *__restrict__ circ, double *sums) {
+    __shared__ double smem[32];
+    int r = blockIdx.y;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    double v[1] = {0.0};
+    int ncell = a.Lx * a.Ly * a.Lz;
+    if (t < ncell * ncirc) {
+        int cell = t / ncirc, ic = t - cell * ncirc;
+        int z = cell % a.Lz, y = (cell / a.Lz) % a.Ly, x = cell / (a.Lz * a.Ly);
+        const real *sp = (const real *)a.spin + (size_t)r * 3 * a.N;
+        double s[3][3], l[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int *e = circ + (ic * 3 + k) * 4;
+            int xx = (x + e[1]) % a.Lx, yy = (y + e[2]) % a.Ly, zz = (z + e[3]) % a.Lz;
+            int p = struct_pos(a, xx, yy, zz, e[0]);
+            s[k][0] = sp[p]; s[k][1] = sp[(size_t)a.N + p]; s[k][2] = sp[2 * (size_t)a.N + p];
+            l[k] = fabs(a.classes[p / a.ncellc].S);
+        }
+        v[0] = signed_area_s(s[0], s[1], s[2], l[0], l[1], l[2]);
+    }
+    block_accumulate<1>(v, sums + (size_t)r * NSUM + SUM_AREA, smem);
+}
+
+template <int NC, typename real>
+__global__ void __launch_bounds__(256) k_struct_init(StructArgs a, double flunc) {
+    int r = blockIdx.y;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.N) return;
+    real *sp = (real *)a.spin + (size_t)r * NC * a.N;
+    int q = p / a.ncellc;
+    double S = a.classes[q].S;   // signed S of the orbital
+    double aS = fabs(S);
+    if (NC == 1) { sp[p] = (real)S; return; }
+    uint32_t w[4];
+    rng4(a.key, a.replica0 + r, STREAM_INIT, 0, 0, (uint32_t)struct_site_id(a, p), w);
+    double n[3];
+    if (sizeof(real) == 4) { float nf[3]; random_dir<NC, float>(w[0], w[1], nf); n[0] = nf[0]; n[1] = nf[1]; n[2] = nf[2]; }
+    else random_dir<NC, double>(w[0], w[1], n);
+    double v[3] = {S + flunc * n[0], flunc * n[1], NC == 3 ? flunc * n[2] : 0.0};
+    double len = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    if (!(len < 1e-5)) { v[0] /= len; v[1] /= len; v[2] /= len; }
+    sp[p] = (real)(v[0] * aS);
+    sp[(size_t)a.N + p] = (real)(v[1] * aS);
+    if (NC == 3) sp[2 * (size_t)a.N + p] = (real)(v[2] * aS);
+}
+
+template <int NC, typename real, bool GATHER>
+__global__ void __launch_bounds__(256) k_struct_frame(StructArgs a, int r, double *buf) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.N) return;
+    real *sp = (real *)a.spin + (size_t)r * NC * a.N;
+    size_t i = (size_t)struct_site_id(a, p);
+    if (NC == 1) {
+        if (GATHER) buf[i] = sp[p]; else sp[p] = (real)buf[i];
+        return;
+    }
+    if (GATHER) {
+        buf[3 * i] = sp[p]; buf[3 * i + 1] = sp[(size_t)a.N + p];
+        buf[3 * i + 2] = NC == 3 ? (double)sp[2 * (size_t)a.N + p] : 0.0;
+    } else {
+        sp[p] = (real)buf[3 * i]; sp[(size_t)a.N + p] = (real)buf[3 * i + 1];
+        if (NC == 3) sp[2 * (size_t)a.N + p] = (real)buf[3 * i + 2];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: link templates, colouring period search, class tables
+// ---------------------------------------------------------------------------------------------
+struct Tmpl {
+    int o2;
+    int d[3];       // internal axes, reduced mod L into (-L/2, L/2]
+    double J[9];
+    bool self;
+};
+
+static int mod(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
+
+static StructArgs struct_args(const mcg_system *s) {
+    const StructuredSystem *st = s->st;
+    StructArgs a;
+    a.Xd = st->Xd; a.Yd = st->Yd; a.Zd = st->Zd; a.Zc = st->Zd / st->V; a.ncellc = st->ncellc; a.nclass = st->nclass;
+    a.nrows = st->nrows; a.N = s->N;
+    a.px = st->p[0]; a.py = st->p[1]; a.pz = st->p[2]; a.norb = st->norb; a.Lx = st->L[0]; a.Ly = st->L[1]; a.Lz = st->L[2];
+    a.classes = st->d_classes; a.links = st->d_links; a.J = st->d_J; a.classOf = st->d_classOf;
+    a.spin = s->d_spin; a.beta = s->d_beta; a.field = s->d_field; a.cnt = s->d_cnt; a.classSums = st->d_classSums;
+    a.key.k0 = (uint32_t)s->seed; a.key.k1 = (uint32_t)(s->seed >> 32);
+    a.replica0 = s->replica0;
+    return a;
+}
+
+void structured_create(mcg_system *s, const mcg_lattice_desc *d) {
+    MCG_REQUIRE(d->model >= 1 && d->model <= 3, "model must be 1, 2 or 3");
+    MCG_REQUIRE(d->norb >= 1 && d->S, "norb/S invalid");
+    for (int k = 0; k < 3; k++) MCG_REQUIRE(d->L[k] >= 1, "supercell dims must be >= 1");
+    MCG_REQUIRE((long long)d->L[0] * d->L[1] * d->L[2] * d->norb < (1ll << 31), "lattice too large for 32-bit site ids");
+    MCG_REQUIRE(d->nbond >= 0 && (d->nbond == 0 || d->bonds), "bonds invalid");
+    MCG_REQUIRE(d->pair_s >= 0 && d->pair_s < d->norb && d->pair_t >= 0 && d->pair_t < d->norb, "pair orbital out of range");
+    std::unique_ptr<StructuredSystem> stp(new StructuredSystem());
+    StructuredSystem *st = stp.get();
+    const int no = d->norb;
+    st->norb = no;
+    // canonical internal axes: drop unit dims, left-pad with 1 (keeps the row-major site id formula)
+    int ax[3], nax = 0;
+    for (int k = 0; k < 3; k++) if (d->L[k] > 1) ax[nax++] = k;
+    int map[3] = {-1, -1, -1};   // internal axis i <- original axis map[i] (or -1)
+    for (int i = 0; i < nax; i++) map[3 - nax + i] = ax[i];
+    for (int i = 0; i < 3; i++) st->L[i] = map[i] >= 0 ? d->L[map[i]] : 1;
+    auto conv = [&](const int32_t *v, int *o) { for (int i = 0; i < 3; i++) o[i] = map[i] >= 0 ? v[map[i]] : 0; };
+    const int *L = st->L;
+
+    s->model = d->model; s->NC = d->model; s->structured = true;
+    s->N = L[0] * L[1] * L[2] * no;
+    bool full = false;
+    // link templates per orbital, with the reference's merge rule (Lattice.py:36-52) applied per template
+    std::vector<std::vector<Tmpl>> tm(no);
+    auto add_link = [&](int o, int o2, const int *dd, const double *J9, bool transpose) {
+        Tmpl t;
+        t.o2 = o2;
+        for (int k = 0; k < 3; k++) { int m = mod(dd[k], L[k]); if (m > L[k] / 2) m -= L[k]; t.d[k] = m; }
+        static const int T9[9] = {0, 1, 2, 6, 7, 8, 3, 4, 5};
+        for (int k = 0; k < 9; k++) t.J[k] = d->model == 1 ? (k == 0 ? J9[0] : 0.0) : J9[transpose ? T9[k] : k];
+        t.self = (o2 == o && t.d[0] == 0 && t.d[1] == 0 && t.d[2] == 0);
+        if (t.self && transpose) return;   // Lattice.py:261: no back link to oneself
+        for (auto &e : tm[o])
+            if (e.o2 == t.o2 && e.d[0] == t.d[0] && e.d[1] == t.d[1] && e.d[2] == t.d[2]) {
+                double diff = 0;
+                for (int k = 0; k < 9; k++) diff += std::fabs(e.J[k] - t.J[k]);
+                if (diff < 1e-5) return;
+                for (int k = 0; k < 9; k++) e.J[k] += t.J[k];
+                return;
+            }
+        tm[o].push_back(t);
+    };
+    for (int b = 0; b < d->nbond; b++) {
+        const mcg_bond &B = d->bonds[b];
+        MCG_REQUIRE(B.src >= 0 && B.src < no && B.tgt >= 0 && B.tgt < no, "bond orbital index out of range");
+        int dd[3], nd[3];
+        conv(B.d, dd);
+        for (int k = 0; k < 3; k++) nd[k] = -dd[k];
+        add_link(B.src, B.tgt, dd, B.J, false);
+        add_link(B.tgt, B.src, nd, B.J, true);
+    }
+    for (int o = 0; o < no; o++) {
+        MCG_REQUIRE((int)tm[o].size() <= MAXLINK, "more than 32 links per site: use the table path");
+        for (auto &t : tm[o]) {
+            if (t.self) st->hasSelf = true;
+            if (d->model != 1) for (int k = 3; k < 9; k++) if (std::fabs(t.J[k]) > 1e-6) full = true;   // mcMain.py:174
+        }
+    }
+    s->fullJ = full;
+
+    // ---- colouring period search ----
+    auto candidates = [&](int Ld) {
+        std::vector<int> c;
+        if (Ld == 1) { c.push_back(1); return c; }
+        for (int p = 1; p <= 6; p++) if (Ld % p == 0) c.push_back(p);
+        if (Ld > 6 && Ld <= 16) c.push_back(Ld);
+        return c;
+    };
+    int best[3] = {0, 0, 0}, bestC = 1 << 30, bestN = 1 << 30;
+    std::vector<int> bestColour;
+    for (int px : candidates(L[0])) for (int py : candidates(L[1])) for (int pz : candidates(L[2])) {
+        int ncls = px * py * pz * no;
+        if (ncls > 1024) continue;
+        auto cid = [&](int a, int b, int c, int o) { return ((a * py + b) * pz + c) * no + o; };
+        std::vector<std::vector<int>> adj(ncls);
+        bool ok = true;
+        for (int a = 0; a < px && ok; a++) for (int b = 0; b < py && ok; b++) for (int c = 0; c < pz && ok; c++)
+            for (int o = 0; o < no && ok; o++)
+                for (auto &t : tm[o]) {
+                    if (t.self) continue;
+                    int n = cid(mod(a + t.d[0], px), mod(b + t.d[1], py), mod(c + t.d[2], pz), t.o2);
+                    if (n == cid(a, b, c, o)) { ok = false; break; }
+                    adj[cid(a, b, c, o)].push_back(n);
+                    adj[n].push_back(cid(a, b, c, o));
+                }
+        if (!ok) continue;
+        std::vector<int> col(ncls, -1);
+        int C = 0;
+        for (int i = 0; i < ncls; i++) {
+            std::vector<char> used(ncls + 1, 0);
+            for (int n : adj[i]) if (col[n] >= 0) used[col[n]] = 1;
+            int c = 0;
+            while (used[c]) c++;
+            col[i] = c;
+            C = std::max(C, c + 1);
+        }
+        if (C < bestC || (C == bestC && ncls < bestN)) {
+            bestC = C; bestN = ncls; best[0] = px; best[1] = py; best[2] = pz; bestColour = col;
+        }
+    }
+    MCG_REQUIRE(best[0] > 0, "no periodic colouring with period <= 6 divides this supercell: use the table path");
+    for (int k = 0; k < 3; k++) st->p[k] = best[k];
+    const int px = best[0], py = best[1], pz = best[2];
+    st->nclass = bestN; s->C = bestC;
+    st->Xd = L[0] / px; st->Yd = L[1] / py; st->Zd = L[2] / pz;
+    st->ncellc = st->Xd * st->Yd * st->Zd;
+    st->nrows = st->Xd * st->Yd;
+    int Vmax = s->prec == 32 ? 4 : 2;
+    st->V = (st->Zd % Vmax == 0) ? Vmax : 1;
+
+    // classes sorted by colour (stable), classOf = inverse
+    std::vector<int> order(bestN);
+    for (int i = 0; i < bestN; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return bestColour[a] < bestColour[b]; });
+    st->classOf.assign(bestN, -1);
+    for (int q = 0; q < bestN; q++) st->classOf[order[q]] = q;
+    st->colourClassStart.assign(bestC + 1, 0);
+    for (int i = 0; i < bestN; i++) st->colourClassStart[bestColour[i] + 1]++;
+    for (int c = 0; c < bestC; c++) st->colourClassStart[c + 1] += st->colourClassStart[c];
+    st->classes.resize(bestN);
+    std::vector<SLinkD> links((size_t)bestN * MAXLINK);
+    std::memset(links.data(), 0, links.size() * sizeof(SLinkD));
+    const int JW = d->model == 1 ? 1 : 9;
+    std::vector<double> Jt((size_t)bestN * MAXLINK * JW, 0.0);
+    for (int q = 0; q < bestN; q++) {
+        int id = order[q];
+        int o = id % no, c = (id / no) % pz, b = (id / (no * pz)) % py, a = id / (no * pz * py);
+        SClassD &cl = st->classes[q];
+        cl.a = a; cl.b = b; cl.c = c; cl.o = o; cl.colour = bestColour[id]; cl.nlink = (int)tm[o].size(); cl.pad = 0;
+        cl.S = d->S[o];
+        for (int k = 0; k < 3; k++) cl.D[k] = (d->D && d->model != 1) ? d->D[3 * o + k] : 0.0;
+        int nlow = 0, nreal = 0;
+        for (int k = 0; k < cl.nlink; k++) {
+            const Tmpl &t = tm[o][k];
+            SLinkD &l = links[(size_t)q * MAXLINK + k];
+            int na = a + t.d[0], nb = b + t.d[1], nc = c + t.d[2];
+            auto fdiv = [](int v, int m) { return (v >= 0) ? v / m : -((-v + m - 1) / m); };
+            int cX = fdiv(na, px), cY = fdiv(nb, py), cZ = fdiv(nc, pz);
+            int nid = ((mod(na, px) * py + mod(nb, py)) * pz + mod(nc, pz)) * no + t.o2;
+            l.qn = st->classOf[nid];
+            l.cX = mod(cX, st->Xd); l.cY = mod(cY, st->Yd);
+            int z = mod(cZ, st->Zd); if (z > st->Zd / 2) z -= st->Zd;
+            l.cZ = z;
+            l.self = t.self ? 1 : 0;
+            l.low = (!t.self && bestColour[nid] < bestColour[id]) ? 1 : 0;
+            if (!t.self) { nreal++; nlow += l.low; }
+            for (int e = 0; e < JW; e++) Jt[((size_t)q * MAXLINK + k) * JW + e] = t.J[e];
+        }
+        cl.lowmode = nlow == 0 ? 0 : (nlow == nreal ? 1 : 2);
+    }
+    // measurement templates
+    st->pair_s = d->pair_s; st->pair_t = d->pair_t;
+    conv(d->pair_d, st->pair_d);
+    for (int k = 0; k < 3; k++) st->pair_d[k] = mod(st->pair_d[k], L[k]);
+    st->selfPairs = st->pair_s == st->pair_t && st->pair_d[0] == 0 && st->pair_d[1] == 0 && st->pair_d[2] == 0;
+    s->nLat = L[0] * L[1] * L[2];
+    st->ncircuit = d->model == 3 ? d->ncircuit : 0;
+    s->nTri = st->ncircuit * s->nLat;
+    for (int i = 0; i < st->ncircuit * 3; i++) {
+        const int32_t *e = d->circuits + 4 * i;
+        MCG_REQUIRE(e[0] >= 0 && e[0] < no, "circuit orbital out of range");
+        int dd[3];
+        conv(e + 1, dd);
+        st->circuits.push_back(e[0]);
+        for (int k = 0; k < 3; k++) st->circuits.push_back(mod(dd[k], L[k]));
+    }
+    s->S_host.clear();
+    s->maxL = 0;
+    for (int o = 0; o < no; o++) s->maxL = std::max(s->maxL, (int)tm[o].size());
+
+    // ---- upload ----
+    auto up = [&](const void *src, size_t bytes) { void *p = nullptr; MCG_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 16))); if (bytes) MCG_CUDA(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice)); return p; };
+    st->d_classes = (SClassD *)up(st->classes.data(), st->classes.size() * sizeof(SClassD));
+    st->d_links = (SLinkD *)up(links.data(), links.size() * sizeof(SLinkD));
+    if (s->prec == 64) st->d_J = up(Jt.data(), Jt.size() * sizeof(double));
+    else { std::vector<float> jf(Jt.begin(), Jt.end()); st->d_J = up(jf.data(), jf.size() * sizeof(float)); }
+    st->d_classOf = (int *)up(st->classOf.data(), st->classOf.size() * sizeof(int));
+    st->d_circuits = (int *)up(st->circuits.data(), st->circuits.size() * sizeof(int));
+    size_t cs = (size_t)s->R * st->nclass * 4 * sizeof(double);
+    MCG_CUDA(cudaMalloc(&st->d_classSums, cs));
+    MCG_CUDA(cudaMemset(st->d_classSums, 0, cs));
+    MCG_CUDA(cudaMalloc(&s->d_spin, (size_t)s->R * s->NC * s->N * s->real_size()));
+    s->st = stp.release();
+}
+
+void structured_destroy(StructuredSystem *st) {
+    if (!st) return;
+    void *bufs[] = {st->d_classes, st->d_links, st->d_J, st->d_classOf, st->d_circuits, st->d_classSums, st->d_stage};
+    for (void *b : bufs) if (b) cudaFree(b);
+    delete st;
+}
+
+template <typename F> static void sdispatch(const mcg_system *s, F &&f) {
+    bool d = s->prec == 64, fj = s->fullJ;
+    switch (s->NC) {
+    case 1: d ? f.template operator()<1, double, false>() : f.template operator()<1, float, false>(); break;
+    case 2:
+        if (d) fj ? f.template operator()<2, double, true>() : f.template operator()<2, double, false>();
+        else fj ? f.template operator()<2, float, true>() : f.template operator()<2, float, false>();
+        break;
+    default:
+        if (d) fj ? f.template operator()<3, double, true>() : f.template operator()<3, double, false>();
+        else fj ? f.template operator()<3, float, true>() : f.template operator()<3, float, false>();
+    }
+}
+
+void structured_init_spins(mcg_system *s, double flunc) {
+    StructArgs a = struct_args(s);
+    dim3 g((s->N + 255) / 256, s->R);
+    sdispatch(s, [&]<int NC, typename real, bool FJ>() { k_struct_init<NC, real><<<g, 256, 0, s->stream>>>(a, flunc); });
+    MCG_CUDA(cudaGetLastError());
+}
+
+static double *stage(mcg_system *s) {
+    if (!s->st->d_stage) MCG_CUDA(cudaMalloc(&s->st->d_stage, 3 * (size_t)s->N * sizeof(double)));
+    return s->st->d_stage;
+}
+
+void structured_set_spins(mcg_system *s, int r, const double *spins) {
+    StructArgs a = struct_args(s);
+    double *buf = stage(s);
+    size_t n = (size_t)s->N * (s->NC == 1 ? 1 : 3);
+    MCG_CUDA(cudaMemcpyAsync(buf, spins, n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    sdispatch(s, [&]<int NC, typename real, bool FJ>() { k_struct_frame<NC, real, false><<<(s->N + 255) / 256, 256, 0, s->stream>>>(a, r, buf); });
+    MCG_CUDA(cudaGetLastError());
+    MCG_CUDA(cudaStreamSynchronize(s->stream));
+}
+
+void structured_get_spins(mcg_system *s, int r, double *spins) {
+    StructArgs a = struct_args(s);
+    double *buf = stage(s);
+    size_t n = (size_t)s->N * (s->NC == 1 ? 1 : 3);
+    sdispatch(s, [&]<int NC, typename real, bool FJ>() { k_struct_frame<NC, real, true><<<(s->N + 255) / 256, 256, 0, s->stream>>>(a, r, buf); });
+    MCG_CUDA(cudaGetLastError());
+    MCG_CUDA(cudaMemcpyAsync(spins, buf, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    MCG_CUDA(cudaStreamSynchronize(s->stream));
+}
+
+void structured_colour_order(const mcg_system *s, int32_t *order) {
+    const StructuredSystem *st = s->st;
+    for (int p = 0; p < s->N; p++) {
+        int q = p / st->ncellc, cell = p % st->ncellc;
+        int Z = cell % st->Zd, Y = (cell / st->Zd) % st->Yd, X = cell / (st->Zd * st->Yd);
+        const SClassD &c = st->classes[q];
+        int x = X * st->p[0] + c.a, y = Y * st->p[1] + c.b, z = Z * st->p[2] + c.c;
+        order[p] = ((x * st->L[1] + y) * st->L[2] + z) * st->norb + c.o;
+    }
+}
+
+template <int MODE> static void launch_pass(mcg_system *s, int colour, uint64_t sweep, double pAtt) {
+    StructuredSystem *st = s->st;
+    StructArgs a = struct_args(s);
+    int q0 = st->colourClassStart[colour], nqc = st->colourClassStart[colour + 1] - q0;
+    if (nqc == 0) return;
+    int Zc = st->Zd / st->V;
+    int bx = 1;
+    while (bx < Zc && bx < 64) bx <<= 1;
+    int by = 256 / bx;
+    int iters = 8;
+    auto nblocks = [&](int it) { return (long long)s->R * nqc * ((st->nrows + by * it - 1) / (by * it)); };
+    while (iters > 1 && nblocks(iters) < 2368) iters >>= 1;   // >= 16 blocks per SM on 148 SMs when the lattice allows
+    int rowsPerBlock = by * iters;
+    int nrb = (st->nrows + rowsPerBlock - 1) / rowsPerBlock;
+    dim3 block(bx, by), grid((unsigned)(s->R * nrb * nqc));
+    sdispatch(s, [&]<int NC, typename real, bool FJ>() {
+        if (st->V == 1) k_struct<NC, real, FJ, MODE, 1><<<grid, block, 0, s->stream>>>(a, q0, nqc, rowsPerBlock, nrb, sweep, (real)pAtt);
+        else if constexpr (sizeof(real) == 4) k_struct<NC, real, FJ, MODE, 4><<<grid, block, 0, s->stream>>>(a, q0, nqc, rowsPerBlock, nrb, sweep, (real)pAtt);
+        else k_struct<NC, real, FJ, MODE, 2><<<grid, block, 0, s->stream>>>(a, q0, nqc, rowsPerBlock, nrb, sweep, (real)pAtt);
+    });
+}
+
+static void fold_and_extras(mcg_system *s) {
+    StructuredSystem *st = s->st;
+    StructArgs a = struct_args(s);
+    k_struct_fold<<<(s->R + 63) / 64, 64, 0, s->stream>>>(a, s->R, st->pair_s, st->pair_t, st->selfPairs ? 1 : 0, (double)s->nLat, s->d_sums);
+    if (!st->selfPairs) {
+        dim3 g((s->nLat + 255) / 256, s->R);
+        sdispatch(s, [&]<int NC, typename real, bool FJ>() {
+            k_struct_pairs<NC, real><<<g, 256, 0, s->stream>>>(a, st->pair_s, st->pair_t, st->pair_d[0], st->pair_d[1], st->pair_d[2], s->d_sums);
+        });
+    }
+    if (st->ncircuit > 0 && s->NC == 3) {
+        dim3 g((s->nTri + 255) / 256, s->R);
+        if (s->prec == 64) k_struct_topo<double><<<g, 256, 0, s->stream>>>(a, st->ncircuit, st->d_circuits, s->d_sums);
+        else k_struct_topo<float><<<g, 256, 0, s->stream>>>(a, st->ncircuit, st->d_circuits, s->d_sums);
+    }
+    MCG_CUDA(cudaGetLastError());
+}
+
+void structured_measure_sums(mcg_system *s) {
+    for (int c = 0; c < s->C; c++) launch_pass<2>(s, c, 0, 1.0);
+    fold_and_extras(s);
+}
+
+void structured_sweeps(mcg_system *s, int64_t n, double pAtt, bool fusedMeasure) {
+    bool fuse = fusedMeasure && !s->st->hasSelf;
+    for (int64_t it = 0; it < n; it++) {
+        bool last = it == n - 1;
+        for (int c = 0; c < s->C; c++) {
+            if (last && fuse) launch_pass<1>(s, c, s->sweepCtr, pAtt);
+            else launch_pass<0>(s, c, s->sweepCtr, pAtt);
+        }
+        s->sweepCtr++;
+    }
+    MCG_CUDA(cudaGetLastError());
+    if (fusedMeasure) {
+        if (fuse) fold_and_extras(s);
+        else structured_measure_sums(s);
+    }
+}
+
 }  // namespace mcg

@@ -204,6 +204,12 @@ class System:
     def metropolis_sweeps(self, n, p_attempt=1.0):
         check(_ffi.lib().mcg_metropolis_sweeps(self._h, int(n), float(p_attempt)))
 
+    def timed_sweeps(self, n, p_attempt=1.0, with_measure=False):
+        """Device time (ms, CUDA events on the launch stream) of n Metropolis sweeps."""
+        ms = C.c_double(0)
+        check(_ffi.lib().mcg_timed_sweeps(self._h, int(n), float(p_attempt), int(bool(with_measure)), C.byref(ms)))
+        return ms.value
+
     def wolff_steps(self, n):
         check(_ffi.lib().mcg_wolff_steps(self._h, int(n)))
 

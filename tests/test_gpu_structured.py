@@ -1,0 +1,124 @@
+"""GPU parity tests of the structured (descriptor-driven) path: same checks as the table path,
+plus equality of the two paths' observables on the same configuration."""
+import numpy as np
+import pytest
+
+from tests import util
+from tests.specs import spec_of
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("skyrmion", (6, 6, 1), 0.3, 3, 0.2), ("skyrmion", (8, 12, 1), 0.3, 3, 0.2), ("cri3", (4, 4, 1), 35.0, 3, 0.0),
+         ("cri3", (6, 6, 1), 35.0, 3, 0.0), ("aniso", (6, 6, 2), 0.7, 3, 0.3), ("aniso", (6, 6, 1), 0.7, 2, 0.3),
+         ("square", (8, 8, 1), 0.9, 2, 0.05), ("square", (16, 8, 1), 0.9, 2, 0.05), ("cubic", (6, 6, 6), 1.4, 3, 0.1),
+         ("cubic", (4, 6, 8), 1.4, 3, 0.1), ("cubic", (8, 8, 16), 1.4, 3, 0.0), ("square", (8, 8, 1), 2.3, 1, 0.05),
+         ("cubic", (6, 6, 8), 4.4, 1, 0.0), ("cubic", (3, 3, 3), 1.4, 3, 0.0), ("square", (5, 5, 1), 0.9, 2, 0.0)]
+IDS = ["%s-%s-m%d" % (c[0], "x".join(map(str, c[1])), c[3]) for c in CASES]
+
+
+def _eng():
+    from mcsolver_b200 import engine
+    return engine
+
+
+def _start(o, t, model, seed):
+    if model == 1:
+        rng = np.random.RandomState(seed)
+        return rng.choice([-1.0, 1.0], size=t.N) * np.abs(t.S)
+    return o.init_spins_philox(0.8, seed=seed)
+
+
+@pytest.mark.parametrize("case", CASES, ids=IDS)
+def test_structured_energy_observables_and_trajectory_fp64(case):
+    eng = _eng()
+    name, L, T, model, h = case
+    spec = spec_of(name, L)
+    t = util.tables_for(dict(spec=name, L=L, T=T, model=model))
+    hT = h / T
+    o = util.oracle_system(t, hT)
+    # structured systems take UNSCALED couplings and beta = 1/T per replica
+    with eng.System.from_spec(spec, model, precision=64, beta=[1.0 / T], field=[h], seed=4321) as s:
+        order = s.colour_order()
+        assert sorted(order.tolist()) == list(range(t.N))
+        start = _start(o, t, model, 4321)
+        if model != 1:
+            s.init_spins(0.8)
+            assert np.max(np.abs(s.get_spins() - start)) < 1e-12
+        s.set_spins(start)
+        E = s.energy()
+        Eo = o.total_energy(start)
+        assert abs(E - Eo) <= 1e-12 * max(1.0, abs(Eo))
+        s.measure()
+        out, _ = s.results()
+        if model != 1:
+            oo, _ = o.observe(start)
+            for k in util.ON_CORE_SLOTS:
+                assert abs(out[k] - oo[k]) <= 1e-11 * max(1.0, abs(oo[k])), (k, out[k], oo[k])
+        s.reset_measurements()
+        r = o.run(2, 9, 1, t.N, order=order, seed=4321, spins=start)
+        s.metropolis_sweeps(10)
+        got = s.get_spins()
+        assert np.max(np.abs(got - r["spins"].reshape(got.shape))) < 1e-9
+        att, acc, _ = s.counters()
+        assert (att, acc) == (int(r["counters"][0]), int(r["counters"][1]))
+
+
+@pytest.mark.parametrize("case", CASES[:11], ids=IDS[:11])
+def test_structured_whole_run_fused_measurement_matches_oracle(case):
+    """mcg_run on a structured system: the measurement sums come out of the colour passes
+    themselves (fused); the result tuple must equal the oracle's restatement of the same loop."""
+    eng = _eng()
+    name, L, T, model, h = case
+    spec = spec_of(name, L)
+    t = util.tables_for(dict(spec=name, L=L, T=T, model=model))
+    hT = h / T
+    o = util.oracle_system(t, hT)
+    with eng.System.from_spec(spec, model, precision=64, beta=[1.0 / T], field=[h], seed=17) as s:
+        order = s.colour_order()
+        s.init_spins(0.3)
+        fr = s.run(0, 4, 15, 2 * t.N, spinFrame=3)
+        out, _ = s.results()
+    r = o.run(2, 4, 15, 2 * t.N, flunc=0.3, spinFrame=3, order=order, seed=17)
+    for k in util.ON_CORE_SLOTS + [7]:
+        assert abs(out[k] - r["out"][k]) <= 1e-9 * max(1.0, abs(r["out"][k])), (k, out[k], r["out"][k])
+    assert np.max(np.abs(fr[0] - r["frames"])) < 1e-9
+
+
+def test_structured_replicas_are_independent_points_of_a_scan():
+    """A batch of replicas = the reference's (T,H) grid: replica r of a batch gives exactly what a
+    single-replica system with replica_offset=r gives (GPU-count independent streams)."""
+    eng = _eng()
+    spec = spec_of("cubic", (6, 6, 8))
+    Ts = np.array([1.0, 1.4, 2.0])
+    hs = np.array([0.0, 0.1, 0.2])
+    with eng.System.from_spec(spec, 3, precision=64, nReplica=3, beta=1 / Ts, field=hs, seed=9) as s:
+        s.init_spins(0.2)
+        s.run(0, 3, 6, spec.nsite)
+        batch = [s.results(r)[0] for r in range(3)]
+        sp = [s.get_spins(r) for r in range(3)]
+    for r in range(3):
+        with eng.System.from_spec(spec, 3, precision=64, nReplica=1, beta=[1 / Ts[r]], field=[hs[r]], seed=9, replica_offset=r) as s:
+            s.init_spins(0.2)
+            s.run(0, 3, 6, spec.nsite)
+            one = s.results(0)[0]
+            assert np.array_equal(s.get_spins(0), sp[r])
+        assert np.allclose(one, batch[r], rtol=1e-12, atol=1e-14)
+
+
+def test_structured_fp32_vector_path_statistics():
+    """fp32 float4 path on a lattice large enough for V=4: energy of the ordered state is exact,
+    a short run stays normalised and close to the fp64 run's energy."""
+    eng = _eng()
+    spec = spec_of("cubic", (8, 8, 16))
+    res = {}
+    for prec in (32, 64):
+        with eng.System.from_spec(spec, 3, precision=prec, beta=[1 / 1.2], seed=3) as s:
+            s.init_spins(0.0)
+            assert abs(s.energy() - (-3.0 * spec.nsite / 1.2)) < 1e-3
+            s.run(0, 200, 400, spec.nsite)
+            res[prec] = s.results()[0]
+            n = np.linalg.norm(s.get_spins(), axis=1)
+            assert np.allclose(n, 1.0, atol=3e-6)
+    # <e> at T=1.2 on 8x8x16: statistical agreement (two different chains, ~1% tolerance)
+    assert abs(res[32][8] - res[64][8]) < 0.02 * abs(res[64][8])
+    assert abs(res[32][10] - res[64][10]) < 0.05
