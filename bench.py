@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py - the headline measurement (BASELINE.json: attempted Metropolis spin updates / s).
+
+Workload (config.workload): 3D Heisenberg, simple cubic 256^3 (N = 16 777 216 spins), J = diag(-1,-1,-1)
+on [100],[010],[001], initial state polarised (S,0,0) as in the reference, temperature scan with 8
+replicas per GPU (the 64-point ladder of BASELINE configs[4] sharded over 8 GPUs; dipole term not in
+this round).  One "step" = SWEEPS colour-class Metropolis sweeps over all replicas of the rank, every
+sweep followed by the reference's per-sweep measurement (fused into the colour passes).
+
+  python bench.py --gpus N --steps K --warmup W              # our engine (torchrun for N>1)
+  python bench.py --impl reference --gpus N --steps K ...    # the reference's own C engine on host cores
+
+JSON line keys follow the driver contract; see DESIGN.md "Measurement" for the byte model.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+J_ISO = [-1.0, -1.0, -1.0] + [0.0] * 6
+TC = 1.443  # Heisenberg sc, |J| = 1
+
+
+def cubic_spec(L):
+    from mcsolver_b200.lattice import LatticeSpec
+    return LatticeSpec(L=(L, L, L), S=[1.0], bonds=[(0, 0, (1, 0, 0), J_ISO), (0, 0, (0, 1, 0), J_ISO), (0, 0, (0, 0, 1), J_ISO)])
+
+
+def ladder(n_total):
+    """geometric temperature ladder in [0.8 Tc, 1.3 Tc]"""
+    return 0.8 * TC * (1.3 / 0.8) ** (np.arange(n_total) / max(1, n_total - 1))
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's own compiled C engine (oracle/_ref) on host cores
+# ---------------------------------------------------------------------------------------------
+def _ref_worker(job):
+    L, T, nthermal, nsweep, seed = job
+    from oracle import refharness as rh
+    from mcsolver_b200.lattice import build_tables
+    t = build_tables(cubic_spec(L), T, 3)
+    args = t.on_args(0, nthermal, nsweep, t.N, 0.0, 0.0, 0)
+    t0 = time.time()
+    out = rh.run_ref_engine(3, args, seed=seed)
+    dt = time.time() - t0
+    return t.N * (nthermal + nsweep), dt, out[8] * T
+
+
+def reference_step(nproc, L, nthermal, nsweep):
+    """One bounded sample: nproc independent temperature points, one process each (the reference's
+    own parallel axis, win.py:90-91).  Returns (attempts, wall seconds of the engine calls)."""
+    import multiprocessing as mp
+    Ts = ladder(nproc)
+    jobs = [(L, float(Ts[i]), nthermal, nsweep, i + 1) for i in range(nproc)]
+    ctx = mp.get_context("fork")
+    t0 = time.time()
+    with ctx.Pool(processes=nproc) as pool:
+        res = pool.map(_ref_worker, jobs)
+    wall = time.time() - t0
+    attempts = sum(r[0] for r in res)
+    engine_wall = max(r[1] for r in res)
+    return attempts, engine_wall, wall
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def ref_kind():
+    from oracle import refharness as rh
+    return "reference" if rh.have_ref_engine() else "port"
+
+
+def run_reference_arm(a, rank, world):
+    if rank != 0:
+        return
+    cores = min(host_cores(), 128)
+    L, nth, nsw = a.ref_L, 2, a.ref_sweeps
+    for _ in range(max(0, min(a.warmup, 1))):
+        reference_step(cores, L, 1, 2)
+    att, eng, t = 0, 0.0, 0.0
+    t0 = time.time()
+    for _ in range(a.steps):
+        x, e, w = reference_step(cores, L, nth, nsw)
+        att += x
+        eng += e
+        t += w
+    wall = time.time() - t0
+    val = att / eng
+    sample = "sc %d^3 Heisenberg, %d temperature points (1 process each), %d+%d sweeps per point per step, engine-call time only" % (L, cores, nth, nsw)
+    line = {"impl": "reference", "metric": "attempted Metropolis spin updates per second", "value": val, "unit": "attempts/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * eng / max(1, a.steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(a, world), "gpu_launches": 0,
+            "cpu_baseline": {"value": val, "unit": "attempts/s", "cores": cores, "kind": ref_kind(), "sample": sample},
+            "e2e": {"value": val, "unit": "attempts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": wall}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(a, world):
+    return {"workload": "heisenberg_sc_%d^3_Tscan_%d_replicas_per_gpu" % (a.L, a.replicas), "lattice": "simple cubic %d^3" % a.L,
+            "spins": a.L ** 3, "replicas_per_gpu": a.replicas, "replicas_total": a.replicas * world,
+            "sweeps_per_step": a.sweeps, "measurement": "every sweep (fused M,E; reference definitions)",
+            "state": "fp32 SoA planes, 12 B/spin", "parallelism": "replica-sharded x%d (no data-path collective)" % world,
+            "l2": "inputs larger than L2: %.0f MB of spin state per colour pass" % (a.replicas * a.L ** 3 * 12 / 1e6),
+            "dipole": "not included (SURVEY 8 f2)"}
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, n in enumerate(names):
+                if f[4 + k].lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--L", type=int, default=256)
+    ap.add_argument("--replicas", type=int, default=8)
+    ap.add_argument("--sweeps", type=int, default=20, help="Metropolis sweeps (each measured) per step")
+    ap.add_argument("--ref-L", type=int, default=32)
+    ap.add_argument("--ref-sweeps", type=int, default=60)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if a.impl == "reference":
+        a.steps = min(a.steps, 3)      # each step is a bounded multi-second CPU sample
+        run_reference_arm(a, rank, world)
+        return
+
+    # ---- CPU baseline first (rank 0, N=1): forks workers, so it must precede CUDA initialisation
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cores = min(host_cores(), 128)
+        att, eng, _ = reference_step(cores, a.ref_L, 2, a.ref_sweeps)
+        cpu = {"value": att / eng, "unit": "attempts/s", "cores": cores, "kind": ref_kind(),
+               "sample": "reference C engine (oracle/_ref heisenberglib), sc %d^3, %d temperature points x (2+%d) sweeps, one "
+                         "process per point, engine-call time %.1f s" % (a.ref_L, cores, a.ref_sweeps, eng)}
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+
+    def barrier_max(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    from mcsolver_b200 import engine, scan
+    spec = cubic_spec(a.L)
+    N, R = spec.nsite, a.replicas
+    Ts = ladder(R * world)[rank * R:(rank + 1) * R]
+    s = engine.System.from_spec(spec, 3, precision=32, nReplica=R, beta=1.0 / Ts, field=np.zeros(R), seed=1,
+                                replica_offset=rank * R, device=local)
+    s.init_spins(0.0)
+    for _ in range(a.warmup):
+        s.timed_sweeps(a.sweeps, with_measure=True)
+    s.reset_measurements()
+    s.profile_passes(True)
+    l0 = s.launch_count()
+    clocks = ClockSampler(local)
+    clocks.start()
+    barrier_max(0.0)
+    t0 = time.time()
+    dev_ms = 0.0
+    for _ in range(a.steps):
+        dev_ms += s.timed_sweeps(a.sweeps, with_measure=True)      # CUDA events on the launch stream; syncs
+    wall = time.time() - t0
+    t_max = barrier_max(dev_ms / 1e3)
+    clk = clocks.stop()
+    launches = s.launch_count() - l0
+    pass_ms, npass = s.profile_read()
+    s.profile_passes(False)
+    out0 = s.results(0)[0]
+    s.close()
+
+    attempts_rank = R * N * a.sweeps * a.steps
+    value = world * attempts_rank / t_max
+
+    # ---- roofline of the dominant kernel (colour pass with fused measurement), per launch
+    w_bytes = 12                                   # fp32 x,y,z planes
+    b_alg = 3 * w_bytes                            # own read + own write + each neighbour-colour spin once (2 colours)
+    attempts_per_launch = R * N / 2
+    avg_launch_s = pass_ms / 1e3 / max(1, npass)
+    achieved = attempts_per_launch * b_alg / avg_launch_s / 1e9
+    peak, peak_src = measured_peak()
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "kernel": "mcg::k_struct<3,float,diagJ,MODE=1 (update+fused measure),V=4>", "bytes_per_attempt": b_alg,
+            "attempts_per_launch": attempts_per_launch, "avg_launch_ms": avg_launch_s * 1e3, "launches_timed": npass,
+            "kernel_share_of_step": pass_ms / dev_ms, "peak_source": peak_src}
+
+    # ---- e2e: whole jobs through the public API, host descriptors in, host result rows out
+    e2e_steps = max(1, min(a.steps, 5))
+    desc_bytes = 8 * (len(spec.S) * 4 + len(spec.bonds) * 14) + 16 * R
+    barrier_max(0.0)
+    t0 = time.time()
+    for _ in range(e2e_steps):
+        idx, rows, _ = scan.run_points(spec, 3, ladder(R * world), np.zeros(R * world), 0, a.sweeps, precision=32, seed=1,
+                                       rank=rank, world=world, device=local)
+    e2e_t = barrier_max(time.time() - t0)
+    e2e = {"value": world * R * N * a.sweeps * e2e_steps / e2e_t, "unit": "attempts/s", "h2d_bytes_per_step": desc_bytes,
+           "d2h_bytes_per_step": int(rows.nbytes),
+           "what": "scan.run_points(): create system from host descriptor, init, %d measured sweeps, result rows to host, destroy; "
+                   "host wall clock, max over ranks" % a.sweeps}
+
+    if rank == 0:
+        line = {"metric": "attempted Metropolis spin updates per second", "value": value, "unit": "attempts/s", "n_gpus": world,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_max / a.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(a, world), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roof, "cpu_baseline": cpu, "host_wall_s": wall,
+                "check": {"replica0_T": float(Ts[0]), "e_per_site_over_kT": float(out0[8]), "U4": float(out0[10])}}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

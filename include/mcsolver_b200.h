@@ -152,6 +152,14 @@ MCG_API int mcg_reset_measurements(mcg_system *sys);
 MCG_API int mcg_results(mcg_system *sys, int replica, double *out, double *groupOut);
 MCG_API int mcg_counters(mcg_system *sys, int replica, int64_t *attempts, int64_t *accepted, int64_t *cluster_sites);
 
+/* ---- instrumentation (bench.py) ----
+ * mcg_launch_count: kernels this system has launched so far.
+ * mcg_profile_passes(on): bracket every Metropolis colour-pass launch with CUDA events on the launch stream;
+ * mcg_profile_read: total device time (ms) and number of the bracketed launches since the last read. */
+MCG_API int mcg_launch_count(mcg_system *sys, int64_t *launches);
+MCG_API int mcg_profile_passes(mcg_system *sys, int on);
+MCG_API int mcg_profile_read(mcg_system *sys, double *total_ms, int64_t *nlaunches);
+
 /* ---- the whole MCMainFunction loop on the resident system ----
  * thermalise nthermal intervals, then nsweep x (ninterval updates + measurement).
  * Metropolis: ninterval >= N -> round(ninterval/N) sweeps per interval, else one sweep with

@@ -63,6 +63,9 @@ SIGNATURES = {
     "mcg_reset_measurements": (_i, [_vp]),
     "mcg_results": (_i, [_vp, _i, _vp, _vp]),
     "mcg_counters": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "mcg_launch_count": (_i, [_vp, _vp]),
+    "mcg_profile_passes": (_i, [_vp, _i]),
+    "mcg_profile_read": (_i, [_vp, _vp, _vp]),
     "mcg_run": (_i, [_vp, _i, _i64, _i64, _i64, _i, _vp]),
     "mcg_run_on": (_i, [C.POINTER(Tables), _i, _i64, _i64, _i64, _d, _d, _i, _u64, _i, _vp, _vp, _vp]),
     "mcg_run_ising": (_i, [C.POINTER(Tables), _i, _i64, _i64, _i64, _d, _i, _u64, _i, _vp, _vp]),

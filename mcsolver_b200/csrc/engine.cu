@@ -255,7 +255,7 @@ static void init_spins(mcg_system *s, double flunc) {
     if (s->structured) { structured_init_spins(s, flunc); return; }
     GenArgs a = gen_args(s);
     dispatch(s, [&]<int NC, typename real, bool FJ>() {
-        k_init_generic<NC, real><<<grid_for(s->N, s->R), 256, 0, s->stream>>>(a, s->d_signS, flunc);
+        s->launches++; k_init_generic<NC, real><<<grid_for(s->N, s->R), 256, 0, s->stream>>>(a, s->d_signS, flunc);
     });
     MCG_CUDA(cudaGetLastError());
 }
@@ -267,7 +267,7 @@ static void set_spins(mcg_system *s, int r, const double *spins) {
     MCG_CUDA(cudaMemcpyAsync(s->d_scratch, spins, n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
     GenArgs a = gen_args(s);
     dispatch(s, [&]<int NC, typename real, bool FJ>() {
-        k_scatter_frame<NC, real><<<grid_for(s->N, 1), 256, 0, s->stream>>>(a, r, s->d_scratch);
+        s->launches++; k_scatter_frame<NC, real><<<grid_for(s->N, 1), 256, 0, s->stream>>>(a, r, s->d_scratch);
     });
     MCG_CUDA(cudaGetLastError());
     MCG_CUDA(cudaStreamSynchronize(s->stream));
@@ -279,7 +279,7 @@ static void get_spins(mcg_system *s, int r, double *spins) {
     size_t n = (size_t)s->N * (s->NC == 1 ? 1 : 3);
     GenArgs a = gen_args(s);
     dispatch(s, [&]<int NC, typename real, bool FJ>() {
-        k_gather_frame<NC, real><<<grid_for(s->N, 1), 256, 0, s->stream>>>(a, r, s->d_scratch);
+        s->launches++; k_gather_frame<NC, real><<<grid_for(s->N, 1), 256, 0, s->stream>>>(a, r, s->d_scratch);
     });
     MCG_CUDA(cudaGetLastError());
     MCG_CUDA(cudaMemcpyAsync(spins, s->d_scratch, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
@@ -291,16 +291,17 @@ static void launch_measure_sums(mcg_system *s, int siteRep, double *eb, double *
     if (s->structured) { structured_measure_sums(s); return; }
     GenArgs a = gen_args(s);
     dispatch(s, [&]<int NC, typename real, bool FJ>() {
-        k_measure_generic<NC, real, FJ><<<grid_for(s->N, s->R), 256, 0, s->stream>>>(a, s->d_mi, s->d_mj, s->d_sums, siteRep, eb, eo);
+        s->launches += 2; k_measure_generic<NC, real, FJ><<<grid_for(s->N, s->R), 256, 0, s->stream>>>(a, s->d_mi, s->d_mj, s->d_sums, siteRep, eb, eo);
         k_pairs_generic<NC, real><<<grid_for(s->nLat, s->R), 256, 0, s->stream>>>(s->N, s->nLat, s->d_pairs, s->d_spin, s->d_sums);
         if constexpr (NC == 3)
-            if (s->nTri > 0) k_topo_generic<real><<<grid_for(s->nTri, s->R), 256, 0, s->stream>>>(a, s->nTri, s->d_tri, s->d_sums);
+            if (s->nTri > 0) s->launches++, k_topo_generic<real><<<grid_for(s->nTri, s->R), 256, 0, s->stream>>>(a, s->nTri, s->d_tri, s->d_sums);
     });
     MCG_CUDA(cudaGetLastError());
 }
 
 static void measure(mcg_system *s) {
     launch_measure_sums(s, -1, nullptr, nullptr);
+    s->launches++;
     k_finalize_sweep<<<(s->R + 63) / 64, 64, 0, s->stream>>>(s->model, s->R, s->N, s->nLat, s->d_sums, s->d_acc);
     MCG_CUDA(cudaGetLastError());
 }
@@ -332,9 +333,13 @@ static void metropolis_sweeps(mcg_system *s, int64_t n, double pAtt) {
         for (int c = 0; c < s->C; c++) {
             int cb = s->colourStart[c], ce = s->colourStart[c + 1];
             if (ce == cb) continue;
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            if (s->profilePasses) { MCG_CUDA(cudaEventCreate(&e0)); MCG_CUDA(cudaEventCreate(&e1)); MCG_CUDA(cudaEventRecord(e0, s->stream)); }
+            s->launches++;
             dispatch(s, [&]<int NC, typename real, bool FJ>() {
                 k_metro_generic<NC, real, FJ><<<grid_for(ce - cb, s->R), 256, 0, s->stream>>>(a, cb, ce, s->sweepCtr, (real)pAtt);
             });
+            if (s->profilePasses) { MCG_CUDA(cudaEventRecord(e1, s->stream)); s->passEvents.emplace_back(e0, e1); }
         }
         s->sweepCtr++;
     }
@@ -355,6 +360,7 @@ static void wolff_steps(mcg_system *s, int64_t n) {
     dim3 g = grid_for(s->N, s->R);
     for (int64_t it = 0; it < n; it++) {
         w.step = s->wolffCtr++;
+        s->launches += 5;
         dispatch(s, [&]<int NC, typename real, bool FJ>() {
             k_wolff_init<NC, real><<<g, 256, 0, s->stream>>>(a, w);
             k_wolff_bonds<NC, real, FJ><<<g, 256, 0, s->stream>>>(a, w);
@@ -400,6 +406,7 @@ static void run(mcg_system *s, int algorithm, int64_t nthermal, int64_t nsweep, 
             iFrame++;
         }
         if (fused) {
+            s->launches++;
             k_finalize_sweep<<<(s->R + 63) / 64, 64, 0, s->stream>>>(s->model, s->R, s->N, s->nLat, s->d_sums, s->d_acc);
             MCG_CUDA(cudaGetLastError());
         } else measure(s);
@@ -541,6 +548,7 @@ MCG_API int mcg_timed_sweeps(mcg_system *sys, int64_t nsweeps, double pAttempt, 
             for (int64_t i = 0; i < nsweeps; i++) {
                 if (sys->structured) {
                     structured_sweeps(sys, 1, pAttempt, true);
+                    sys->launches++;
                     k_finalize_sweep<<<(sys->R + 63) / 64, 64, 0, sys->stream>>>(sys->model, sys->R, sys->N, sys->nLat, sys->d_sums, sys->d_acc);
                 } else {
                     metropolis_sweeps(sys, 1, pAttempt);
@@ -582,6 +590,30 @@ MCG_API int mcg_counters(mcg_system *sys, int replica, int64_t *attempts, int64_
         if (attempts) *attempts = (int64_t)c[CNT_ATTEMPT];
         if (accepted) *accepted = (int64_t)c[CNT_ACCEPT];
         if (cluster_sites) *cluster_sites = (int64_t)c[CNT_CLUSTER];
+    });
+}
+
+MCG_API int mcg_launch_count(mcg_system *sys, int64_t *launches) {
+    return guarded([&] { MCG_REQUIRE(sys && launches, "NULL argument"); *launches = (int64_t)sys->launches; });
+}
+MCG_API int mcg_profile_passes(mcg_system *sys, int on) {
+    return guarded([&] { MCG_REQUIRE(sys, "system is NULL"); sys->profilePasses = on != 0; });
+}
+MCG_API int mcg_profile_read(mcg_system *sys, double *total_ms, int64_t *nlaunches) {
+    SYS_GUARD({
+        MCG_REQUIRE(total_ms && nlaunches, "NULL argument");
+        MCG_CUDA(cudaStreamSynchronize(sys->stream));
+        double tot = 0;
+        for (auto &pr : sys->passEvents) {
+            float ms = 0;
+            MCG_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+            tot += ms;
+            cudaEventDestroy(pr.first);
+            cudaEventDestroy(pr.second);
+        }
+        *total_ms = tot;
+        *nlaunches = (int64_t)sys->passEvents.size();
+        sys->passEvents.clear();
     });
 }
 

@@ -635,6 +635,7 @@ template <typename F> static void sdispatch(const mcg_system *s, F &&f) {
 void structured_init_spins(mcg_system *s, double flunc) {
     StructArgs a = struct_args(s);
     dim3 g((s->N + 255) / 256, s->R);
+    s->launches++;
     sdispatch(s, [&]<int NC, typename real, bool FJ>() { k_struct_init<NC, real><<<g, 256, 0, s->stream>>>(a, flunc); });
     MCG_CUDA(cudaGetLastError());
 }
@@ -649,6 +650,7 @@ void structured_set_spins(mcg_system *s, int r, const double *spins) {
     double *buf = stage(s);
     size_t n = (size_t)s->N * (s->NC == 1 ? 1 : 3);
     MCG_CUDA(cudaMemcpyAsync(buf, spins, n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    s->launches++;
     sdispatch(s, [&]<int NC, typename real, bool FJ>() { k_struct_frame<NC, real, false><<<(s->N + 255) / 256, 256, 0, s->stream>>>(a, r, buf); });
     MCG_CUDA(cudaGetLastError());
     MCG_CUDA(cudaStreamSynchronize(s->stream));
@@ -658,6 +660,7 @@ void structured_get_spins(mcg_system *s, int r, double *spins) {
     StructArgs a = struct_args(s);
     double *buf = stage(s);
     size_t n = (size_t)s->N * (s->NC == 1 ? 1 : 3);
+    s->launches++;
     sdispatch(s, [&]<int NC, typename real, bool FJ>() { k_struct_frame<NC, real, true><<<(s->N + 255) / 256, 256, 0, s->stream>>>(a, r, buf); });
     MCG_CUDA(cudaGetLastError());
     MCG_CUDA(cudaMemcpyAsync(spins, buf, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
@@ -690,25 +693,33 @@ template <int MODE> static void launch_pass(mcg_system *s, int colour, uint64_t 
     int rowsPerBlock = by * iters;
     int nrb = (st->nrows + rowsPerBlock - 1) / rowsPerBlock;
     dim3 block(bx, by), grid((unsigned)(s->R * nrb * nqc));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    const bool prof = s->profilePasses && MODE != 2;
+    if (prof) { MCG_CUDA(cudaEventCreate(&e0)); MCG_CUDA(cudaEventCreate(&e1)); MCG_CUDA(cudaEventRecord(e0, s->stream)); }
+    s->launches++;
     sdispatch(s, [&]<int NC, typename real, bool FJ>() {
         if (st->V == 1) k_struct<NC, real, FJ, MODE, 1><<<grid, block, 0, s->stream>>>(a, q0, nqc, rowsPerBlock, nrb, sweep, (real)pAtt);
         else if constexpr (sizeof(real) == 4) k_struct<NC, real, FJ, MODE, 4><<<grid, block, 0, s->stream>>>(a, q0, nqc, rowsPerBlock, nrb, sweep, (real)pAtt);
         else k_struct<NC, real, FJ, MODE, 2><<<grid, block, 0, s->stream>>>(a, q0, nqc, rowsPerBlock, nrb, sweep, (real)pAtt);
     });
+    if (prof) { MCG_CUDA(cudaEventRecord(e1, s->stream)); s->passEvents.emplace_back(e0, e1); }
 }
 
 static void fold_and_extras(mcg_system *s) {
     StructuredSystem *st = s->st;
     StructArgs a = struct_args(s);
+    s->launches++;
     k_struct_fold<<<(s->R + 63) / 64, 64, 0, s->stream>>>(a, s->R, st->pair_s, st->pair_t, st->selfPairs ? 1 : 0, (double)s->nLat, s->d_sums);
     if (!st->selfPairs) {
         dim3 g((s->nLat + 255) / 256, s->R);
+        s->launches++;
         sdispatch(s, [&]<int NC, typename real, bool FJ>() {
             k_struct_pairs<NC, real><<<g, 256, 0, s->stream>>>(a, st->pair_s, st->pair_t, st->pair_d[0], st->pair_d[1], st->pair_d[2], s->d_sums);
         });
     }
     if (st->ncircuit > 0 && s->NC == 3) {
         dim3 g((s->nTri + 255) / 256, s->R);
+        s->launches++;
         if (s->prec == 64) k_struct_topo<double><<<g, 256, 0, s->stream>>>(a, st->ncircuit, st->d_circuits, s->d_sums);
         else k_struct_topo<float><<<g, 256, 0, s->stream>>>(a, st->ncircuit, st->d_circuits, s->d_sums);
     }

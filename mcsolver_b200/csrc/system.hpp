@@ -65,6 +65,10 @@ struct mcg_system {
     double *d_wres = nullptr;            // [R][2] residual, cluster size
     std::vector<double> beta_host, field_host;
     cudaStream_t stream = nullptr;
+    // instrumentation: kernels launched so far; optional CUDA-event timing of the colour-pass kernel
+    uint64_t launches = 0;
+    bool profilePasses = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> passEvents;
     mcg::StructuredSystem *st = nullptr;   // structured (descriptor) path state, owned
     size_t real_size() const { return prec == 32 ? 4 : 8; }
     ~mcg_system();

@@ -210,6 +210,20 @@ class System:
         check(_ffi.lib().mcg_timed_sweeps(self._h, int(n), float(p_attempt), int(bool(with_measure)), C.byref(ms)))
         return ms.value
 
+    def launch_count(self):
+        n = C.c_int64(0)
+        check(_ffi.lib().mcg_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def profile_passes(self, on=True):
+        check(_ffi.lib().mcg_profile_passes(self._h, int(bool(on))))
+
+    def profile_read(self):
+        """(total device ms, launches) of the colour-pass kernel since the last read."""
+        ms, n = C.c_double(0), C.c_int64(0)
+        check(_ffi.lib().mcg_profile_read(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def wolff_steps(self, n):
         check(_ffi.lib().mcg_wolff_steps(self._h, int(n)))
 

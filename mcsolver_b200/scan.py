@@ -1,0 +1,71 @@
+"""(T,H) grid scans on the GPU: the data-parallel axis of the reference, batched.
+
+What it replaces: `win.py:75-144` builds one task per (H,T) point and farms them over a
+`multiprocessing.Pool`, one forked process (and one full Python lattice object graph) per point.
+Here every point is a replica of ONE resident system: all points of a GPU advance in the same
+kernel launches (replica = a grid dimension), sharing the lattice tables; with several GPUs the
+points are sharded over ranks with no data-path collective - only the final result
+rows are gathered by the caller.
+
+Couplings are passed UNSCALED; replica r uses beta_r = 1/max(T_r, 0.1) (mcMain.py:21) and field H_r.
+"""
+import numpy as np
+
+from . import engine
+
+
+def shard(n_points, rank, world):
+    """Contiguous block partition of the grid points over ranks (PT neighbours stay local)."""
+    base, rem = divmod(n_points, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def run_points(spec, model, T, H, nthermal, nsweep, ninterval=0, algorithm=engine.METROPOLIS, precision=32, seed=1,
+               rank=0, world=1, device=-1, flunc=0.0, spin_frames=0, tables=False):
+    """Run the points (T[i], H[i]) owned by `rank` and return (indices, results[n,27|10], frames).
+
+    spec: LatticeSpec (bond templates + supercell).  ninterval<=0 means N (mcMain.py:145).
+    tables=True forces the table-driven engine (needed for Wolff); default is the structured path.
+    Result rows have the reference's tuple layout with E, E2 still in beta units (caller rescales
+    exactly as mcMain.py:251 does)."""
+    T = np.atleast_1d(np.asarray(T, dtype=float))
+    H = np.atleast_1d(np.asarray(H, dtype=float))
+    if T.shape != H.shape:
+        raise ValueError("T and H must list the grid points pairwise")
+    lo, hi = shard(T.size, rank, world)
+    idx = np.arange(lo, hi)
+    if idx.size == 0:
+        return idx, np.zeros((0, 10 if model == engine.ISING else 27)), None
+    Tl = np.maximum(T[lo:hi], 0.1)
+    beta, field = 1.0 / Tl, H[lo:hi]
+    N = spec.nsite
+    nint = N if ninterval <= 0 else int(ninterval)
+    if tables or algorithm == engine.WOLFF:
+        from .lattice import build_tables
+        t = build_tables(spec, 1.0, model)     # unscaled tables, beta per replica
+        sysm = engine.System.from_tables(t, precision=precision, nReplica=idx.size, beta=beta, field=field, seed=seed,
+                                         replica_offset=lo, device=device)
+    else:
+        sysm = engine.System.from_spec(spec, model, precision=precision, nReplica=idx.size, beta=beta, field=field,
+                                       seed=seed, replica_offset=lo, device=device)
+    with sysm as s:
+        s.init_spins(flunc)
+        frames = s.run(algorithm, nthermal, nsweep, nint, spinFrame=spin_frames)
+        out = np.stack([s.results(r)[0] for r in range(idx.size)])
+    return idx, out, frames
+
+
+def observables(rows, T, N, model):
+    """Post-processing of win.py:133-143 / mcMain.py:250-257 on result rows (beta units -> K)."""
+    rows = np.asarray(rows, dtype=float)
+    T = np.maximum(np.asarray(T, dtype=float), 0.1)
+    if model == engine.ISING:
+        si, sj, sij, auto, E, E2, U4 = rows[:, 0], rows[:, 1], rows[:, 2], rows[:, 3], rows[:, 4] * T, rows[:, 5] * T ** 2, rows[:, 8]
+        return dict(Si=si, Sj=sj, Susc=(sij - si * sj) / T, Energy=E, Capacity=(E2 - E * E) / T ** 2 * N, TopoQ=np.zeros_like(E),
+                    U4=U4, AutoCorr=auto)
+    si, sj = rows[:, 0:3], rows[:, 3:6]
+    E, E2 = rows[:, 8] * T, rows[:, 9] * T ** 2
+    return dict(Si=np.linalg.norm(si, axis=1), Sj=np.linalg.norm(sj, axis=1),
+                Susc=(rows[:, 6] - np.sum(si * sj, axis=1)) / T, Energy=E, Capacity=(E2 - E * E) / T ** 2 * N,
+                TopoQ=rows[:, 26], U4=rows[:, 10], AutoCorr=rows[:, 7])
