@@ -118,6 +118,9 @@ MCG_API int mcg_device_count(int *count);
 MCG_API int mcg_create_tables(const mcg_tables *t, const mcg_config *cfg, mcg_system **out);
 MCG_API int mcg_create_lattice(const mcg_lattice_desc *d, const mcg_config *cfg, mcg_system **out);
 MCG_API int mcg_destroy(mcg_system *sys);
+/* Host-only: build the colouring/class tables of a descriptor and compile its specialised colour-pass
+ * kernels with NVRTC for sm_100a (no GPU needed).  ncompiled = kernels modules built (one per colour). */
+MCG_API int mcg_jit_check(const mcg_lattice_desc *d, int precision, int *ncompiled, char *report, int report_len);
 MCG_API int mcg_num_colours(const mcg_system *sys, int *ncolours);
 MCG_API int mcg_colour_order(const mcg_system *sys, int32_t *order /*[N] site ids, colour-major*/);
 MCG_API int mcg_set_params(mcg_system *sys, const double *beta, const double *field); /* per replica */

@@ -49,6 +49,7 @@ SIGNATURES = {
     "mcg_create_tables": (_i, [C.POINTER(Tables), C.POINTER(Config), C.POINTER(_vp)]),
     "mcg_create_lattice": (_i, [C.POINTER(LatticeDesc), C.POINTER(Config), C.POINTER(_vp)]),
     "mcg_destroy": (_i, [_vp]),
+    "mcg_jit_check": (_i, [C.POINTER(LatticeDesc), _i, _vp, _vp, _i]),
     "mcg_num_colours": (_i, [_vp, _vp]),
     "mcg_colour_order": (_i, [_vp, _vp]),
     "mcg_set_params": (_i, [_vp, _vp, _vp]),

@@ -26,8 +26,11 @@ def _newest_source():
 
 
 def build(force=False, verbose=False):
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_source():
+    newest = _newest_source()
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest:
         return LIB
+    headers_t = max([os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC) if not f.endswith(".cu")] +
+                    [os.path.getmtime(os.path.join(os.path.dirname(HERE), "include", "mcsolver_b200.h"))])
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
     logs = []
@@ -39,6 +42,8 @@ def build(force=False, verbose=False):
             continue
         obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
         objs.append(obj)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(sp), headers_t):
+            continue
         cmd = [nvcc] + NVCC_FLAGS + ["-c", sp, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
@@ -47,8 +52,10 @@ def build(force=False, verbose=False):
         if p.returncode != 0:
             sys.stderr.write(out)
             raise RuntimeError("nvcc failed on %s" % src)
-    with open(os.path.join(HERE, "build", "ptxas.log"), "w") as f:
-        f.write("\n".join(logs))
+    for log in logs:
+        name = log.split("==")[1].strip()
+        with open(os.path.join(HERE, "build", "ptxas_%s.log" % name.replace(".cu", "")), "w") as f:
+            f.write(log)
     if verbose:
         print("\n".join(logs))
     cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart_static", "-ldl", "-lrt", "-lpthread"]

@@ -1,0 +1,130 @@
+// Device-side maths shared by every kernel; free of host/std includes so NVRTC can compile it.
+#pragma once
+#include "rng.cuh"
+
+namespace mcg {
+
+// heisenbergLib.c:6 - the reference's truncated PI (Q = sum(area)/(4*PI) is off-integer by ~3e-11)
+#define MCG_REF_PI 3.1415926535
+
+// indices of the per-sweep raw sums (per replica)
+enum { SUM_TOT = 0, SUM_E = 3, SUM_SI = 4, SUM_SJ = 7, SUM_SIJ = 10, SUM_AREA = 11, NSUM = 12 };
+// accumulators over measured sweeps (per replica) - mirrors the locals of heisenbergLib.c:624-642
+enum {
+    ACC_SI = 0, ACC_SJ = 3, ACC_SIJ = 6, ACC_E = 7, ACC_E2 = 8, ACC_M2 = 9, ACC_M4 = 10, ACC_MTMP = 11, ACC_MDOTM = 12,
+    ACC_MTOT = 13, ACC_SIZ = 14, ACC_SJZ = 15, ACC_STZ = 16, ACC_SIH = 17, ACC_SJH = 18, ACC_STH = 19, ACC_Q = 20,
+    ACC_NMEAS = 21, ACC_STOT = 22, ACC_LASTE = 23, ACC_SIR = 24, ACC_SJR = 27, ACC_SIJR = 30, ACC_ER = 31, ACC_E2R = 32,
+    NACC = 40
+};
+enum { CNT_ATTEMPT = 0, CNT_ACCEPT = 1, CNT_CLUSTER = 2, CNT_WSTEPS = 3, NCNT = 4 };
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum NV per-thread doubles over the block and atomically add the block totals to dst[0..NV).
+// smem: at least NV*32 doubles.  All threads of the block must call it.
+template <int NV>
+__device__ __forceinline__ void block_accumulate(double (&v)[NV], double *dst, double *smem) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        double s = warp_sum(v[i]);
+        if (lane == 0) smem[i * 32 + w] = s;
+    }
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+            double s = lane < nw ? smem[i * 32 + lane] : 0.0;
+            s = warp_sum(s);
+            if (lane == 0 && s != 0.0) atomicAdd(dst + i, s);
+        }
+    }
+    __syncthreads();
+}
+
+template <typename real> __device__ __forceinline__ real r_sqrt(real x);
+template <> __device__ __forceinline__ float r_sqrt<float>(float x) { return sqrtf(x); }
+template <> __device__ __forceinline__ double r_sqrt<double>(double x) { return sqrt(x); }
+template <typename real> __device__ __forceinline__ real r_rsqrt(real x);
+template <> __device__ __forceinline__ float r_rsqrt<float>(float x) { return rsqrtf(x); }
+template <> __device__ __forceinline__ double r_rsqrt<double>(double x) { return 1.0 / sqrt(x); }
+// exp(-x) for the Metropolis test.  fp32: ex2.approx (rel. err ~2^-21); fp64: libdevice exp
+template <typename real> __device__ __forceinline__ real r_exp(real x);
+template <> __device__ __forceinline__ float r_exp<float>(float x) { return __expf(x); }
+template <> __device__ __forceinline__ double r_exp<double>(double x) { return exp(x); }
+// sin/cos of 2*pi*u, u in (0,1)
+template <typename real> __device__ __forceinline__ void r_sincos2pi(real u, real &s, real &c);
+template <> __device__ __forceinline__ void r_sincos2pi<float>(float u, float &s, float &c) {
+    // argument folded to (-pi,pi) where the MUFU approximations are accurate to ~5e-7 absolute
+    __sincosf(6.283185307179586f * (u - 0.5f), &s, &c);
+    s = -s; c = -c;
+}
+template <> __device__ __forceinline__ void r_sincos2pi<double>(double u, double &s, double &c) { sincospi(2.0 * u, &s, &c); }
+
+// proposal direction from two Philox words: uniform on S^2 (NC=3) / S^1 (NC=2)
+template <int NC, typename real>
+__device__ __forceinline__ void random_dir(uint32_t w0, uint32_t w1, real (&n)[3]) {
+    if (NC == 3) {
+        real z = real(2) * u01<real>(w0) - real(1);
+        real sn, cs;
+        r_sincos2pi<real>(u01<real>(w1), sn, cs);
+        real rr = r_sqrt<real>(fmax(real(0), real(1) - z * z));
+        n[0] = rr * cs; n[1] = rr * sn; n[2] = z;
+    } else {
+        real sn, cs;
+        r_sincos2pi<real>(u01<real>(w0), sn, cs);
+        n[0] = cs; n[1] = sn; n[2] = real(0);
+    }
+}
+
+// local field of one link: H += J . s_nb   (J flat order xx,yy,zz,xy,xz,yz,yx,zx,zy; XY uses 0,1,3,6)
+template <int NC, typename real, bool FULLJ>
+__device__ __forceinline__ void add_field(real (&H)[3], const real *__restrict__ J, const real (&t)[3]) {
+    if (NC == 1) {
+        H[0] += J[0] * t[0];
+    } else if (NC == 2) {
+        if (FULLJ) {
+            H[0] += J[0] * t[0] + J[3] * t[1];
+            H[1] += J[6] * t[0] + J[1] * t[1];
+        } else {
+            H[0] += J[0] * t[0];
+            H[1] += J[1] * t[1];
+        }
+    } else {
+        if (FULLJ) {
+            H[0] += J[0] * t[0] + J[3] * t[1] + J[4] * t[2];
+            H[1] += J[6] * t[0] + J[1] * t[1] + J[5] * t[2];
+            H[2] += J[7] * t[0] + J[8] * t[1] + J[2] * t[2];
+        } else {
+            H[0] += J[0] * t[0];
+            H[1] += J[1] * t[1];
+            H[2] += J[2] * t[2];
+        }
+    }
+}
+
+// on-site energy  sum_a D_a s_a^2 - h s_axis   (getOnsiteEnergy heisenbergLib.c:249-253, xyLib.c:200-204)
+template <int NC, typename real>
+__device__ __forceinline__ real onsite_energy(const real (&s)[3], const real *__restrict__ D, real beta, real hf) {
+    if (NC == 1) return -hf * s[0];
+    real e = D[0] * s[0] * s[0] + D[1] * s[1] * s[1];
+    if (NC == 3) e += D[2] * s[2] * s[2];
+    return beta * e - hf * (NC == 3 ? s[2] : s[0]);
+}
+
+// n.J.n for the Wolff bond weight (heisenbergLib.c:355: diagonalDot(ref,ref,J))
+template <int NC, typename real, bool FULLJ>
+__device__ __forceinline__ real quad_form(const real *__restrict__ J, const real (&a)[3], const real (&b)[3]) {
+    real H[3] = {0, 0, 0};
+    add_field<NC, real, FULLJ>(H, J, b);
+    real r = a[0] * H[0];
+    if (NC >= 2) r += a[1] * H[1];
+    if (NC == 3) r += a[2] * H[2];
+    return r;
+}
+
+}  // namespace mcg

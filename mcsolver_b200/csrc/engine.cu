@@ -68,7 +68,7 @@ static GenArgs gen_args(const mcg_system *s) {
     a.N = s->N; a.maxL = s->maxL; a.R = s->R; a.nJ = s->nJ; a.ncls = s->ncls;
     a.nbrp = s->d_nbrp; a.jtype = s->d_jtype; a.Jtab = s->d_Jtab; a.cls = s->d_cls; a.clsS = s->d_clsS; a.clsD = s->d_clsD;
     a.site_of = s->d_site_of; a.spin = s->d_spin; a.beta = s->d_beta; a.field = s->d_field; a.cnt = s->d_cnt;
-    a.key.k0 = (uint32_t)s->seed; a.key.k1 = (uint32_t)(s->seed >> 32);
+    a.key = make_rng_key(s->seed);
     a.replica0 = s->replica0;
     return a;
 }
@@ -491,6 +491,17 @@ MCG_API int mcg_create_lattice(const mcg_lattice_desc *d, const mcg_config *cfg,
         alloc_replica_state(sys.get(), cfg);
         MCG_CUDA(cudaStreamCreateWithFlags(&sys->stream, cudaStreamNonBlocking));
         *out = sys.release();
+    });
+}
+
+MCG_API int mcg_jit_check(const mcg_lattice_desc *d, int precision, int *ncompiled, char *report, int report_len) {
+    return guarded([&] {
+        MCG_REQUIRE(d && ncompiled, "NULL argument");
+        MCG_REQUIRE(precision == 32 || precision == 64, "precision must be 32 or 64");
+        std::string rep;
+        *ncompiled = structured_jit_check(d, precision, rep);
+        if (report && report_len > 0) { std::strncpy(report, rep.c_str(), report_len - 1); report[report_len - 1] = 0; }
+        if (*ncompiled < 0) throw Error(MCG_ERR_STATE, "NVRTC compilation failed: " + rep);
     });
 }
 

@@ -8,48 +8,64 @@
 // storage position) the stream of a site is independent of the colouring, the memory layout and
 // the number of GPUs.  oracle/oracle.c (rng4) restates exactly this layout for the checker.
 #pragma once
+#ifdef __CUDACC_RTC__
+typedef unsigned int uint32_t;
+typedef int int32_t;
+typedef unsigned long long uint64_t;
+typedef long long int64_t;
+#else
 #include <cstdint>
+#endif
 
 namespace mcg {
 
 enum : uint32_t { STREAM_METRO = 0, STREAM_INIT = 1, STREAM_WBOND = 2, STREAM_WSEED = 3, STREAM_PT = 4 };
 
+// The ten Philox round keys (k + r*W) of the 64-bit seed, computed once on the host: the kernels read
+// them straight from the constant bank (kernel parameter) as LOP3 operands - zero instructions per
+// attempt instead of 20 integer adds (profiles/r01).
 struct RngKey {
-    uint32_t k0, k1;   // seed
+    uint32_t rk[10][2];
 };
+__host__ __device__ __forceinline__ RngKey make_rng_key(uint64_t seed) {
+    RngKey k;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; r++) { k.rk[r][0] = k0; k.rk[r][1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+    return k;
+}
 
-__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                                       uint32_t k1, uint32_t (&out)[4]) {
-    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const RngKey &key,
+                                                       uint32_t (&out)[4]) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
 #pragma unroll
     for (int r = 0; r < 10; r++) {
-#ifdef __CUDA_ARCH__
-        uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
-        uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
-#else
+        // one IMAD.WIDE.U32 per product on the device
         uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
         uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
-#endif
-        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        uint32_t n0 = hi1 ^ c1 ^ key.rk[r][0], n2 = hi0 ^ c3 ^ key.rk[r][1];
         c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-        k0 += W0; k1 += W1;   // uniform across the grid: folded into immediates / uniform registers
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-__host__ __device__ __forceinline__ void rng4(RngKey key, uint32_t replica, uint32_t stream, uint32_t sub, uint64_t sweep,
+__host__ __device__ __forceinline__ void rng4(const RngKey &key, uint32_t replica, uint32_t stream, uint32_t sub, uint64_t sweep,
                                               uint32_t site, uint32_t (&out)[4]) {
     philox4x32_10(site, (uint32_t)sweep, (uint32_t)((sweep >> 32) & 0xFFFFu) | (sub << 16) | (stream << 24), replica,
-                  key.k0, key.k1, out);
+                  key, out);
 }
 
-// uniforms strictly inside (0,1): fp64 uses all 32 bits, fp32 the top 24 (exactly representable)
+// uniforms strictly inside (0,1): fp64 uses all 32 bits: (r+0.5)/2^32; fp32 the top 23 bits:
+// (k+0.5)/2^23 with k = r>>9, built without an int->float conversion: 1.mantissa - (1 - 2^-24), exact.
 template <typename real> __host__ __device__ __forceinline__ real u01(uint32_t r);
 template <> __host__ __device__ __forceinline__ double u01<double>(uint32_t r) {
     return ((double)r + 0.5) * (1.0 / 4294967296.0);
 }
 template <> __host__ __device__ __forceinline__ float u01<float>(uint32_t r) {
-    return ((float)(r >> 8) + 0.5f) * (1.0f / 16777216.0f);
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(0x3f800000u | (r >> 9)) - 0.99999994f;   // 0.99999994f == 1 - 2^-24 exactly
+#else
+    return ((float)(r >> 9) + 0.5f) * (1.0f / 8388608.0f);
+#endif
 }
 
 }  // namespace mcg

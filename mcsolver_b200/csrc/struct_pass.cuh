@@ -1,0 +1,362 @@
+// The Metropolis colour-pass kernel of the structured path, written once and compiled twice:
+//
+//  * OFFLINE (nvcc, this header included by structured.cu): lattice dimensions and the colour's
+//    link table are runtime values; the table travels as a __grid_constant__ kernel parameter.
+//  * JIT (NVRTC at system creation, -DMCG_JIT + a generated prologue): the lattice IS the program.
+//    Supercell dims, class coordinates, per-link cell offsets, wrap masks, Z shifts and the exchange
+//    tensors are literals; the link loop is unrolled at compile time (no table loads, no index
+//    multiplies by runtime strides, no branches on the link kind, FFMA with immediate J).
+//    profiles/r01: the offline kernel spent ~150 of its ~315 instructions per attempt on exactly
+//    that bookkeeping and was issue-bound at 1/3 of the HBM roofline.
+//
+// Must stay free of host/std includes (NVRTC).  Arithmetic is identical in both builds.
+#pragma once
+#include "devmath.cuh"
+
+namespace mcg {
+
+constexpr int MAXLINK = 32;
+
+struct SLinkD {
+    int qn;          // neighbour class
+    int cX, cY;      // coarse offsets, already reduced to [0,Xd) / [0,Yd)
+    int cZ;          // coarse Z offset in (-Zd/2, Zd/2]
+    int low;         // neighbour class has a lower colour (its spins are final in this sweep)
+    int self;        // link to the site itself (supercell dimension 1)
+};
+struct SClassD {
+    int a, b, c, o, colour, nlink, lowmode, pad;
+    double S, D[3];
+};
+
+struct StructArgs {
+    int Xd, Yd, Zd, Zc, ncellc, nclass, nrows, N;
+    int px, py, pz, norb, Lx, Ly, Lz;
+    const SClassD *classes;
+    const SLinkD *links;
+    const void *J;
+    const int *classOf;
+    void *spin;
+    const double *beta, *field;
+    unsigned long long *cnt;
+    double *classSums;
+    RngKey key;
+    uint32_t replica0;
+};
+
+template <typename real, int V> struct Vec;
+template <> struct Vec<float, 4> { typedef float4 type; };
+template <> struct Vec<float, 1> { typedef float type; };
+template <> struct Vec<double, 2> { typedef double2 type; };
+template <> struct Vec<double, 1> { typedef double type; };
+
+template <typename real, int V> __device__ __forceinline__ void vload(const real *__restrict__ p, real (&o)[V]) {
+    typedef typename Vec<real, V>::type VT;
+    VT v = *reinterpret_cast<const VT *>(p);
+    const real *e = reinterpret_cast<const real *>(&v);
+#pragma unroll
+    for (int i = 0; i < V; i++) o[i] = e[i];
+}
+template <typename real, int V> __device__ __forceinline__ void vstore(real *__restrict__ p, const real (&o)[V]) {
+    typedef typename Vec<real, V>::type VT;
+    VT v;
+    real *e = reinterpret_cast<real *>(&v);
+#pragma unroll
+    for (int i = 0; i < V; i++) e[i] = o[i];
+    *reinterpret_cast<VT *>(p) = v;
+}
+
+// V consecutive cells of a neighbour row, shifted by cZ cells with periodic wrap
+template <typename real, int V>
+__device__ __forceinline__ void load_shifted(const real *__restrict__ row, int Z0, int cZ, int Zd, real (&o)[V]) {
+    if (cZ == 0) {
+        vload<real, V>(row + Z0, o);
+    } else if (V > 1 && cZ == -1) {
+        real t[V];
+        vload<real, V>(row + Z0, t);
+        int zl = Z0 == 0 ? Zd - 1 : Z0 - 1;
+        o[0] = row[zl];
+#pragma unroll
+        for (int i = 1; i < V; i++) o[i] = t[i - 1];
+    } else if (V > 1 && cZ == 1) {
+        real t[V];
+        vload<real, V>(row + Z0, t);
+        int zr = Z0 + V >= Zd ? 0 : Z0 + V;
+#pragma unroll
+        for (int i = 0; i < V - 1; i++) o[i] = t[i + 1];
+        o[V - 1] = row[zr];
+    } else {
+#pragma unroll
+        for (int i = 0; i < V; i++) {
+            int z = Z0 + i + cZ;
+            if (z < 0) z += Zd;
+            if (z >= Zd) z -= Zd;
+            o[i] = row[z];
+        }
+    }
+}
+
+// ---- link / class tables of one colour pass ----
+constexpr int PT_MAXC = 8, PT_MAXL = 16;
+template <typename real> struct PLink {
+    int delta;                  // (qn-q)*ncellc + (cX*Yd + cY)*Zd with signed cX,cY in {-1,0,1}
+    int mxp, mxm, myp, mym;     // 0/1: which per-row wrap correction applies
+    int cZ, low, pad;
+    real J[9];
+};
+template <typename real> struct PassTable {
+    int nl, nqc, pad0, pad1;
+    int ca[PT_MAXC], cb[PT_MAXC], cc[PT_MAXC], co[PT_MAXC], lowmode[PT_MAXC];
+    real S[PT_MAXC], D[PT_MAXC][3];
+    PLink<real> L[PT_MAXC][PT_MAXL];
+};
+
+// runtime views (offline build)
+template <typename real> struct RtLink {
+    const PLink<real> &L;
+    __device__ __forceinline__ int delta() const { return L.delta; }
+    __device__ __forceinline__ int mxp() const { return L.mxp; }
+    __device__ __forceinline__ int mxm() const { return L.mxm; }
+    __device__ __forceinline__ int myp() const { return L.myp; }
+    __device__ __forceinline__ int mym() const { return L.mym; }
+    __device__ __forceinline__ int cZ() const { return L.cZ; }
+    __device__ __forceinline__ int low() const { return L.low; }
+    __device__ __forceinline__ real J(int e) const { return L.J[e]; }
+};
+template <typename real> struct RtClass {
+    const PassTable<real> &T;
+    int j;
+    __device__ __forceinline__ int nl() const { return T.nl; }
+    __device__ __forceinline__ int ca() const { return T.ca[j]; }
+    __device__ __forceinline__ int cb() const { return T.cb[j]; }
+    __device__ __forceinline__ int cc() const { return T.cc[j]; }
+    __device__ __forceinline__ int co() const { return T.co[j]; }
+    __device__ __forceinline__ int lowmode() const { return T.lowmode[j]; }
+    __device__ __forceinline__ real S() const { return T.S[j]; }
+    __device__ __forceinline__ real D(int e) const { return T.D[j][e]; }
+    template <typename F> __device__ __forceinline__ void for_links(F &&f) const {
+        const int n = T.nl;
+        for (int k = 0; k < n; k++) f(RtLink<real>{T.L[j][k]});
+    }
+};
+
+// dims: runtime fields offline, literals under JIT (the generated prologue defines JIT_Xd ...)
+#ifdef MCG_JIT
+#define MCG_DIM(a, f) (JIT_##f)
+#else
+#define MCG_DIM(a, f) ((a).f)
+#endif
+
+template <int I> struct IC { static constexpr int value = I; };
+template <int I, int N, typename F> __device__ __forceinline__ void ct_for(F &&f) {
+    if constexpr (I < N) {
+        f(IC<I>{});
+        ct_for<I + 1, N>(f);
+    }
+}
+
+// One colour pass over the rows [rb*rowsPerBlock, ...) of class q = q0 + j for replica r.
+// MODE 0: update only   1: update + fused measurement (classSums += M, E contributions)
+template <int NC, typename real, bool FULLJ, int MODE, int V, typename CLS>
+__device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, int q, int r, int rb, int rowsPerBlock, uint64_t sweep,
+                                          real pAtt, double *red) {
+    const int Xd = MCG_DIM(a, Xd), Yd = MCG_DIM(a, Yd), Zd = MCG_DIM(a, Zd), Zc = MCG_DIM(a, Zc), N = MCG_DIM(a, N);
+    const int px = MCG_DIM(a, px), py = MCG_DIM(a, py), pz = MCG_DIM(a, pz), norb = MCG_DIM(a, norb);
+    const int Ly = MCG_DIM(a, Ly), Lz = MCG_DIM(a, Lz), nrows = MCG_DIM(a, nrows), nclass = MCG_DIM(a, nclass);
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int lowmode = cls.lowmode();
+    const real S = cls.S();
+    const real D0 = cls.D(0), D1 = cls.D(1), D2 = cls.D(2);
+    const bool hasD = D0 != real(0) || D1 != real(0) || D2 != real(0);   // a literal under JIT: the D terms fold away
+    // fp32 state: |s| is pinned back to S every 8th sweep (rounding drifts it by ~1e-7 per accepted move)
+    const bool renorm = sizeof(real) == 4 && (sweep & 7) == 0;
+    const real beta = (real)a.beta[r], hf = (real)(a.beta[r] * a.field[r]);
+    real *sp = (real *)a.spin + (size_t)r * NC * N;
+    const int idStrideZ = pz * norb;
+    const int planeY = Yd * Zd, planeX = planeY * Xd;
+    real accM[3] = {0, 0, 0}, accE = 0;
+    int natt = 0, nacc = 0;
+
+    const int rowEnd = min(nrows, (rb + 1) * rowsPerBlock);
+    for (int row = rb * rowsPerBlock + threadIdx.y; row < rowEnd; row += blockDim.y) {
+        const int X = row / Yd, Y = row - X * Yd;
+        const int rowBase = ((q * Xd + X) * Yd + Y) * Zd;
+        const int wxp = X == Xd - 1 ? -planeX : 0, wxm = X == 0 ? planeX : 0;
+        const int wyp = Y == Yd - 1 ? -planeY : 0, wym = Y == 0 ? planeY : 0;
+        const int xy = ((X * px + cls.ca()) * Ly + (Y * py + cls.cb())) * Lz;
+        for (int zc = threadIdx.x; zc < Zc; zc += blockDim.x) {
+            const int Z0 = zc * V;
+            real s[3][V], H[3][V], Hl[3][V];
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int v = 0; v < V; v++) { s[c][v] = 0; H[c][v] = 0; Hl[c][v] = 0; }
+            const real *own = sp + rowBase + Z0;
+#pragma unroll
+            for (int c = 0; c < NC; c++) vload<real, V>(own + (size_t)c * N, s[c]);
+            cls.for_links([&](auto L) {
+                const int nb = rowBase + L.delta() + L.mxp() * wxp + L.mxm() * wxm + L.myp() * wyp + L.mym() * wym;
+                real t[3][V];
+#pragma unroll
+                for (int c = 0; c < NC; c++) load_shifted<real, V>(sp + (size_t)c * N + nb, Z0, L.cZ(), Zd, t[c]);
+                const bool lowk = MODE == 1 && lowmode == 2 && L.low();
+#pragma unroll
+                for (int v = 0; v < V; v++) {
+                    const real tx = t[0][v], ty = NC >= 2 ? t[1][v] : real(0), tz = NC == 3 ? t[2][v] : real(0);
+                    real hx, hy = 0, hz = 0;
+                    if (NC == 1) hx = L.J(0) * tx;
+                    else if (NC == 2) {
+                        if (FULLJ) { hx = L.J(0) * tx + L.J(3) * ty; hy = L.J(6) * tx + L.J(1) * ty; }
+                        else { hx = L.J(0) * tx; hy = L.J(1) * ty; }
+                    } else {
+                        if (FULLJ) {
+                            hx = L.J(0) * tx + L.J(3) * ty + L.J(4) * tz;
+                            hy = L.J(6) * tx + L.J(1) * ty + L.J(5) * tz;
+                            hz = L.J(7) * tx + L.J(8) * ty + L.J(2) * tz;
+                        } else { hx = L.J(0) * tx; hy = L.J(1) * ty; hz = L.J(2) * tz; }
+                    }
+                    H[0][v] += hx; H[1][v] += hy; H[2][v] += hz;
+                    if (lowk) { Hl[0][v] += hx; Hl[1][v] += hy; Hl[2][v] += hz; }
+                }
+            });
+            const uint32_t id0 = (uint32_t)((xy + Z0 * pz + cls.cc()) * norb + cls.co());
+#pragma unroll
+            for (int v = 0; v < V; v++) {
+                real sx = s[0][v], sy = s[1][v], sz = s[2][v];
+                const real hx = H[0][v], hy = H[1][v], hz = H[2][v];
+                uint32_t w[4];
+                rng4(a.key, a.replica0 + r, STREAM_METRO, 0, sweep, id0 + (uint32_t)(v * idStrideZ), w);
+                const bool att = !(pAtt < real(1)) || u01<real>(w[3]) < pAtt;
+                bool acc;
+                if (NC == 1) {
+                    const real corr = real(2) * (beta * sx * hx - hf * sx);                     // isingLib.c:242
+                    acc = att && (corr >= real(0) || r_exp<real>(corr) > u01<real>(w[2]));
+                    sx = acc ? -sx : sx;
+                } else {
+                    real n[3];
+                    random_dir<NC, real>(w[0], w[1], n);
+                    const real s1n = real(-2) * (sx * n[0] + sy * n[1] + (NC == 3 ? sz * n[2] : real(0)));
+                    const real tx = n[0] * s1n, ty = n[1] * s1n, tz = NC == 3 ? n[2] * s1n : real(0);
+                    real dE = tx * hx + ty * hy + (NC == 3 ? tz * hz : real(0));
+                    real nx = sx + tx, ny = sy + ty, nz = sz + tz;
+                    if (hasD) {
+                        real dOn = D0 * (nx * nx - sx * sx) + D1 * (ny * ny - sy * sy);
+                        if (NC == 3) dOn += D2 * (nz * nz - sz * sz);
+                        dE += dOn;
+                    }
+                    dE = beta * dE - hf * (NC == 3 ? tz : tx);
+                    acc = att && (dE <= real(0) || r_exp<real>(-dE) > u01<real>(w[2]));          // heisenbergLib.c:461
+                    sx = acc ? nx : sx; sy = acc ? ny : sy; sz = acc ? nz : sz;
+                    if (renorm) {   // every site, accepted or not
+                        const real f = S * r_rsqrt<real>(sx * sx + sy * sy + sz * sz);
+                        sx *= f; sy *= f; sz *= f;
+                    }
+                }
+                natt += att ? 1 : 0;
+                nacc += acc ? 1 : 0;
+                s[0][v] = sx; s[1][v] = sy; s[2][v] = sz;
+                if (MODE == 1) {
+                    accM[0] += sx; accM[1] += sy; accM[2] += sz;
+                    real eb;
+                    if (lowmode == 1) eb = sx * hx + sy * hy + sz * hz;
+                    else if (lowmode == 2) eb = sx * Hl[0][v] + sy * Hl[1][v] + sz * Hl[2][v];
+                    else eb = real(0);
+                    const real sv[3] = {sx, sy, sz};
+                    const real Dv[3] = {D0, D1, D2};
+                    accE += beta * eb + onsite_energy<NC, real>(sv, Dv, beta, hf);
+                }
+            }
+            real *ownw = sp + rowBase + Z0;
+#pragma unroll
+            for (int c = 0; c < NC; c++) vstore<real, V>(ownw + (size_t)c * N, s[c]);
+        }
+    }
+    natt = __reduce_add_sync(0xffffffffu, natt);
+    nacc = __reduce_add_sync(0xffffffffu, nacc);
+    if ((tid & 31) == 0 && natt) {
+        atomicAdd(a.cnt + (size_t)r * NCNT + CNT_ATTEMPT, (unsigned long long)natt);
+        atomicAdd(a.cnt + (size_t)r * NCNT + CNT_ACCEPT, (unsigned long long)nacc);
+    }
+    if (MODE == 1) {
+        double v[4] = {(double)accM[0], (double)accM[1], (double)accM[2], (double)accE};
+        const int lane = tid & 31, w = tid >> 5, nw = (blockDim.x * blockDim.y + 31) >> 5;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            double sum = warp_sum(v[i]);
+            if (lane == 0) red[i * 32 + w] = sum;
+        }
+        __syncthreads();
+        if (w == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                double sum = lane < nw ? red[i * 32 + lane] : 0.0;
+                sum = warp_sum(sum);
+                if (lane == 0 && sum != 0.0) atomicAdd(a.classSums + ((size_t)r * nclass + q) * 4 + i, sum);
+            }
+        }
+    }
+}
+
+#ifndef MCG_JIT
+// offline entry: tables as a __grid_constant__ parameter
+template <int NC, typename real, bool FULLJ, int MODE, int V>
+__global__ void __launch_bounds__(256, 4)
+k_struct_fast(const __grid_constant__ StructArgs a, const __grid_constant__ PassTable<real> T, int q0, int rowsPerBlock, int nrb,
+              uint64_t sweep, real pAtt) {
+    __shared__ double red[4 * 32];
+    const int nqc = T.nqc;
+    const int bid = blockIdx.x;
+    const int j = bid % nqc, tq = bid / nqc, rb = tq % nrb, r = tq / nrb;
+    pass_body<NC, real, FULLJ, MODE, V>(a, RtClass<real>{T, j}, q0 + j, r, rb, rowsPerBlock, sweep, pAtt, red);
+}
+#else
+// ---- JIT entry points: JIT_NC, jit_real, JIT_FULLJ, JIT_V, JIT_NQC, JIT_NL, JIT_MINB, CtLinkData<J,K>, CtClassData<J>
+// come from the generated prologue ----
+template <int JJ, int K> struct CtLink {
+    typedef CtLinkData<JJ, K> D;
+    __device__ __forceinline__ constexpr int delta() const { return D::delta; }
+    __device__ __forceinline__ constexpr int mxp() const { return D::mxp; }
+    __device__ __forceinline__ constexpr int mxm() const { return D::mxm; }
+    __device__ __forceinline__ constexpr int myp() const { return D::myp; }
+    __device__ __forceinline__ constexpr int mym() const { return D::mym; }
+    __device__ __forceinline__ constexpr int cZ() const { return D::cZ; }
+    __device__ __forceinline__ constexpr int low() const { return D::low; }
+    __device__ __forceinline__ constexpr jit_real J(int e) const { return D::J(e); }
+};
+template <int JJ> struct CtClass {
+    typedef CtClassData<JJ> C;
+    __device__ __forceinline__ constexpr int nl() const { return C::nl; }
+    __device__ __forceinline__ constexpr int ca() const { return C::ca; }
+    __device__ __forceinline__ constexpr int cb() const { return C::cb; }
+    __device__ __forceinline__ constexpr int cc() const { return C::cc; }
+    __device__ __forceinline__ constexpr int co() const { return C::co; }
+    __device__ __forceinline__ constexpr int lowmode() const { return C::lowmode; }
+    __device__ __forceinline__ constexpr jit_real S() const { return C::S; }
+    __device__ __forceinline__ constexpr jit_real D(int e) const { return C::D(e); }
+    template <typename F> __device__ __forceinline__ void for_links(F &&f) const {
+        ct_for<0, C::nl>([&](auto k) { f(CtLink<JJ, decltype(k)::value>{}); });
+    }
+};
+
+template <int MODE, int J>
+__device__ __forceinline__ void jit_case(const StructArgs &a, int j, int q0, int r, int rb, int rowsPerBlock, uint64_t sweep,
+                                         jit_real pAtt, double *red) {
+    if constexpr (J < JIT_NQC) {
+        if (j == J) pass_body<JIT_NC, jit_real, JIT_FULLJ, MODE, JIT_V>(a, CtClass<J>{}, q0 + J, r, rb, rowsPerBlock, sweep, pAtt, red);
+        else jit_case<MODE, J + 1>(a, j, q0, r, rb, rowsPerBlock, sweep, pAtt, red);
+    }
+}
+
+#define MCG_JIT_ENTRY(NAME, MODE)                                                                                              \
+    extern "C" __global__ void __launch_bounds__(256, JIT_MINB)                                                                \
+    NAME(const __grid_constant__ StructArgs a, int q0, int rowsPerBlock, int nrb, uint64_t sweep, jit_real pAtt) {             \
+        __shared__ double red[4 * 32];                                                                                         \
+        const int bid = blockIdx.x;                                                                                            \
+        const int j = bid % JIT_NQC, tq = bid / JIT_NQC, rb = tq % nrb, r = tq / nrb;                                          \
+        jit_case<MODE, 0>(a, j, q0, r, rb, rowsPerBlock, sweep, pAtt, red);                                                    \
+    }
+MCG_JIT_ENTRY(mcg_pass_m0, 0)
+MCG_JIT_ENTRY(mcg_pass_m1, 1)
+#endif
+
+}  // namespace mcg

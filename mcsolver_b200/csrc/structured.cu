@@ -22,22 +22,10 @@
 #include <vector>
 
 #include "structured.hpp"
+#include "struct_pass.cuh"
+#include "jit.hpp"
 
 namespace mcg {
-
-constexpr int MAXLINK = 32;
-
-struct SLinkD {
-    int qn;          // neighbour class
-    int cX, cY;      // coarse offsets, already reduced to [0,Xd) / [0,Yd)
-    int cZ;          // coarse Z offset in (-Zd/2, Zd/2]
-    int low;         // neighbour class has a lower colour (its spins are final in this sweep)
-    int self;        // link to the site itself (supercell dimension 1)
-};
-struct SClassD {
-    int a, b, c, o, colour, nlink, lowmode, pad;
-    double S, D[3];
-};
 
 struct StructuredSystem {
     int L[3], p[3], Xd, Yd, Zd, ncellc, nclass, norb, V;
@@ -49,6 +37,11 @@ struct StructuredSystem {
     std::vector<SClassD> classes;        // sorted by colour
     std::vector<int> classOf;            // [(a*py+b)*pz+c)*norb+o] -> class index
     std::vector<int> colourClassStart;   // [C+1]
+    std::vector<SLinkD> linksHost;       // [nclass][MAXLINK]
+    std::vector<int> cXs, cYs;           // signed coarse offsets per link (fast path needs |c|<=1)
+    std::vector<double> JHost;           // [nclass][MAXLINK][JW]
+    std::vector<char> fastOK;            // per colour: pass table fits the __grid_constant__ fast path
+    std::vector<std::vector<char>> passTables;   // per colour: PassTable<real> bytes
     SClassD *d_classes = nullptr;
     SLinkD *d_links = nullptr;
     void *d_J = nullptr;
@@ -56,76 +49,6 @@ struct StructuredSystem {
     double *d_classSums = nullptr;       // [R][nclass][4]
     double *d_stage = nullptr;           // [3N] host<->device staging, allocated on demand
 };
-
-struct StructArgs {
-    int Xd, Yd, Zd, Zc, ncellc, nclass, nrows, N;
-    int px, py, pz, norb, Lx, Ly, Lz;
-    const SClassD *classes;
-    const SLinkD *links;
-    const void *J;
-    const int *classOf;
-    void *spin;
-    const double *beta, *field;
-    unsigned long long *cnt;
-    double *classSums;
-    RngKey key;
-    uint32_t replica0;
-};
-
-// ---------------------------------------------------------------------------------------------
-// device helpers
-// ---------------------------------------------------------------------------------------------
-template <typename real, int V> struct Vec;
-template <> struct Vec<float, 4> { typedef float4 type; };
-template <> struct Vec<float, 1> { typedef float type; };
-template <> struct Vec<double, 2> { typedef double2 type; };
-template <> struct Vec<double, 1> { typedef double type; };
-
-template <typename real, int V> __device__ __forceinline__ void vload(const real *__restrict__ p, real (&o)[V]) {
-    typedef typename Vec<real, V>::type VT;
-    VT v = *reinterpret_cast<const VT *>(p);
-    const real *e = reinterpret_cast<const real *>(&v);
-#pragma unroll
-    for (int i = 0; i < V; i++) o[i] = e[i];
-}
-template <typename real, int V> __device__ __forceinline__ void vstore(real *__restrict__ p, const real (&o)[V]) {
-    typedef typename Vec<real, V>::type VT;
-    VT v;
-    real *e = reinterpret_cast<real *>(&v);
-#pragma unroll
-    for (int i = 0; i < V; i++) e[i] = o[i];
-    *reinterpret_cast<VT *>(p) = v;
-}
-
-// V consecutive cells of a neighbour row, shifted by cZ cells with periodic wrap
-template <typename real, int V>
-__device__ __forceinline__ void load_shifted(const real *__restrict__ row, int Z0, int cZ, int Zd, real (&o)[V]) {
-    if (cZ == 0) {
-        vload<real, V>(row + Z0, o);
-    } else if (V > 1 && cZ == -1) {
-        real t[V];
-        vload<real, V>(row + Z0, t);
-        int zl = Z0 == 0 ? Zd - 1 : Z0 - 1;
-        o[0] = row[zl];
-#pragma unroll
-        for (int i = 1; i < V; i++) o[i] = t[i - 1];
-    } else if (V > 1 && cZ == 1) {
-        real t[V];
-        vload<real, V>(row + Z0, t);
-        int zr = Z0 + V >= Zd ? 0 : Z0 + V;
-#pragma unroll
-        for (int i = 0; i < V - 1; i++) o[i] = t[i + 1];
-        o[V - 1] = row[zr];
-    } else {
-#pragma unroll
-        for (int i = 0; i < V; i++) {
-            int z = Z0 + i + cZ;
-            if (z < 0) z += Zd;
-            if (z >= Zd) z -= Zd;
-            o[i] = row[z];
-        }
-    }
-}
 
 __device__ __forceinline__ int struct_pos(const StructArgs &a, int x, int y, int z, int o) {
     int ca = x % a.px, cb = y % a.py, cc = z % a.pz;
@@ -284,6 +207,7 @@ __global__ void __launch_bounds__(256) k_struct(StructArgs a, int q0, int nqc, i
     }
 }
 
+
 // classSums -> the raw per-sweep sums the common finalize kernel consumes; clears classSums
 __global__ void k_struct_fold(StructArgs a, int R, int pair_s, int pair_t, int selfPairs, double nLat, double *sums) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -400,6 +324,194 @@ __global__ void __launch_bounds__(256) k_struct_frame(StructArgs a, int r, doubl
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// JIT: generate the prologue (lattice as literals), compile struct_pass.cuh with NVRTC for sm_100a,
+// load the cubin through the driver API.  libnvrtc / libcuda are dlopen'ed lazily so that the
+// library itself has no link-time dependency on them; any failure falls back to the offline
+// (runtime-table) CUDA kernel - never to a CPU path.
+// ---------------------------------------------------------------------------------------------
+}  // namespace mcg
+#include <cuda.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <map>
+#include <mutex>
+#include <sstream>
+namespace mcg {
+
+struct JitApi {
+    bool ok = false, rtc_ok = false;
+    std::string why;
+    decltype(&nvrtcCreateProgram) createProgram;
+    decltype(&nvrtcCompileProgram) compileProgram;
+    decltype(&nvrtcGetCUBINSize) getCUBINSize;
+    decltype(&nvrtcGetCUBIN) getCUBIN;
+    decltype(&nvrtcGetProgramLogSize) getLogSize;
+    decltype(&nvrtcGetProgramLog) getLog;
+    decltype(&nvrtcDestroyProgram) destroyProgram;
+    decltype(&cuModuleLoadData) moduleLoadData;
+    decltype(&cuModuleGetFunction) moduleGetFunction;
+    decltype(&cuLaunchKernel) launchKernel;
+};
+
+static JitApi &jit_api() {
+    static JitApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *rtc = nullptr;
+        for (const char *n : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"})
+            if ((rtc = dlopen(n, RTLD_NOW | RTLD_LOCAL))) break;
+        void *drv = dlopen("libcuda.so.1", RTLD_NOW | RTLD_LOCAL);
+        if (!rtc) { api.why = "cannot dlopen libnvrtc"; return; }
+#define MCG_SYM(lib, field, name)                                               \
+    api.field = reinterpret_cast<decltype(api.field)>(dlsym(lib, name));        \
+    if (!api.field) { api.why = std::string("missing symbol ") + name; return; }
+        MCG_SYM(rtc, createProgram, "nvrtcCreateProgram")
+        MCG_SYM(rtc, compileProgram, "nvrtcCompileProgram")
+        MCG_SYM(rtc, getCUBINSize, "nvrtcGetCUBINSize")
+        MCG_SYM(rtc, getCUBIN, "nvrtcGetCUBIN")
+        MCG_SYM(rtc, getLogSize, "nvrtcGetProgramLogSize")
+        MCG_SYM(rtc, getLog, "nvrtcGetProgramLog")
+        MCG_SYM(rtc, destroyProgram, "nvrtcDestroyProgram")
+        api.rtc_ok = true;
+        if (!drv) { api.why = "cannot dlopen libcuda.so.1"; return; }
+        MCG_SYM(drv, moduleLoadData, "cuModuleLoadData")
+        MCG_SYM(drv, moduleGetFunction, "cuModuleGetFunction")
+        MCG_SYM(drv, launchKernel, "cuLaunchKernel")
+#undef MCG_SYM
+        api.ok = true;
+    });
+    return api;
+}
+
+static std::string csrc_dir() {
+    Dl_info info;
+    if (dladdr(reinterpret_cast<void *>(&csrc_dir), &info) && info.dli_fname) {
+        std::string p = info.dli_fname;
+        size_t k = p.find_last_of('/');
+        return (k == std::string::npos ? std::string(".") : p.substr(0, k)) + "/csrc";
+    }
+    return "mcsolver_b200/csrc";
+}
+
+static std::string lit(double v, bool f32) {
+    char buf[64];
+    if (f32) snprintf(buf, sizeof buf, "%.9ef", (double)(float)v);
+    else snprintf(buf, sizeof buf, "%.17e", v);
+    return buf;
+}
+
+std::string jit_prologue(const mcg_system *s, int colour) {
+    const StructuredSystem *st = s->st;
+    const bool f32 = s->prec == 32;
+    const int q0 = st->colourClassStart[colour], nqc = st->colourClassStart[colour + 1] - q0;
+    const int JW = s->NC == 1 ? 1 : 9;
+    std::ostringstream o;
+    o << "#define MCG_JIT 1\ntypedef " << (f32 ? "float" : "double") << " jit_real;\n";
+    o << "#define JIT_NC " << s->NC << "\n#define JIT_FULLJ " << (s->fullJ ? "true" : "false") << "\n#define JIT_V " << st->V
+      << "\n#define JIT_NQC " << nqc << "\n#define JIT_MINB " << (getenv("MCG_JIT_MINB") ? atoi(getenv("MCG_JIT_MINB")) : (f32 ? 4 : 2)) << "\n";
+    o << "#define JIT_Xd " << st->Xd << "\n#define JIT_Yd " << st->Yd << "\n#define JIT_Zd " << st->Zd << "\n#define JIT_Zc "
+      << st->Zd / st->V << "\n#define JIT_N " << s->N << "\n#define JIT_px " << st->p[0] << "\n#define JIT_py " << st->p[1]
+      << "\n#define JIT_pz " << st->p[2] << "\n#define JIT_norb " << st->norb << "\n#define JIT_Ly " << st->L[1]
+      << "\n#define JIT_Lz " << st->L[2] << "\n#define JIT_nrows " << st->nrows << "\n#define JIT_nclass " << st->nclass << "\n";
+    o << "namespace mcg {\ntemplate <int J, int K> struct CtLinkData;\ntemplate <int J> struct CtClassData;\n";
+    for (int j = 0; j < nqc; j++) {
+        const SClassD &cl = st->classes[q0 + j];
+        o << "template <> struct CtClassData<" << j << "> { static constexpr int nl=" << cl.nlink << ", ca=" << cl.a << ", cb=" << cl.b
+          << ", cc=" << cl.c << ", co=" << cl.o << ", lowmode=" << cl.lowmode << "; static constexpr jit_real S=" << lit(std::fabs(cl.S), f32)
+          << "; static __device__ constexpr jit_real D(int e) { constexpr jit_real v[3] = {" << lit(cl.D[0], f32) << "," << lit(cl.D[1], f32)
+          << "," << lit(cl.D[2], f32) << "}; return v[e]; } };\n";
+        for (int k = 0; k < cl.nlink; k++) {
+            size_t li = (size_t)(q0 + j) * MAXLINK + k;
+            int cx = st->cXs[li], cy = st->cYs[li];
+            int delta = (st->linksHost[li].qn - (q0 + j)) * st->ncellc + (cx * st->Yd + cy) * st->Zd;
+            o << "template <> struct CtLinkData<" << j << "," << k << "> { static constexpr int delta=" << delta << ", mxp=" << (cx > 0)
+              << ", mxm=" << (cx < 0) << ", myp=" << (cy > 0) << ", mym=" << (cy < 0) << ", cZ=" << st->linksHost[li].cZ
+              << ", low=" << st->linksHost[li].low << "; static __device__ constexpr jit_real J(int e) { constexpr jit_real v[9] = {";
+            for (int e = 0; e < 9; e++) o << (e ? "," : "") << lit(e < JW ? st->JHost[li * JW + e] : 0.0, f32);
+            o << "}; return v[e]; } };\n";
+        }
+    }
+    o << "}\n#include \"struct_pass.cuh\"\n";
+    return o.str();
+}
+
+struct JitPass {
+    CUfunction f[2] = {nullptr, nullptr};
+    bool failed = false;
+};
+static std::mutex g_jit_mutex;
+static std::map<std::pair<int, std::string>, JitPass> g_jit_cache;   // (device, prologue) -> loaded kernels
+
+// compile (or fetch) the specialised kernels; also usable without a GPU up to the cubin (tests)
+std::vector<char> jit_compile_cubin(const std::string &src, std::string &log) {
+    JitApi &api = jit_api();
+    if (!api.rtc_ok) { log = api.why; return {}; }
+    nvrtcProgram prog;
+    if (api.createProgram(&prog, src.c_str(), "mcg_pass.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) { log = "nvrtcCreateProgram failed"; return {}; }
+    std::string inc = "-I" + csrc_dir();
+    const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", inc.c_str(), "-default-device"};
+    nvrtcResult res = api.compileProgram(prog, 5, opts);
+    size_t ls = 0;
+    api.getLogSize(prog, &ls);
+    if (ls > 1) { log.resize(ls); api.getLog(prog, &log[0]); }
+    std::vector<char> cubin;
+    if (res == NVRTC_SUCCESS) {
+        size_t cs = 0;
+        api.getCUBINSize(prog, &cs);
+        cubin.resize(cs);
+        api.getCUBIN(prog, cubin.data());
+        if (const char *dump = getenv("MCG_JIT_DUMP")) {   // debugging aid: keep the last cubin for cuobjdump -sass
+            if (FILE *f = fopen(dump, "wb")) { fwrite(cubin.data(), 1, cubin.size(), f); fclose(f); }
+        }
+    }
+    api.destroyProgram(&prog);
+    return cubin;
+}
+
+static bool jit_enabled(const mcg_system *s) {
+    const char *e = getenv("MCG_JIT");
+    if (e && e[0] == '0') return false;
+    if (e && e[0] == '1') return true;
+    return (long long)s->N * s->R >= (1ll << 20);   // creation-time compile (~seconds) only pays for big jobs
+}
+
+bool jit_launch_pass(mcg_system *s, int colour, int mode, const StructArgs &a, int q0, int rowsPerBlock, int nrb, uint64_t sweep,
+                     double pAtt, dim3 grid, dim3 block) {
+    if (!jit_enabled(s)) return false;
+    JitApi &api = jit_api();
+    if (!api.ok) return false;
+    JitPass *jp;
+    {
+        std::lock_guard<std::mutex> lock(g_jit_mutex);
+        auto key = std::make_pair(s->device, jit_prologue(s, colour));
+        auto it = g_jit_cache.find(key);
+        if (it == g_jit_cache.end()) {
+            JitPass np;
+            std::string log;
+            std::vector<char> cubin = jit_compile_cubin(key.second, log);
+            CUmodule mod = nullptr;
+            if (cubin.empty() || api.moduleLoadData(&mod, cubin.data()) != CUDA_SUCCESS ||
+                api.moduleGetFunction(&np.f[0], mod, "mcg_pass_m0") != CUDA_SUCCESS ||
+                api.moduleGetFunction(&np.f[1], mod, "mcg_pass_m1") != CUDA_SUCCESS) {
+                np.failed = true;
+                fprintf(stderr, "mcsolver_b200: JIT specialisation unavailable (%s); using the offline CUDA kernel\n", log.substr(0, 2000).c_str());
+            }
+            it = g_jit_cache.emplace(key, np).first;
+        }
+        jp = &it->second;
+    }
+    if (jp->failed) return false;
+    float pf = (float)pAtt;
+    double pd = pAtt;
+    void *params[] = {(void *)&a, &q0, &rowsPerBlock, &nrb, &sweep, s->prec == 32 ? (void *)&pf : (void *)&pd};
+    CUresult r = api.launchKernel(jp->f[mode], grid.x, 1, 1, block.x, block.y, 1, 0, (CUstream)s->stream, params, nullptr);
+    if (r != CUDA_SUCCESS) throw Error(MCG_ERR_CUDA, "cuLaunchKernel of the JIT pass kernel failed");
+    return true;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host: link templates, colouring period search, class tables
 // ---------------------------------------------------------------------------------------------
@@ -420,12 +532,12 @@ static StructArgs struct_args(const mcg_system *s) {
     a.px = st->p[0]; a.py = st->p[1]; a.pz = st->p[2]; a.norb = st->norb; a.Lx = st->L[0]; a.Ly = st->L[1]; a.Lz = st->L[2];
     a.classes = st->d_classes; a.links = st->d_links; a.J = st->d_J; a.classOf = st->d_classOf;
     a.spin = s->d_spin; a.beta = s->d_beta; a.field = s->d_field; a.cnt = s->d_cnt; a.classSums = st->d_classSums;
-    a.key.k0 = (uint32_t)s->seed; a.key.k1 = (uint32_t)(s->seed >> 32);
+    a.key = make_rng_key(s->seed);
     a.replica0 = s->replica0;
     return a;
 }
 
-void structured_create(mcg_system *s, const mcg_lattice_desc *d) {
+static void structured_build_host(mcg_system *s, const mcg_lattice_desc *d, std::vector<SLinkD> &links, std::vector<double> &Jt) {
     MCG_REQUIRE(d->model >= 1 && d->model <= 3, "model must be 1, 2 or 3");
     MCG_REQUIRE(d->norb >= 1 && d->S, "norb/S invalid");
     for (int k = 0; k < 3; k++) MCG_REQUIRE(d->L[k] >= 1, "supercell dims must be >= 1");
@@ -546,10 +658,11 @@ void structured_create(mcg_system *s, const mcg_lattice_desc *d) {
     for (int i = 0; i < bestN; i++) st->colourClassStart[bestColour[i] + 1]++;
     for (int c = 0; c < bestC; c++) st->colourClassStart[c + 1] += st->colourClassStart[c];
     st->classes.resize(bestN);
-    std::vector<SLinkD> links((size_t)bestN * MAXLINK);
-    std::memset(links.data(), 0, links.size() * sizeof(SLinkD));
+    links.assign((size_t)bestN * MAXLINK, SLinkD{0, 0, 0, 0, 0, 0});
+    st->cXs.assign((size_t)bestN * MAXLINK, 0);
+    st->cYs.assign((size_t)bestN * MAXLINK, 0);
     const int JW = d->model == 1 ? 1 : 9;
-    std::vector<double> Jt((size_t)bestN * MAXLINK * JW, 0.0);
+    Jt.assign((size_t)bestN * MAXLINK * JW, 0.0);
     for (int q = 0; q < bestN; q++) {
         int id = order[q];
         int o = id % no, c = (id / no) % pz, b = (id / (no * pz)) % py, a = id / (no * pz * py);
@@ -569,12 +682,55 @@ void structured_create(mcg_system *s, const mcg_lattice_desc *d) {
             l.cX = mod(cX, st->Xd); l.cY = mod(cY, st->Yd);
             int z = mod(cZ, st->Zd); if (z > st->Zd / 2) z -= st->Zd;
             l.cZ = z;
+            { int v = mod(cX, st->Xd); if (v > st->Xd / 2) v -= st->Xd; st->cXs[(size_t)q * MAXLINK + k] = v; }
+            { int v = mod(cY, st->Yd); if (v > st->Yd / 2) v -= st->Yd; st->cYs[(size_t)q * MAXLINK + k] = v; }
             l.self = t.self ? 1 : 0;
             l.low = (!t.self && bestColour[nid] < bestColour[id]) ? 1 : 0;
             if (!t.self) { nreal++; nlow += l.low; }
             for (int e = 0; e < JW; e++) Jt[((size_t)q * MAXLINK + k) * JW + e] = t.J[e];
         }
         cl.lowmode = nlow == 0 ? 0 : (nlow == nreal ? 1 : 2);
+    }
+    st->linksHost = links;
+    st->JHost = Jt;
+    // ---- per-colour pass tables for the fast kernel ----
+    st->fastOK.assign(bestC, 0);
+    st->passTables.assign(bestC, std::vector<char>());
+    auto build_pass = [&](auto realTag, int colour) {
+        typedef decltype(realTag) real;
+        int q0 = st->colourClassStart[colour], nqc = st->colourClassStart[colour + 1] - q0;
+        if (nqc < 1 || nqc > PT_MAXC || st->hasSelf) return;
+        int nl = 0;
+        for (int j = 0; j < nqc; j++) nl = std::max(nl, st->classes[q0 + j].nlink);
+        if (nl < 1) return;
+        int G = 1;
+        int nlp = nl;
+        if (nlp > PT_MAXL) return;
+        std::vector<char> buf(sizeof(PassTable<real>), 0);
+        PassTable<real> *P = reinterpret_cast<PassTable<real> *>(buf.data());
+        P->nl = nlp; P->nqc = nqc;
+        for (int j = 0; j < nqc; j++) {
+            const SClassD &cl = st->classes[q0 + j];
+            P->ca[j] = cl.a; P->cb[j] = cl.b; P->cc[j] = cl.c; P->co[j] = cl.o; P->lowmode[j] = cl.lowmode;
+            P->S[j] = (real)std::fabs(cl.S);
+            for (int e = 0; e < 3; e++) P->D[j][e] = (real)cl.D[e];
+            for (int k = 0; k < nlp; k++) {
+                PLink<real> &L = P->L[j][k];
+                if (k >= cl.nlink) { L.delta = 0; L.mxp = L.mxm = L.myp = L.mym = 0; L.cZ = 0; L.low = 0; continue; }   // zero-J pad: own cell
+                size_t li = (size_t)(q0 + j) * MAXLINK + k;
+                int cx = st->cXs[li], cy = st->cYs[li];
+                if (cx < -1 || cx > 1 || cy < -1 || cy > 1) return;
+                L.delta = (links[li].qn - (q0 + j)) * st->ncellc + (cx * st->Yd + cy) * st->Zd;
+                L.mxp = cx > 0; L.mxm = cx < 0; L.myp = cy > 0; L.mym = cy < 0;
+                L.cZ = links[li].cZ; L.low = links[li].low;
+                for (int e = 0; e < JW; e++) L.J[e] = (real)Jt[li * JW + e];
+            }
+        }
+        st->passTables[colour] = buf;
+        st->fastOK[colour] = (char)G;
+    };
+    for (int c = 0; c < bestC; c++) {
+        if (s->prec == 32) build_pass(float(0), c); else build_pass(double(0), c);
     }
     // measurement templates
     st->pair_s = d->pair_s; st->pair_t = d->pair_t;
@@ -596,6 +752,14 @@ void structured_create(mcg_system *s, const mcg_lattice_desc *d) {
     s->maxL = 0;
     for (int o = 0; o < no; o++) s->maxL = std::max(s->maxL, (int)tm[o].size());
 
+    s->st = stp.release();
+}
+
+void structured_create(mcg_system *s, const mcg_lattice_desc *d) {
+    std::vector<SLinkD> links;
+    std::vector<double> Jt;
+    structured_build_host(s, d, links, Jt);
+    StructuredSystem *st = s->st;
     // ---- upload ----
     auto up = [&](const void *src, size_t bytes) { void *p = nullptr; MCG_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 16))); if (bytes) MCG_CUDA(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice)); return p; };
     st->d_classes = (SClassD *)up(st->classes.data(), st->classes.size() * sizeof(SClassD));
@@ -608,7 +772,31 @@ void structured_create(mcg_system *s, const mcg_lattice_desc *d) {
     MCG_CUDA(cudaMalloc(&st->d_classSums, cs));
     MCG_CUDA(cudaMemset(st->d_classSums, 0, cs));
     MCG_CUDA(cudaMalloc(&s->d_spin, (size_t)s->R * s->NC * s->N * s->real_size()));
-    s->st = stp.release();
+}
+
+// host-only check used by the CPU tests: build the class tables of a descriptor and compile the
+// specialised pass kernels of every colour with NVRTC (no device needed up to the cubin)
+int structured_jit_check(const mcg_lattice_desc *d, int precision, std::string &report) {
+    mcg_system tmp;
+    tmp.prec = precision;
+    tmp.R = 1;
+    std::vector<SLinkD> links;
+    std::vector<double> Jt;
+    structured_build_host(&tmp, d, links, Jt);
+    int ncompiled = 0;
+    std::ostringstream o;
+    o << "colours=" << tmp.C << " classes=" << tmp.st->nclass << " period=" << tmp.st->p[0] << "x" << tmp.st->p[1] << "x" << tmp.st->p[2]
+      << " V=" << tmp.st->V << "\n";
+    for (int c = 0; c < tmp.C; c++) {
+        if (!tmp.st->fastOK[c] || tmp.st->V == 1) { o << "colour " << c << ": not eligible for the fast path\n"; continue; }
+        std::string log;
+        std::vector<char> cubin = jit_compile_cubin(jit_prologue(&tmp, c), log);
+        o << "colour " << c << ": cubin " << cubin.size() << " bytes" << (log.empty() ? "" : " log: " + log.substr(0, 1500)) << "\n";
+        if (cubin.empty()) { report = o.str(); return -1; }
+        ncompiled++;
+    }
+    report = o.str();
+    return ncompiled;
 }
 
 void structured_destroy(StructuredSystem *st) {
@@ -697,6 +885,19 @@ template <int MODE> static void launch_pass(mcg_system *s, int colour, uint64_t 
     const bool prof = s->profilePasses && MODE != 2;
     if (prof) { MCG_CUDA(cudaEventCreate(&e0)); MCG_CUDA(cudaEventCreate(&e1)); MCG_CUDA(cudaEventRecord(e0, s->stream)); }
     s->launches++;
+    const int G = (MODE != 2 && st->V > 1 && !getenv("MCG_NO_FAST")) ? st->fastOK[colour] : 0;
+    if (G) {
+        bool launched = false;
+        if constexpr (MODE != 2) launched = jit_launch_pass(s, colour, MODE, a, q0, rowsPerBlock, nrb, sweep, pAtt, grid, block);
+        if (!launched)
+            sdispatch(s, [&]<int NC, typename real, bool FJ>() {
+                if constexpr (MODE != 2) {
+                    constexpr int VV = sizeof(real) == 4 ? 4 : 2;
+                    const PassTable<real> &P = *reinterpret_cast<const PassTable<real> *>(st->passTables[colour].data());
+                    k_struct_fast<NC, real, FJ, MODE, VV><<<grid, block, 0, s->stream>>>(a, P, q0, rowsPerBlock, nrb, sweep, (real)pAtt);
+                }
+            });
+    } else
     sdispatch(s, [&]<int NC, typename real, bool FJ>() {
         if (st->V == 1) k_struct<NC, real, FJ, MODE, 1><<<grid, block, 0, s->stream>>>(a, q0, nqc, rowsPerBlock, nrb, sweep, (real)pAtt);
         else if constexpr (sizeof(real) == 4) k_struct<NC, real, FJ, MODE, 4><<<grid, block, 0, s->stream>>>(a, q0, nqc, rowsPerBlock, nrb, sweep, (real)pAtt);

@@ -119,10 +119,8 @@ class System:
         check(_ffi.lib().mcg_create_tables(C.byref(st), C.byref(cfg), C.byref(h)))
         return cls(h, ta.model, ta.N, nReplica, ta.nG)
 
-    @classmethod
-    def from_spec(cls, spec, model, precision=32, nReplica=1, beta=None, field=None, seed=1, replica_offset=0, device=-1):
-        """Structured path: spec is a mcsolver_b200.lattice.LatticeSpec (bond templates + supercell)."""
-        keep = []
+    @staticmethod
+    def _desc(spec, model, keep):
         d = _ffi.LatticeDesc()
         d.model = int(model)
         d.L = (C.c_int32 * 3)(*spec.L)
@@ -139,6 +137,13 @@ class System:
         d.pair_s, d.pair_t = spec.pair[0], spec.pair[1]
         d.pair_d = (C.c_int32 * 3)(*spec.pair[2])
         d.ncircuit, d.circuits = len(spec.circuits), ptr(circ)
+        return d
+
+    @classmethod
+    def from_spec(cls, spec, model, precision=32, nReplica=1, beta=None, field=None, seed=1, replica_offset=0, device=-1):
+        """Structured path: spec is a mcsolver_b200.lattice.LatticeSpec (bond templates + supercell)."""
+        keep = []
+        d = cls._desc(spec, model, keep)
         cfg = _config(precision, nReplica, beta, field, seed, replica_offset, device, keep)
         h = C.c_void_p()
         check(_ffi.lib().mcg_create_lattice(C.byref(d), C.byref(cfg), C.byref(h)))
@@ -256,6 +261,16 @@ class System:
 # ---------------------------------------------------------------------------------------------
 # legacy one-shot calls: positional tuples in, reference-layout tuples out
 # ---------------------------------------------------------------------------------------------
+def jit_check(spec, model, precision=32):
+    """Host-only: NVRTC-compile the specialised pass kernels of a lattice; returns (n_modules, report)."""
+    keep = []
+    d = System._desc(spec, model, keep)
+    n = C.c_int(0)
+    buf = C.create_string_buffer(8192)
+    check(_ffi.lib().mcg_jit_check(C.byref(d), int(precision), C.byref(n), buf, len(buf)))
+    return n.value, buf.value.decode()
+
+
 def _as_int(x, name):
     if isinstance(x, bool) or not isinstance(x, (int, np.integer)):
         raise TypeError("%s must be an int, got %r" % (name, type(x).__name__))

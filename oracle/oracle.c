@@ -83,8 +83,8 @@ static void rng4(uint64_t seed, uint32_t replica, uint32_t stream, uint32_t sub,
     orc_philox4x32(ctr, key, out);
 }
 static double u01(uint32_t r) { return ((double)r + 0.5) * (1.0 / 4294967296.0); }
-/* fp32 engine convention: 24 random bits, (k+0.5)/2^24, evaluated exactly in double here */
-static double u01f(uint32_t r) { return ((double)(r >> 8) + 0.5) * (1.0 / 16777216.0); }
+/* fp32 engine convention: 23 random bits, (k+0.5)/2^23, evaluated exactly in double here */
+static double u01f(uint32_t r) { return ((double)(r >> 9) + 0.5) * (1.0 / 8388608.0); }
 
 /* ------------------------------------------------------------------------------------------ */
 /* physics of one configuration (spins: O(n) [N*3] with unused comps 0; Ising [N])            */
