@@ -173,12 +173,12 @@ def measured_peak():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--L", type=int, default=256)
     ap.add_argument("--replicas", type=int, default=8)
-    ap.add_argument("--sweeps", type=int, default=20, help="Metropolis sweeps (each measured) per step")
+    ap.add_argument("--sweeps", type=int, default=100, help="Metropolis sweeps (each measured) per step")
     ap.add_argument("--ref-L", type=int, default=32)
     ap.add_argument("--ref-sweeps", type=int, default=60)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -259,7 +259,7 @@ def main():
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-            "kernel": "mcg::k_struct<3,float,diagJ,MODE=1 (update+fused measure),V=4>", "bytes_per_attempt": b_alg,
+            "kernel": "mcg_pass_m1 = pass_body<NC=3,float,diagJ,MODE=1 (update + fused measurement),V=4>, NVRTC-specialised for the lattice (struct_pass.cuh)", "bytes_per_attempt": b_alg,
             "attempts_per_launch": attempts_per_launch, "avg_launch_ms": avg_launch_s * 1e3, "launches_timed": npass,
             "kernel_share_of_step": pass_ms / dev_ms, "peak_source": peak_src}
 

@@ -47,14 +47,22 @@ __device__ __forceinline__ void block_accumulate(double (&v)[NV], double *dst, d
 }
 
 template <typename real> __device__ __forceinline__ real r_sqrt(real x);
-template <> __device__ __forceinline__ float r_sqrt<float>(float x) { return sqrtf(x); }
+template <> __device__ __forceinline__ float r_sqrt<float>(float x) {
+    float y;   // one MUFU.SQRT; sqrtf() expands to a guarded Newton sequence with a slow-path call
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 template <> __device__ __forceinline__ double r_sqrt<double>(double x) { return sqrt(x); }
 template <typename real> __device__ __forceinline__ real r_rsqrt(real x);
 template <> __device__ __forceinline__ float r_rsqrt<float>(float x) { return rsqrtf(x); }
 template <> __device__ __forceinline__ double r_rsqrt<double>(double x) { return 1.0 / sqrt(x); }
 // exp(-x) for the Metropolis test.  fp32: ex2.approx (rel. err ~2^-21); fp64: libdevice exp
 template <typename real> __device__ __forceinline__ real r_exp(real x);
-template <> __device__ __forceinline__ float r_exp<float>(float x) { return __expf(x); }
+template <> __device__ __forceinline__ float r_exp<float>(float x) {
+    float y;   // FMUL + MUFU.EX2 (flush-to-zero: exp(-dE) below 1e-38 compares as 0 against u >= 2^-24 anyway)
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+}
 template <> __device__ __forceinline__ double r_exp<double>(double x) { return exp(x); }
 // sin/cos of 2*pi*u, u in (0,1)
 template <typename real> __device__ __forceinline__ void r_sincos2pi(real u, real &s, real &c);

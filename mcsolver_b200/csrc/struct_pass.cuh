@@ -230,7 +230,7 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                 bool acc;
                 if (NC == 1) {
                     const real corr = real(2) * (beta * sx * hx - hf * sx);                     // isingLib.c:242
-                    acc = att && (corr >= real(0) || r_exp<real>(corr) > u01<real>(w[2]));
+                    acc = att & ((corr >= real(0)) | (r_exp<real>(corr) > u01<real>(w[2])));   // no short-circuit: branch-free
                     sx = acc ? -sx : sx;
                 } else {
                     real n[3];
@@ -245,7 +245,7 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                         dE += dOn;
                     }
                     dE = beta * dE - hf * (NC == 3 ? tz : tx);
-                    acc = att && (dE <= real(0) || r_exp<real>(-dE) > u01<real>(w[2]));          // heisenbergLib.c:461
+                    acc = att & ((dE <= real(0)) | (r_exp<real>(-dE) > u01<real>(w[2])));       // heisenbergLib.c:461, branch-free
                     sx = acc ? nx : sx; sy = acc ? ny : sy; sz = acc ? nz : sz;
                     if (renorm) {   // every site, accepted or not
                         const real f = S * r_rsqrt<real>(sx * sx + sy * sy + sz * sz);
@@ -261,9 +261,9 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                     if (lowmode == 1) eb = sx * hx + sy * hy + sz * hz;
                     else if (lowmode == 2) eb = sx * Hl[0][v] + sy * Hl[1][v] + sz * Hl[2][v];
                     else eb = real(0);
-                    const real sv[3] = {sx, sy, sz};
-                    const real Dv[3] = {D0, D1, D2};
-                    accE += beta * eb + onsite_energy<NC, real>(sv, Dv, beta, hf);
+                    real eon = -hf * (NC == 3 ? sz : sx);
+                    if (hasD && NC > 1) eon += beta * (D0 * sx * sx + D1 * sy * sy + (NC == 3 ? D2 * sz * sz : real(0)));
+                    accE += beta * eb + eon;
                 }
             }
             real *ownw = sp + rowBase + Z0;
