@@ -178,13 +178,21 @@ MCG_API int mcg_run_on(const mcg_tables *t, int algorithm, int64_t nthermal, int
 MCG_API int mcg_run_ising(const mcg_tables *t, int algorithm, int64_t nthermal, int64_t nsweep, int64_t ninterval, double h,
                   int spinFrame, uint64_t seed, int precision, double out10[10], double *frames);
 
-/* ---- parallel tempering (new capability): replica ladder, temperature-label swaps ---- */
-/* Exchange attempt between neighbouring temperatures of the ladder held by this system (single
- * GPU) - energies come from the last measurement/energy evaluation. parity = 0/1 (even/odd pairs). */
-MCG_API int mcg_pt_swap_local(mcg_system *sys, int parity, uint64_t step);
-/* Multi-GPU: energies[] of ALL replicas of the ladder (allgathered by the host layer over NCCL) */
-MCG_API int mcg_pt_energies(mcg_system *sys, double *energies_local /*[nReplica]*/);
-MCG_API int mcg_pt_apply(mcg_system *sys, const double *beta_local, const double *field_local);
+/* ---- parallel tempering (new capability): replica ladder, temperature-LABEL swaps ----
+ * Configurations stay where they are; a swap exchanges the (beta, field) labels of two replicas.
+ * Per swap step the host layer allgathers mcg_pt_state() of all ranks (2 doubles per replica - the
+ * only data crossing NVLink), every rank calls mcg_pt_decide() (pure host arithmetic, same Philox
+ * draw everywhere) and applies its share with mcg_pt_set_labels().  Accumulators are per label
+ * (mcg_pt_configure), mcg_results(sys, label) reads them; sum them over ranks at the end. */
+MCG_API int mcg_pt_configure(mcg_system *sys, int nLabels);
+MCG_API int mcg_pt_state(mcg_system *sys, double *state /*[nReplica][2] = E0, M_axis*/);
+MCG_API int mcg_pt_set_labels(mcg_system *sys, const int32_t *label, const double *beta, const double *field);
+MCG_API int mcg_pt_decide(int n, const double *beta, const double *field, const double *E0, const double *M, int32_t *holder,
+                          int parity, uint64_t seed, uint64_t step, int32_t *accepted);
+/* raw accumulator row of a label (NACC doubles, plain sums over measured sweeps) for cross-rank reduction,
+ * and its inverse; n_acc = row length. */
+MCG_API int mcg_acc_get(mcg_system *sys, int label, double *row, int *n_acc);
+MCG_API int mcg_acc_set(mcg_system *sys, int label, const double *row);
 
 #ifdef __cplusplus
 }

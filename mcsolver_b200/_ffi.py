@@ -70,9 +70,12 @@ SIGNATURES = {
     "mcg_run": (_i, [_vp, _i, _i64, _i64, _i64, _i, _vp]),
     "mcg_run_on": (_i, [C.POINTER(Tables), _i, _i64, _i64, _i64, _d, _d, _i, _u64, _i, _vp, _vp, _vp]),
     "mcg_run_ising": (_i, [C.POINTER(Tables), _i, _i64, _i64, _i64, _d, _i, _u64, _i, _vp, _vp]),
-    "mcg_pt_swap_local": (_i, [_vp, _i, _u64]),
-    "mcg_pt_energies": (_i, [_vp, _vp]),
-    "mcg_pt_apply": (_i, [_vp, _vp, _vp]),
+    "mcg_pt_configure": (_i, [_vp, _i]),
+    "mcg_pt_state": (_i, [_vp, _vp]),
+    "mcg_pt_set_labels": (_i, [_vp, _vp, _vp, _vp]),
+    "mcg_pt_decide": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _u64, _u64, _vp]),
+    "mcg_acc_get": (_i, [_vp, _i, _vp, _vp]),
+    "mcg_acc_set": (_i, [_vp, _i, _vp]),
 }
 
 

@@ -155,6 +155,12 @@ static void alloc_replica_state(mcg_system *s, const mcg_config *cfg) {
     s->d_field = dupload(s->field_host);
     s->d_sums = dalloc<double>((size_t)s->R * NSUM);
     s->d_acc = dalloc<double>((size_t)s->R * NACC);
+    s->nLabel = s->R;
+    s->slot_host.resize(s->R);
+    for (int r = 0; r < s->R; r++) s->slot_host[r] = r;
+    s->d_slot = dupload(s->slot_host);
+    s->d_last = dalloc<double>(4 * (size_t)s->R);
+    MCG_CUDA(cudaMemset(s->d_last, 0, sizeof(double) * 4 * s->R));
     s->d_cnt = dalloc<unsigned long long>((size_t)s->R * NCNT);
     MCG_CUDA(cudaMemset(s->d_sums, 0, sizeof(double) * s->R * NSUM));
     MCG_CUDA(cudaMemset(s->d_acc, 0, sizeof(double) * s->R * NACC));
@@ -302,7 +308,7 @@ static void launch_measure_sums(mcg_system *s, int siteRep, double *eb, double *
 static void measure(mcg_system *s) {
     launch_measure_sums(s, -1, nullptr, nullptr);
     s->launches++;
-    k_finalize_sweep<<<(s->R + 63) / 64, 64, 0, s->stream>>>(s->model, s->R, s->N, s->nLat, s->d_sums, s->d_acc);
+    k_finalize_sweep<<<(s->R + 63) / 64, 64, 0, s->stream>>>(s->model, s->R, s->N, s->nLat, s->d_sums, s->d_acc, s->d_slot, s->d_last);
     MCG_CUDA(cudaGetLastError());
 }
 
@@ -407,7 +413,7 @@ static void run(mcg_system *s, int algorithm, int64_t nthermal, int64_t nsweep, 
         }
         if (fused) {
             s->launches++;
-            k_finalize_sweep<<<(s->R + 63) / 64, 64, 0, s->stream>>>(s->model, s->R, s->N, s->nLat, s->d_sums, s->d_acc);
+            k_finalize_sweep<<<(s->R + 63) / 64, 64, 0, s->stream>>>(s->model, s->R, s->N, s->nLat, s->d_sums, s->d_acc, s->d_slot, s->d_last);
             MCG_CUDA(cudaGetLastError());
         } else measure(s);
         if ((i & 255) == 255) MCG_CUDA(cudaStreamSynchronize(s->stream));   // bound the launch queue
@@ -416,7 +422,7 @@ static void run(mcg_system *s, int algorithm, int64_t nthermal, int64_t nsweep, 
 }
 
 static void results(mcg_system *s, int r, double *out, double *groupOut) {
-    MCG_REQUIRE(r >= 0 && r < s->R && out, "bad replica index or NULL out");
+    MCG_REQUIRE(r >= 0 && r < s->nLabel && out, "bad replica/label index or NULL out");
     double A[NACC];
     MCG_CUDA(cudaStreamSynchronize(s->stream));
     MCG_CUDA(cudaMemcpy(A, s->d_acc + (size_t)r * NACC, sizeof(A), cudaMemcpyDeviceToHost));
@@ -445,7 +451,7 @@ static void results(mcg_system *s, int r, double *out, double *groupOut) {
 mcg_system::~mcg_system() {
     cudaSetDevice(device);
     void *bufs[] = {d_nbrp, d_site_of, d_pos_of, d_pairs, d_tri, d_mi, d_mj, d_jtype, d_cls, d_Jtab, d_clsS, d_clsD, d_spin,
-                    d_signS, d_beta, d_field, d_sums, d_acc, d_cnt, d_scratch, d_parent, d_proj, d_wres};
+                    d_signS, d_beta, d_field, d_sums, d_acc, d_cnt, d_scratch, d_parent, d_proj, d_wres, d_slot, d_last};
     for (void *b : bufs) if (b) cudaFree(b);
     if (st) mcg::structured_destroy(st);
     if (stream) cudaStreamDestroy(stream);
@@ -560,7 +566,7 @@ MCG_API int mcg_timed_sweeps(mcg_system *sys, int64_t nsweeps, double pAttempt, 
                 if (sys->structured) {
                     structured_sweeps(sys, 1, pAttempt, true);
                     sys->launches++;
-                    k_finalize_sweep<<<(sys->R + 63) / 64, 64, 0, sys->stream>>>(sys->model, sys->R, sys->N, sys->nLat, sys->d_sums, sys->d_acc);
+                    k_finalize_sweep<<<(sys->R + 63) / 64, 64, 0, sys->stream>>>(sys->model, sys->R, sys->N, sys->nLat, sys->d_sums, sys->d_acc, sys->d_slot, sys->d_last);
                 } else {
                     metropolis_sweeps(sys, 1, pAttempt);
                     measure(sys);
@@ -584,7 +590,7 @@ MCG_API int mcg_measure(mcg_system *sys) {
 }
 MCG_API int mcg_reset_measurements(mcg_system *sys) {
     SYS_GUARD({
-        MCG_CUDA(cudaMemsetAsync(sys->d_acc, 0, sizeof(double) * sys->R * NACC, sys->stream));
+        MCG_CUDA(cudaMemsetAsync(sys->d_acc, 0, sizeof(double) * sys->nLabel * NACC, sys->stream));
         MCG_CUDA(cudaMemsetAsync(sys->d_sums, 0, sizeof(double) * sys->R * NSUM, sys->stream));
         MCG_CUDA(cudaMemsetAsync(sys->d_cnt, 0, sizeof(unsigned long long) * sys->R * NCNT, sys->stream));
         MCG_CUDA(cudaStreamSynchronize(sys->stream));
@@ -592,6 +598,21 @@ MCG_API int mcg_reset_measurements(mcg_system *sys) {
 }
 MCG_API int mcg_results(mcg_system *sys, int replica, double *out, double *groupOut) { SYS_GUARD(results(sys, replica, out, groupOut)); }
 
+MCG_API int mcg_acc_get(mcg_system *sys, int label, double *row, int *n_acc) {
+    SYS_GUARD({
+        MCG_REQUIRE(label >= 0 && label < sys->nLabel && row, "bad label or NULL row");
+        MCG_CUDA(cudaStreamSynchronize(sys->stream));
+        MCG_CUDA(cudaMemcpy(row, sys->d_acc + (size_t)label * NACC, sizeof(double) * NACC, cudaMemcpyDeviceToHost));
+        if (n_acc) *n_acc = NACC;
+    });
+}
+MCG_API int mcg_acc_set(mcg_system *sys, int label, const double *row) {
+    SYS_GUARD({
+        MCG_REQUIRE(label >= 0 && label < sys->nLabel && row, "bad label or NULL row");
+        MCG_CUDA(cudaStreamSynchronize(sys->stream));
+        MCG_CUDA(cudaMemcpy(sys->d_acc + (size_t)label * NACC, row, sizeof(double) * NACC, cudaMemcpyHostToDevice));
+    });
+}
 MCG_API int mcg_counters(mcg_system *sys, int replica, int64_t *attempts, int64_t *accepted, int64_t *cluster_sites) {
     SYS_GUARD({
         MCG_REQUIRE(replica >= 0 && replica < sys->R, "bad replica index");

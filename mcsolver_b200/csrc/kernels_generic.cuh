@@ -193,10 +193,11 @@ __global__ void __launch_bounds__(256) k_topo_generic(GenArgs a, int nTri, const
 //   O(n):  heisenbergLib.c:677-744 / xyLib.c:605-673      Ising: isingLib.c:395-431
 // All projections are linear in the sums:  sum_j n.s_j = n.(sum_j s_j).
 // ---------------------------------------------------------------------------------------------
-__global__ void k_finalize_sweep(int model, int R, int N, int nLat, double *sums, double *acc) {
+__global__ void k_finalize_sweep(int model, int R, int N, int nLat, double *sums, double *acc, const int32_t *slot, double *last) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
-    double *s = sums + (size_t)r * NSUM, *A = acc + (size_t)r * NACC;
+    double *s = sums + (size_t)r * NSUM, *A = acc + (size_t)slot[r] * NACC;
+    last[4 * r] = s[SUM_E]; last[4 * r + 1] = s[SUM_TOT]; last[4 * r + 2] = s[SUM_TOT + 1]; last[4 * r + 3] = s[SUM_TOT + 2];
     double nl = (double)nLat;
     double E = s[SUM_E];
     double e_avg = E / N;

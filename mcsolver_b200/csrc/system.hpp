@@ -57,6 +57,12 @@ struct mcg_system {
     double *d_signS = nullptr;           // [N] signed S (storage order) for init
     int nJ = 0, ncls = 0;
     double *d_beta = nullptr, *d_field = nullptr, *d_sums = nullptr, *d_acc = nullptr;
+    // parallel tempering: accumulators live per temperature LABEL (nLabel >= R slots), replica r
+    // accumulates into slot d_slot[r]; d_last[r] = {reduced energy, Mx, My, Mz} of the last measured sweep
+    int nLabel = 0;
+    int32_t *d_slot = nullptr;
+    double *d_last = nullptr;
+    std::vector<int32_t> slot_host;
     unsigned long long *d_cnt = nullptr;
     double *d_scratch = nullptr;         // [2N] per-site energies / frame staging (3N)
     // wolff

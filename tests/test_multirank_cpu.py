@@ -1,0 +1,87 @@
+"""CPU tests of the N>1 host logic with a world_size-2 gloo group: grid sharding, the parallel-
+tempering ladder bookkeeping and the determinism of the swap decisions across ranks.  No GPU: the
+engine is replaced by a synthetic energy model; mcg_pt_decide is pure host code in the C-ABI library."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys, json
+import numpy as np
+sys.path.insert(0, os.environ["MCG_ROOT"])
+import torch.distributed as dist
+from mcsolver_b200 import pt, scan
+dist.init_process_group(backend="gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+n = 16
+T = np.linspace(1.0, 2.5, n)
+lad = pt.Ladder(1.0 / T, np.zeros(n), rank=rank, world=world, seed=7)
+ag = pt.torch_allgather(None)
+rng = np.random.RandomState(100 + rank)
+lo, hi = lad.lo, lad.hi
+hist = []
+for step in range(40):
+    labels = lad.local_labels()
+    # synthetic replica state: energy fluctuating around -N*T_label-dependent mean (overlapping distributions)
+    e_local = -100.0 / T[labels] + 3.0 * rng.randn(hi - lo)
+    st = np.stack([e_local, np.zeros(hi - lo)], axis=1)
+    lad.exchange(ag(st.reshape(-1)))
+    hist.append(lad.holder.tolist())
+out = dict(rank=rank, lo=lo, hi=hi, holder=lad.holder.tolist(), hist=hist, acc=lad.accepts.tolist(), att=lad.attempts.tolist(),
+           shard=[list(scan.shard(21, r, world)) for r in range(world)])
+json.dump(out, open(os.environ["MCG_OUT"] + ".%d" % rank, "w"))
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_ladder_is_consistent_across_two_gloo_ranks(tmp_path):
+    import json
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    out = str(tmp_path / "out.json")
+    env = dict(os.environ, MCG_ROOT=ROOT, MCG_OUT=out, OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), str(script)]
+    subprocess.run(cmd, env=env, check=True, timeout=300, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    r0, r1 = (json.load(open(out + ".%d" % r)) for r in range(2))
+    # both ranks drew the same decisions from the same allgathered state
+    assert r0["hist"] == r1["hist"] and r0["holder"] == r1["holder"]
+    assert sorted(r0["holder"]) == list(range(16))                     # labels stay a permutation of replicas
+    assert (r0["lo"], r0["hi"], r1["lo"], r1["hi"]) == (0, 8, 8, 16)   # contiguous blocks
+    assert sum(r0["acc"]) > 0 and sum(r0["acc"]) < sum(r0["att"])      # some, not all, swaps accepted
+    assert r0["shard"] == [[0, 11], [11, 21]]                          # ragged split of 21 grid points
+    # labels actually travel between the two ranks' blocks
+    assert any(h != list(range(16)) for h in r0["hist"])
+    assert any(set(h[:8]) != set(range(8)) for h in r0["hist"])
+
+
+def test_decide_detailed_balance_limits():
+    from mcsolver_b200 import pt
+    beta = np.array([1.0, 0.5])
+    # replica 0 (cold label) has HIGHER energy than replica 1: swapping lowers the action -> always accepted
+    hold, acc = pt.decide(beta, [0, 0], [5.0, -5.0], [0, 0], [0, 1], 0, 1, 0)
+    assert hold.tolist() == [1, 0] and acc[0] == 1
+    # the reverse costs Delta = (b0-b1)*(E1-E0) = 0.5*40 = 20: accepted with prob e^-20 -> essentially never
+    n_acc = sum(pt.decide(beta, [0, 0], [-20.0, 20.0], [0, 0], [0, 1], 0, 1, s)[1][0] for s in range(200))
+    assert n_acc == 0
+    # equal energies: always accepted; parity 1 leaves pair (0,1) untouched
+    assert pt.decide(beta, [0, 0], [1.0, 1.0], [0, 0], [0, 1], 0, 1, 3)[1][0] == 1
+    assert pt.decide(beta, [0, 0], [5.0, -5.0], [0, 0], [0, 1], 1, 1, 0)[0].tolist() == [0, 1]
+    # acceptance frequency matches exp(-Delta) for a moderate Delta = 0.5*(1.0) = 0.5 -> 0.6065
+    n = 4000
+    f = sum(pt.decide(beta, [0, 0], [0.0, 1.0], [0, 0], [0, 1], 0, 11, s)[1][0] for s in range(n)) / n
+    assert abs(f - np.exp(-0.5)) < 4 * np.sqrt(0.6065 * 0.3935 / n)
