@@ -10,6 +10,7 @@
 #include <map>
 #include <numeric>
 
+#include "kernels_extra.cuh"
 #include "kernels_wolff.cuh"
 #include "structured.hpp"
 
@@ -241,16 +242,65 @@ static mcg_system *create_from_tables(const mcg_tables *t, const mcg_config *cfg
     }
     for (int j = 0; j < 3 * s->nTri; j++) tri[j] = s->pos_of[t->tri[j]];
     s->nG = t->nG; s->maxG = t->maxG; s->nR = t->nR; s->nC = t->nC;
+    if (s->nG > 0) MCG_REQUIRE(t->groups && t->maxG >= 1, "orbGroupList is NULL");
+    if (s->nR > 0) MCG_REQUIRE(t->rOrb && t->rCl && t->rNbr && t->nC >= 1, "block-spin tables are NULL");
+    std::vector<int32_t> groupsP((size_t)s->nG * std::max(1, s->maxG), -1);
+    for (size_t i = 0; i < groupsP.size() && s->nG > 0; i++) {
+        int o = t->groups[i];
+        MCG_REQUIRE(o < N, "orbGroupList index out of range");
+        groupsP[i] = o < 0 ? -1 : s->pos_of[o];
+    }
+    std::vector<int32_t> rowOf(N, -1), rPos(s->nR), rClP((size_t)s->nR * std::max(1, s->nC)), rNbrRow((size_t)s->nR * s->maxL, -1), rNl(s->nR);
+    std::vector<int32_t> pairRowI(t->nLat, -1), pairRowJ(t->nLat, -1);
+    for (int i = 0; i < s->nR; i++) { MCG_REQUIRE(t->rOrb[i] >= 0 && t->rOrb[i] < N, "rOrb index out of range"); rowOf[t->rOrb[i]] = i; }
+    for (int i = 0; i < s->nR; i++) {
+        int o = t->rOrb[i];
+        rPos[i] = s->pos_of[o];
+        rNl[i] = t->nlink[o];
+        for (int q = 0; q < s->nC; q++) {
+            int m = t->rCl[(size_t)i * s->nC + q];
+            MCG_REQUIRE(m >= 0 && m < N, "rOrbCluster index out of range");
+            rClP[(size_t)i * s->nC + q] = s->pos_of[m];
+        }
+        for (int k = 0; k < maxL; k++) {
+            int nb = t->rNbr[(size_t)i * maxL + k];
+            MCG_REQUIRE(nb < N, "linkedOrb_rnorm index out of range");
+            rNbrRow[(size_t)i * s->maxL + k] = nb < 0 ? -1 : rowOf[nb];   // reference: UB for -1 / unchosen (odd or tiny supercells); skipped
+        }
+    }
+    for (int j = 0; j < t->nLat && s->nR > 0; j++) {
+        pairRowI[j] = rowOf[t->pairs[2 * j]]; pairRowJ[j] = rowOf[t->pairs[2 * j + 1]];
+        if (pairRowI[j] >= 0) s->rg_ci += 1;
+        if (pairRowJ[j] >= 0) s->rg_cj += 1;
+        if (pairRowI[j] >= 0 && pairRowJ[j] >= 0) s->rg_cij += 1;
+    }
 
     s->d_nbrp = dupload(nbrp); s->d_jtype = dupload(jtype); s->d_cls = dupload(cls);
     s->d_site_of = dupload(s->site_of); s->d_pos_of = dupload(s->pos_of);
     s->d_pairs = dupload(pairs); s->d_tri = dupload(tri); s->d_mi = dupload(mi); s->d_mj = dupload(mj);
     s->d_signS = dupload(signS);
+    if (s->nG > 0) s->d_groups = dupload(groupsP);
+    if (s->nR > 0) {
+        s->d_rPos = dupload(rPos); s->d_rCl = dupload(rClP); s->d_rNbrRow = dupload(rNbrRow); s->d_rNl = dupload(rNl);
+        s->d_pairRowI = dupload(pairRowI); s->d_pairRowJ = dupload(pairRowJ);
+    }
     if (s->prec == 64) { s->d_Jtab = dupload_real<double>(Jtab); s->d_clsS = dupload_real<double>(clsS); s->d_clsD = dupload_real<double>(clsD); }
     else { s->d_Jtab = dupload_real<float>(Jtab); s->d_clsS = dupload_real<float>(clsS); s->d_clsD = dupload_real<float>(clsD); }
     MCG_CUDA(cudaMalloc(&s->d_spin, (size_t)s->R * s->NC * N * s->real_size()));
     s->d_scratch = dalloc<double>(3 * (size_t)N);
     alloc_replica_state(s, cfg);
+    if (s->nR > 0) {
+        s->d_ms = dalloc<double>((size_t)s->R * s->nR * 3);
+        s->d_rsums = dalloc<double>((size_t)s->R * NRS);
+        MCG_CUDA(cudaMemset(s->d_rsums, 0, sizeof(double) * s->R * NRS));
+    }
+    if (s->nG > 0) {
+        size_t n1 = s->nG + 1;
+        s->d_gsum = dalloc<double>((size_t)s->R * n1 * 3);
+        s->d_gacc = dalloc<double>((size_t)s->R * (n1 + 1) * n1);
+        MCG_CUDA(cudaMemset(s->d_gsum, 0, sizeof(double) * s->R * n1 * 3));
+        MCG_CUDA(cudaMemset(s->d_gacc, 0, sizeof(double) * s->R * (n1 + 1) * n1));
+    }
     MCG_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     return sys.release();
 }
@@ -305,8 +355,35 @@ static void launch_measure_sums(mcg_system *s, int siteRep, double *eb, double *
     MCG_CUDA(cudaGetLastError());
 }
 
+static void launch_extras(mcg_system *s) {
+    if (s->structured || (s->nR == 0 && s->nG == 0)) return;
+    GenArgs a = gen_args(s);
+    if (s->nR > 0) {
+        RgArgs g;
+        g.nR = s->nR; g.nC = s->nC; g.nLat = s->nLat; g.rPos = s->d_rPos; g.rCl = s->d_rCl; g.rNbrRow = s->d_rNbrRow; g.rNl = s->d_rNl;
+        g.pairRowI = s->d_pairRowI; g.pairRowJ = s->d_pairRowJ; g.ms = s->d_ms; g.rsums = s->d_rsums; g.meas = s->measCtr;
+        dispatch(s, [&]<int NC, typename real, bool FJ>() {
+            k_rg_majority<NC, real><<<grid_for(s->nR, s->R), 256, 0, s->stream>>>(a, g, s->d_signS);
+            k_rg_sums<NC, real, FJ><<<grid_for(std::max(s->nR, s->nLat), s->R), 256, 0, s->stream>>>(a, g);
+        });
+        s->launches += 2;
+    }
+    if (s->nG > 0 && s->model != MCG_ISING) {
+        dispatch(s, [&]<int NC, typename real, bool FJ>() {
+            k_group_sums<NC, real><<<dim3(s->nG, s->R), 256, 0, s->stream>>>(a, s->nG, s->maxG, s->d_groups, s->d_gsum);
+        });
+        s->launches++;
+    }
+    k_extra_finalize<<<(s->R + 63) / 64, 64, 0, s->stream>>>(s->model, s->R, s->nLat, s->nR, s->rg_ci, s->rg_cj, s->rg_cij, s->nG,
+                                                              s->d_sums, s->d_rsums, s->d_gsum, s->d_acc, s->d_gacc, s->d_slot);
+    s->launches++;
+    s->measCtr++;
+    MCG_CUDA(cudaGetLastError());
+}
+
 static void measure(mcg_system *s) {
     launch_measure_sums(s, -1, nullptr, nullptr);
+    launch_extras(s);
     s->launches++;
     k_finalize_sweep<<<(s->R + 63) / 64, 64, 0, s->stream>>>(s->model, s->R, s->N, s->nLat, s->d_sums, s->d_acc, s->d_slot, s->d_last);
     MCG_CUDA(cudaGetLastError());
@@ -443,7 +520,14 @@ static void results(mcg_system *s, int r, double *out, double *groupOut) {
     out[20] = A[ACC_SIZ] / ns; out[21] = A[ACC_SJZ] / ns; out[22] = A[ACC_STZ] / ns;
     out[23] = A[ACC_SIH] / ns; out[24] = A[ACC_SJH] / ns; out[25] = A[ACC_STH] / ns;
     out[26] = A[ACC_Q] / ns;
-    if (groupOut) for (int i = 0; i < (s->nG + 2) * (s->nG + 1); i++) groupOut[i] = 0.0;
+    if (groupOut) {
+        int n = (s->nG + 2) * (s->nG + 1);
+        if (s->d_gacc && r < s->nLabel) {
+            MCG_CUDA(cudaMemcpy(groupOut, s->d_gacc + (size_t)r * n, sizeof(double) * n, cudaMemcpyDeviceToHost));
+            for (int i = 0; i < n; i++) groupOut[i] /= ns;
+        } else
+            for (int i = 0; i < n; i++) groupOut[i] = 0.0;
+    }
 }
 
 }  // namespace mcg
@@ -451,7 +535,8 @@ static void results(mcg_system *s, int r, double *out, double *groupOut) {
 mcg_system::~mcg_system() {
     cudaSetDevice(device);
     void *bufs[] = {d_nbrp, d_site_of, d_pos_of, d_pairs, d_tri, d_mi, d_mj, d_jtype, d_cls, d_Jtab, d_clsS, d_clsD, d_spin,
-                    d_signS, d_beta, d_field, d_sums, d_acc, d_cnt, d_scratch, d_parent, d_proj, d_wres, d_slot, d_last};
+                    d_signS, d_beta, d_field, d_sums, d_acc, d_cnt, d_scratch, d_parent, d_proj, d_wres, d_slot, d_last, d_rPos, d_rCl, d_rNbrRow, d_rNl, d_pairRowI, d_pairRowJ, d_groups, d_ms, d_rsums,
+                    d_gsum, d_gacc};
     for (void *b : bufs) if (b) cudaFree(b);
     if (st) mcg::structured_destroy(st);
     if (stream) cudaStreamDestroy(stream);
@@ -593,6 +678,8 @@ MCG_API int mcg_reset_measurements(mcg_system *sys) {
         MCG_CUDA(cudaMemsetAsync(sys->d_acc, 0, sizeof(double) * sys->nLabel * NACC, sys->stream));
         MCG_CUDA(cudaMemsetAsync(sys->d_sums, 0, sizeof(double) * sys->R * NSUM, sys->stream));
         MCG_CUDA(cudaMemsetAsync(sys->d_cnt, 0, sizeof(unsigned long long) * sys->R * NCNT, sys->stream));
+        if (sys->d_gacc) MCG_CUDA(cudaMemsetAsync(sys->d_gacc, 0, sizeof(double) * sys->nLabel * (sys->nG + 2) * (sys->nG + 1), sys->stream));
+        sys->measCtr = 0;
         MCG_CUDA(cudaStreamSynchronize(sys->stream));
     });
 }

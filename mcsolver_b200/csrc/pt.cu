@@ -36,6 +36,13 @@ MCG_API int mcg_pt_configure(mcg_system *sys, int nLabels) {
         sys->d_acc = nullptr;
         MCG_CUDA(cudaMalloc(&sys->d_acc, sizeof(double) * (size_t)nLabels * NACC));
         MCG_CUDA(cudaMemset(sys->d_acc, 0, sizeof(double) * (size_t)nLabels * NACC));
+        if (sys->d_gacc) {   // per-label group accumulators follow
+            size_t n = (size_t)(sys->nG + 2) * (sys->nG + 1);
+            cudaFree(sys->d_gacc);
+            sys->d_gacc = nullptr;
+            MCG_CUDA(cudaMalloc(&sys->d_gacc, sizeof(double) * nLabels * n));
+            MCG_CUDA(cudaMemset(sys->d_gacc, 0, sizeof(double) * nLabels * n));
+        }
         sys->nLabel = nLabels;
     });
 }

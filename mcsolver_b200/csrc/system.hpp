@@ -65,6 +65,12 @@ struct mcg_system {
     std::vector<int32_t> slot_host;
     unsigned long long *d_cnt = nullptr;
     double *d_scratch = nullptr;         // [2N] per-site energies / frame staging (3N)
+    // block-spin (RG) and orbital-group statistics (table path)
+    int32_t *d_rPos = nullptr, *d_rCl = nullptr, *d_rNbrRow = nullptr, *d_rNl = nullptr, *d_pairRowI = nullptr, *d_pairRowJ = nullptr;
+    int32_t *d_groups = nullptr;
+    double *d_ms = nullptr, *d_rsums = nullptr, *d_gsum = nullptr, *d_gacc = nullptr;
+    double rg_ci = 0, rg_cj = 0, rg_cij = 0;
+    uint64_t measCtr = 0;
     // wolff
     int32_t *d_parent = nullptr;         // [R][N]
     void *d_proj = nullptr;              // [R][N] real

@@ -640,7 +640,7 @@ void orc_observe_on(const orc_sys *s, const double *sp, double *out27, double *g
 /* ------------------------------------------------------------------------------------------ */
 /* Ising - isingLib.c                                                                         */
 /* ------------------------------------------------------------------------------------------ */
-static double ising_majority(const orc_sys *s, const double *sp, int row, int use_rand, uint32_t *tiectr) {
+static double ising_majority(const orc_sys *s, const double *sp, int row, int use_rand, uint64_t seed, uint32_t replica, uint64_t meas) {
     /* getMajoritySpin - isingLib.c:133-150; ties are broken with rand() in the reference */
     double avg = 0;
     for (int q = 0; q < s->nC; q++) avg += sp[s->rCl[(size_t)row * s->nC + q]];
@@ -648,8 +648,9 @@ static double ising_majority(const orc_sys *s, const double *sp, int row, int us
     if (avg > 0) return a;
     if (avg < 0) return -a;
     if (use_rand) return (rand() / (double)RAND_MAX > 0.5) ? a : -a;
-    (*tiectr)++;
-    return ((*tiectr) & 1) ? a : -a;
+    uint32_t w[4]; /* engine convention: stream 5 (block-spin ties), counter = (site, measurement index) */
+    rng4(seed, replica, 5, 0, meas, (uint32_t)s->rOrb[row], w);
+    return u01(w[0]) > 0.5 ? a : -a;
 }
 static void ising_local_update_ref(const orc_sys *s, double *sp, orc_state *st) { /* isingLib.c:238-254 */
     int i = ref_random_site(s->N);
@@ -722,7 +723,6 @@ int orc_run_ising(const orc_sys *s, int update_mode, long nthermal, long nsweep,
     orc_state st;
     memset(&st, 0, sizeof st);
     uint64_t sweepCtr = 0;
-    uint32_t tiectr = 0;
     long nsub = 1;
     double pAtt = 1.0;
     if (update_mode == 2) {
@@ -779,11 +779,11 @@ int orc_run_ising(const orc_sys *s, int update_mode, long nthermal, long nsweep,
             int o = s->rOrb[row];
             const double *J = isingJ(s, o);
             double corr = 0;
-            double ms = ising_majority(s, sp, row, update_mode <= 1, &tiectr);
+            double ms = ising_majority(s, sp, row, update_mode <= 1, seed, replica, (uint64_t)isw);
             for (int k = 0; k < s->nlink[o]; k++) {
                 int t = s->rNbr[(size_t)row * s->maxL + k];
                 if (t < 0 || rowOf[t] < 0) continue; /* reference: UB (odd supercell); skipped here */
-                double mt = ising_majority(s, sp, rowOf[t], update_mode <= 1, &tiectr);
+                double mt = ising_majority(s, sp, rowOf[t], update_mode <= 1, seed, replica, (uint64_t)isw);
                 corr += J[k] * ms * mt;
             }
             er += corr / 2 - s->h * sp[o];

@@ -33,6 +33,6 @@ def rel_err(a, b):
     return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)) if a.size else 0.0
 
 
-# result-tuple slots that are defined for this engine version.  11-19 (block-spin statistics) and
-# 28 (orbital-group statistics) are SURVEY 8 (f3) "next" rows; 7 (autoCorr) depends on the dynamics.
+# result-tuple slots compared on one configuration / one trajectory; 7 (autoCorr) needs two sweeps.
 ON_CORE_SLOTS = [0, 1, 2, 3, 4, 5, 6, 8, 9, 10, 20, 21, 22, 23, 24, 25, 26]
+ON_RG_SLOTS = [11, 12, 13, 14, 15, 16, 17, 18, 19]    # block-spin statistics (table path)
