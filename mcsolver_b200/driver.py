@@ -1,0 +1,88 @@
+"""`loadMC(parameterfile)` on the GPU: the reference's headless entry (mcsolver/__init__.py:16-17 ->
+win.py:40-159) with the whole (H,T) grid run as one replica batch instead of a process pool.
+
+Writes the same files in the current directory: `./out` (one labelled line per point, mcMain.py:128-132 /
+:261-265), `./result.txt` (win.py:152-156, 10 columns %15.6E) and `./spinDotSpin.txt` (mcMain.py:274-289).
+Rows appear in grid order (the reference writes them in task-completion order).
+"""
+import os
+import time
+
+import numpy as np
+
+from . import engine, paramfile, scan
+
+
+def _write_out_line(f, model, T, h, r, extra=None):
+    if model == engine.ISING:     # mcMain.py:126-132
+        si, sj, sij, auto, E, E2, Er, E2r, U4, stot = r[:10]
+        E, E2, Er, E2r = E * T, E2 * T ** 2, Er * T, E2r * T ** 2
+        f.write("%.3f %.3f %.3f %.3f %.3f %.3f %.3f %.3f %.3f %.3f %.6f\n" % (T, h, si, sj, stot, sij, E, E2, Er, E2r, U4))
+        return
+    si, sj = r[0:3], r[3:6]          # mcMain.py:250-265
+    sir, sjr = r[11:14], r[14:17]
+    E, E2, Er, E2r = r[8] * T, r[9] * T ** 2, r[18] * T, r[19] * T ** 2
+    f.write('T= %.6E h= %.6E <Siz>= %.6E <Sjz>= %.6E <Sz>= %.6E <Sih>= %.6E <Sjh>= %.6E <Sh>= %.6E <Si>= %.6E <Sj>= %.6E <SiSj>= %.6E '
+            '<Si><Sj>= %.6E <E>= %.6E <E^2>= %.6E <U4>= %.6E <SiSj>r= %.6E <Si>r<Sj>r= %.6E <Er>= %.6E <E^2_r>= %.6E <Q>= %.6E\n' % (
+                T, h, r[20], r[21], r[22], r[23], r[24], r[25], np.linalg.norm(si), np.linalg.norm(sj), r[6], np.dot(si, sj), E, E2, r[10],
+                r[17], np.dot(sir, sjr), Er, E2r, r[26]))
+
+
+def loadMC(rpath, precision=None, seed=None, rank=0, world=1, device=-1, workdir=".", table_limit=200000, quiet=False):
+    """Run the simulation described by a reference parameter file.  Returns the result table
+    (dict of columns, as written to result.txt).  With world > 1 each rank runs its share of the
+    grid and returns only its rows; rank 0 should gather and write (see scripts/)."""
+    t0 = time.time()
+    p = paramfile.parse(rpath)
+    if abs(p.dipoleAlpha) > 1e-5:
+        raise NotImplementedError("dipole coupling: the reference's own path raises (Lattice.py:298); not built in this round")
+    if p.algorithm not in ("Metropolis", "Wolff"):
+        raise ValueError("only Metropolis and Wolff algorithm is supported")
+    model = p.model
+    spec = p.spec()
+    T, H = p.grid()
+    Tf = np.maximum(T, 0.1)
+    algo = engine.WOLFF if p.algorithm == "Wolff" else engine.METROPOLIS
+    prec = engine.default_precision() if precision is None else precision
+    sd = engine.default_seed() if seed is None else seed
+    use_tables = algo == engine.WOLFF or spec.nsite <= table_limit     # full tuples (block-spin, groups) when affordable
+    ninterval = spec.nsite if p.ninterval <= 0 else p.ninterval
+    idx, rows, frames = scan.run_points(spec, model, T, H, p.nthermal, p.nsweep, ninterval=ninterval, algorithm=algo, precision=prec,
+                                        seed=sd, rank=rank, world=world, device=device, spin_frames=p.spinFrame, tables=use_tables,
+                                        want_groups=True)
+    rows, groups = rows
+    obs = scan.observables(rows, Tf[idx], spec.nsite, model)
+    if rank == 0:
+        with open(os.path.join(workdir, "out"), "w") as f:
+            f.write("#T #H\n")
+            for k, i in enumerate(idx):
+                _write_out_line(f, model, Tf[i], H[i], rows[k])
+        with open(os.path.join(workdir, "spinDotSpin.txt"), "w") as f:
+            f.write("#T #H\n")
+            if model != engine.ISING and groups is not None and len(p.orbGroupList) > 0:
+                for k, i in enumerate(idx):
+                    f.write("%.3f %.3f " % (Tf[i], H[i]) + "".join("%.6f " % v for v in groups[k]) + "\n")
+        with open(os.path.join(workdir, "result.txt"), "w") as f:
+            f.write("#Temp          #Field         #<Si>          #<Sj>          #Susc          #Energy(K)     #Capacity(K/K) #Topo.Q        #U4            #Auto-corr.    \n")
+            for k, i in enumerate(idx):
+                f.write("%15.6E%15.6E%15.6E%15.6E%15.6E%15.6E%15.6E%15.6E%15.6E%15.6E\n" % (
+                    Tf[i], H[i], obs["Si"][k], obs["Sj"][k], obs["Susc"][k], obs["Energy"][k], obs["Capacity"][k], obs["TopoQ"][k],
+                    obs["U4"][k], obs["AutoCorr"][k]))
+        if p.spinFrame > 0 and frames is not None:
+            from .lattice import positions
+            xyz = positions(spec)
+            for k, i in enumerate(idx):
+                for fr in range(p.spinFrame):
+                    if model == engine.ISING:    # mcMain.py:291-297
+                        name = "IsingSpinDistribution.T%.3f.H%.3f.%d.txt" % (Tf[i], H[i], fr)
+                        np.savetxt(os.path.join(workdir, name), np.column_stack([xyz, frames[k, fr]]), fmt="%.6f %.6f %.6f %.3f",
+                                   header="x       #y       #z       #spin", comments="#")
+                    else:                        # mcMain.py:317-323
+                        name = "OnSpinDistribution.T%.3f.H%.3f.%d.txt" % (Tf[i], H[i], fr)
+                        np.savetxt(os.path.join(workdir, name), np.column_stack([xyz, frames[k, fr]]), fmt="%.6f",
+                                   header="x       #y       #z       #spinx  #spiny  #spinz", comments="#")
+    if not quiet and rank == 0:
+        print("time elapsed %.3f s" % (time.time() - t0))
+    out = dict(T=Tf[idx], H=H[idx], **obs)
+    out["rows"] = rows
+    return out

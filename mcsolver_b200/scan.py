@@ -22,7 +22,7 @@ def shard(n_points, rank, world):
 
 
 def run_points(spec, model, T, H, nthermal, nsweep, ninterval=0, algorithm=engine.METROPOLIS, precision=32, seed=1,
-               rank=0, world=1, device=-1, flunc=0.0, spin_frames=0, tables=False):
+               rank=0, world=1, device=-1, flunc=0.0, spin_frames=0, tables=False, want_groups=False):
     """Run the points (T[i], H[i]) owned by `rank` and return (indices, results[n,27|10], frames).
 
     spec: LatticeSpec (bond templates + supercell).  ninterval<=0 means N (mcMain.py:145).
@@ -36,7 +36,8 @@ def run_points(spec, model, T, H, nthermal, nsweep, ninterval=0, algorithm=engin
     lo, hi = shard(T.size, rank, world)
     idx = np.arange(lo, hi)
     if idx.size == 0:
-        return idx, np.zeros((0, 10 if model == engine.ISING else 27)), None
+        empty = np.zeros((0, 10 if model == engine.ISING else 27))
+        return idx, ((empty, None) if want_groups else empty), None
     Tl = np.maximum(T[lo:hi], 0.1)
     beta, field = 1.0 / Tl, H[lo:hi]
     N = spec.nsite
@@ -52,8 +53,10 @@ def run_points(spec, model, T, H, nthermal, nsweep, ninterval=0, algorithm=engin
     with sysm as s:
         s.init_spins(flunc)
         frames = s.run(algorithm, nthermal, nsweep, nint, spinFrame=spin_frames)
-        out = np.stack([s.results(r)[0] for r in range(idx.size)])
-    return idx, out, frames
+        res = [s.results(r) for r in range(idx.size)]
+        out = np.stack([r[0] for r in res])
+        groups = np.stack([r[1] for r in res]) if (model != engine.ISING and res[0][1] is not None and res[0][1].size) else None
+    return idx, ((out, groups) if want_groups else out), frames
 
 
 def observables(rows, T, N, model):

@@ -1,0 +1,40 @@
+"""GPU tests of the headless entry: mcsolver_b200.loadMC(parameterfile) writes the reference's files."""
+import numpy as np
+import pytest
+
+from tests import paramfiles, util
+
+pytestmark = pytest.mark.gpu
+
+
+def test_loadmc_xy_wolff_sample_layout_and_values(tmp_path):
+    import mcsolver_b200
+    f = tmp_path / "Square_XY"
+    f.write_text(paramfiles.XY_SQUARE.format(L=16, T0=0.9, T1=0.9, nT=1, nthermal=4000, nsweep=16000, tau=1, model="XY", algo="Wolff"))
+    res = mcsolver_b200.loadMC(str(f), workdir=str(tmp_path), precision=64, seed=3, quiet=True)
+    lines = (tmp_path / "result.txt").read_text().splitlines()
+    assert lines[0].startswith("#Temp          #Field         #<Si>") and len(lines) == 2 and len(lines[1]) == 150
+    row = np.array([float(lines[1][15 * i:15 * (i + 1)]) for i in range(10)])
+    assert row[0] == 0.9 and row[1] == 0.0
+    out = (tmp_path / "out").read_text().splitlines()
+    assert out[0] == "#T #H" and out[1].startswith("T= 9.000000E-01 h= 0.000000E+00 <Siz>=") and "<Q>=" in out[1]
+    assert len((tmp_path / "spinDotSpin.txt").read_text().splitlines()) == 2
+    # same physics as the reference's seeded runs of this point (stats fixture C1_xy_wolff, T=0.9)
+    ref = [p for p in util.load_json("stats.json") if p["tag"] == "C1_xy_wolff"][0]
+    rr = np.array(ref["rows"])
+    e_ref, e_sd = (rr[:, 8] * 0.9).mean(), (rr[:, 8] * 0.9).std(ddof=1)
+    assert abs(res["Energy"][0] - e_ref) < 5 * e_sd + 1e-3
+    assert abs(res["U4"][0] - rr[:, 10].mean()) < 5 * rr[:, 10].std(ddof=1) + 1e-3
+
+
+def test_loadmc_skyrmion_field_scan_with_frames(tmp_path):
+    import mcsolver_b200
+    f = tmp_path / "Skyrmion"
+    f.write_text(paramfiles.SKYRMION_HEX.format(L=12, H0=0.0, H1=0.6, nH=3, frames=1, nthermal=500, nsweep=1000))
+    res = mcsolver_b200.loadMC(str(f), workdir=str(tmp_path), precision=32, seed=1, quiet=True)
+    assert np.allclose(res["H"], [0.0, 0.3, 0.6]) and np.all(res["T"] == 0.3)
+    assert np.all(np.isfinite(res["TopoQ"])) and res["Energy"][2] < res["Energy"][0]      # field lowers the energy
+    frames = sorted(p.name for p in tmp_path.glob("OnSpinDistribution.*"))
+    assert frames == ["OnSpinDistribution.T0.300.H0.000.0.txt", "OnSpinDistribution.T0.300.H0.300.0.txt", "OnSpinDistribution.T0.300.H0.600.0.txt"]
+    fr = np.loadtxt(tmp_path / frames[0])
+    assert fr.shape == (288, 6) and np.allclose(np.linalg.norm(fr[:, 3:], axis=1), 1.0, atol=1e-5)
