@@ -431,26 +431,25 @@ static void metropolis_sweeps(mcg_system *s, int64_t n, double pAtt) {
 
 static void wolff_steps(mcg_system *s, int64_t n) {
     MCG_REQUIRE(n >= 0, "negative step count");
-    MCG_REQUIRE(!s->structured, "Wolff updates need a table-built system in this version");
     if (!s->d_parent) {
         s->d_parent = dalloc<int32_t>((size_t)s->R * s->N);
         MCG_CUDA(cudaMalloc(&s->d_proj, (size_t)s->R * s->N * s->real_size()));
         s->d_wres = dalloc<double>(2 * (size_t)s->R);
     }
-    GenArgs a = gen_args(s);
     WolffArgs w;
-    w.parent = s->d_parent; w.proj = s->d_proj; w.wres = s->d_wres; w.pos_of = s->d_pos_of;
-    dim3 g = grid_for(s->N, s->R);
+    w.parent = s->d_parent; w.proj = s->d_proj; w.wres = s->d_wres; w.N = s->N; w.R = s->R; w.spin = s->d_spin;
+    w.beta = s->d_beta; w.field = s->d_field; w.cnt = s->d_cnt; w.key = make_rng_key(s->seed); w.replica0 = s->replica0;
     for (int64_t it = 0; it < n; it++) {
         w.step = s->wolffCtr++;
         s->launches += 5;
-        dispatch(s, [&]<int NC, typename real, bool FJ>() {
-            k_wolff_init<NC, real><<<g, 256, 0, s->stream>>>(a, w);
-            k_wolff_bonds<NC, real, FJ><<<g, 256, 0, s->stream>>>(a, w);
-            k_wolff_flatten<<<g, 256, 0, s->stream>>>(s->N, s->d_parent);
-            k_wolff_residual<NC, real, FJ><<<g, 256, 0, s->stream>>>(a, w);
-            k_wolff_flip<NC, real><<<g, 256, 0, s->stream>>>(a, w);
-        });
+        if (s->structured) structured_wolff_step(s, w);
+        else {
+            GenArgs a = gen_args(s);
+            dispatch(s, [&]<int NC, typename real, bool FJ>() {
+                TableTopo<NC, real> topo{a, s->d_pos_of};
+                wolff_launch_step<NC, real, FJ>(topo, w, s->stream);
+            });
+        }
     }
     MCG_CUDA(cudaGetLastError());
 }

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(256) k_group_sums(GenArgs a, int nG, int maxG,
 }
 
 // fold block-spin and group sums into their accumulators (before k_finalize_sweep clears the raw sums)
-__global__ void k_extra_finalize(int model, int R, int nLat, int nR, double ci, double cj, double cij, int nG, const double *sums,
+static __global__ void k_extra_finalize(int model, int R, int nLat, int nR, double ci, double cj, double cij, int nG, const double *sums,
                                  double *rsums, double *gsum, double *acc, double *gacc, const int32_t *slot) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;

@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(256) k_topo_generic(GenArgs a, int nTri, const
 //   O(n):  heisenbergLib.c:677-744 / xyLib.c:605-673      Ising: isingLib.c:395-431
 // All projections are linear in the sums:  sum_j n.s_j = n.(sum_j s_j).
 // ---------------------------------------------------------------------------------------------
-__global__ void k_finalize_sweep(int model, int R, int N, int nLat, double *sums, double *acc, const int32_t *slot, double *last) {
+static __global__ void k_finalize_sweep(int model, int R, int N, int nLat, double *sums, double *acc, const int32_t *slot, double *last) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
     double *s = sums + (size_t)r * NSUM, *A = acc + (size_t)slot[r] * NACC;

@@ -3,14 +3,20 @@
 // Reference: blockUpdate/expandBlock - heisenbergLib.c:310-439, xyLib.c:256-380, isingLib.c:165-236.
 // The reference grows ONE cluster from a random seed by a sequential FIFO and pays O(N) per step
 // anyway (flag reset, two N-pointer mallocs, full energy recompute).  Here every bond of the lattice
-// is activated independently with the reference's probability 1-exp(min(0,corr)) (each bond owns one
-// Philox word keyed by its lower-id endpoint and that endpoint's link slot), active bonds are merged
-// with an atomicCAS union-find, and only the cluster containing the seed is reflected: the seed's
-// cluster of the bond-percolation configuration has exactly the distribution of the FIFO-grown one
-// (a bond is tested at most once in either formulation).  The cluster-wide residual energy (the parts
-// of J not proportional to n n^T, single-ion anisotropy, field) is reduced over the selected cluster
-// and the reflection accepted with min(1,exp(-res)) as in heisenbergLib.c:403-423 - evaluated with the
-// FULL move (the reference reads the half move; oracle flag wolffHalfMove=0).
+// is activated independently with the reference's probability 1-exp(min(0,corr)), active bonds are
+// merged with an atomicCAS union-find, and only the cluster containing the seed is reflected: the
+// seed's cluster of the bond-percolation configuration has exactly the distribution of the FIFO-grown
+// one (a bond is tested at most once in either formulation).  The cluster-wide residual energy (the
+// parts of J not proportional to n n^T, single-ion anisotropy, field) is reduced over the selected
+// cluster and the reflection accepted with min(1,exp(-res)) as in heisenbergLib.c:403-423 - evaluated
+// with the FULL move (the reference reads the half move; oracle flag wolffHalfMove=0).
+//
+// The uniform of a bond is one Philox word keyed by (lower reference site id, higher reference site
+// id, step, replica): independent of the link-slot order, the storage layout and the path, so the
+// table path, the structured path and the oracle's FIFO restatement select the same clusters.
+//
+// The kernels are written over a topology policy: TableTopo (neighbour tables of the legacy payload)
+// or StructTopo (structured.cu: neighbours computed from the class decomposition).
 #pragma once
 #include "kernels_generic.cuh"
 
@@ -20,18 +26,29 @@ struct WolffArgs {
     int32_t *parent;      // [R][N]
     void *proj;           // [R][N] real: a_p = -(s_p . n)
     double *wres;         // [R][2]: residual energy, cluster size
-    const int32_t *pos_of;
     uint64_t step;
+    int N, R;
+    void *spin;           // [R][NC][N] real
+    const double *beta, *field;
+    unsigned long long *cnt;
+    RngKey key;
+    uint32_t replica0;
 };
 
+__host__ __device__ __forceinline__ void rng_bond(const RngKey &key, uint32_t replica, uint64_t step, uint32_t lo, uint32_t hi,
+                                                  uint32_t (&out)[4]) {
+    philox4x32_10(lo, hi, (STREAM_WBOND << 24) | (uint32_t)((step >> 16) & 0xFFFFFFu), (replica & 0xFFFFu) | ((uint32_t)(step & 0xFFFFu) << 16),
+                  key, out);
+}
+
 template <int NC, typename real>
-__device__ __forceinline__ void wolff_seed(const GenArgs &a, int r, uint64_t step, real (&n)[3], int &seedSite, real &uAcc) {
-    uint32_t w[4];
-    rng4(a.key, a.replica0 + r, STREAM_WSEED, 0, step, 0u, w);
-    seedSite = (int)(((uint64_t)w[3] * (uint64_t)a.N) >> 32);
-    uAcc = u01<real>(w[2]);
+__device__ __forceinline__ void wolff_seed(const WolffArgs &w, int r, real (&n)[3], int &seedSite, real &uAcc) {
+    uint32_t ww[4];
+    rng4(w.key, w.replica0 + r, STREAM_WSEED, 0, w.step, 0u, ww);
+    seedSite = (int)(((uint64_t)ww[3] * (uint64_t)w.N) >> 32);
+    uAcc = u01<real>(ww[2]);
     if (NC == 1) { n[0] = 1; n[1] = n[2] = 0; }
-    else random_dir<NC, real>(w[0], w[1], n);
+    else random_dir<NC, real>(ww[0], ww[1], n);
 }
 
 __device__ __forceinline__ int uf_find(int32_t *parent, int x) {
@@ -53,57 +70,79 @@ __device__ __forceinline__ void uf_unite(int32_t *parent, int a, int b) {
     }
 }
 
-template <int NC, typename real>
-__global__ void __launch_bounds__(256) k_wolff_init(GenArgs a, WolffArgs w) {
+// ---- topology of the table path ----
+template <int NC, typename real> struct TableTopo {
+    GenArgs a;
+    const int32_t *pos_of;
+    struct Ctx { int p; };
+    __device__ __forceinline__ Ctx begin(int p) const { return Ctx{p}; }
+    __device__ __forceinline__ int site_id(const Ctx &c) const { return a.site_of[c.p]; }
+    __device__ __forceinline__ int site_id_of(int q) const { return a.site_of[q]; }
+    __device__ __forceinline__ int pos_of_site(int id) const { return pos_of[id]; }
+    __device__ __forceinline__ int nlinks(const Ctx &) const { return a.maxL; }
+    // k-th link: neighbour storage position and exchange tensor; false for padding / self image
+    __device__ __forceinline__ bool link(const Ctx &c, int k, int &q, const real *&J) const {
+        q = a.nbrp[(size_t)k * a.N + c.p];
+        if (q == c.p) return false;
+        J = (const real *)a.Jtab + (size_t)a.jtype[(size_t)k * a.N + c.p] * (NC == 1 ? 1 : 9);
+        return true;
+    }
+    __device__ __forceinline__ real S(const Ctx &c) const { return ((const real *)a.clsS)[a.cls[c.p]]; }
+    __device__ __forceinline__ void D(const Ctx &c, real (&d)[3]) const {
+        const real *D = (const real *)a.clsD + 3 * a.cls[c.p];
+        d[0] = D[0]; d[1] = D[1]; d[2] = D[2];
+    }
+};
+
+template <int NC, typename real, typename TOPO>
+__global__ void __launch_bounds__(256) k_wolff_init(TOPO topo, WolffArgs w) {
     int r = blockIdx.y;
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p == 0) { w.wres[2 * r] = 0.0; w.wres[2 * r + 1] = 0.0; }
-    if (p >= a.N) return;
-    w.parent[(size_t)r * a.N + p] = p;
+    if (p >= w.N) return;
+    w.parent[(size_t)r * w.N + p] = p;
     if (NC > 1) {
         real n[3], u; int seed;
-        wolff_seed<NC, real>(a, r, w.step, n, seed, u);
-        const real *sp = (const real *)a.spin + (size_t)r * NC * a.N;
+        wolff_seed<NC, real>(w, r, n, seed, u);
+        const real *sp = (const real *)w.spin + (size_t)r * NC * w.N;
         real s[3];
-        load_spin<NC, real>(sp, a.N, p, s);
-        ((real *)w.proj)[(size_t)r * a.N + p] = -(s[0] * n[0] + s[1] * n[1] + s[2] * n[2]);   // sDotN, heisenbergLib.c:324
+        load_spin<NC, real>(sp, w.N, p, s);
+        ((real *)w.proj)[(size_t)r * w.N + p] = -(s[0] * n[0] + s[1] * n[1] + s[2] * n[2]);   // sDotN, heisenbergLib.c:324
     }
 }
 
-template <int NC, typename real, bool FULLJ>
-__global__ void __launch_bounds__(256) k_wolff_bonds(GenArgs a, WolffArgs w) {
-    constexpr int JW = NC == 1 ? 1 : 9;
+template <int NC, typename real, bool FULLJ, typename TOPO>
+__global__ void __launch_bounds__(256) k_wolff_bonds(TOPO topo, WolffArgs w) {
     int r = blockIdx.y;
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= a.N) return;
-    const real *Jtab = (const real *)a.Jtab;
-    const real *sp = (const real *)a.spin + (size_t)r * NC * a.N;
-    const real *proj = (const real *)w.proj + (size_t)r * a.N;
-    int32_t *parent = w.parent + (size_t)r * a.N;
-    real beta = (real)a.beta[r];
+    if (p >= w.N) return;
+    const real *sp = (const real *)w.spin + (size_t)r * NC * w.N;
+    const real *proj = (const real *)w.proj + (size_t)r * w.N;
+    int32_t *parent = w.parent + (size_t)r * w.N;
+    real beta = (real)w.beta[r];
     real n[3], uAcc; int seed;
-    wolff_seed<NC, real>(a, r, w.step, n, seed, uAcc);
-    int ip = a.site_of[p];
+    wolff_seed<NC, real>(w, r, n, seed, uAcc);
+    auto c = topo.begin(p);
+    const int ip = topo.site_id(c);
     real ap = NC == 1 ? sp[p] : proj[p];
-    uint32_t wd[4];
-    int have = -1;
-    for (int k = 0; k < a.maxL; k++) {
-        int q = a.nbrp[(size_t)k * a.N + p];
-        if (q == p) continue;                         // padding / self image
-        if (a.site_of[q] < ip) continue;              // bond owned by the lower reference id
-        int jt = a.jtype[(size_t)k * a.N + p];
-        const real *J = Jtab + (size_t)jt * JW;
+    const int nl = topo.nlinks(c);
+    for (int k = 0; k < nl; k++) {
+        int q; const real *J;
+        if (!topo.link(c, k, q, J)) continue;
+        const int iq = topo.site_id_of(q);
+        if (iq < ip) continue;                        // bond owned by the lower reference id
         real corr;
         if (NC == 1) corr = real(2) * beta * J[0] * ap * sp[q];                       // isingLib.c:183-185
         else corr = real(2) * ap * proj[q] * beta * quad_form<NC, real, FULLJ>(J, n, n);   // heisenbergLib.c:355
         if (corr < real(0)) {
-            if (have != (k >> 2)) { rng4(a.key, a.replica0 + r, STREAM_WBOND, (uint32_t)(k >> 2), w.step, (uint32_t)ip, wd); have = k >> 2; }
-            if ((real(1) - r_exp<real>(corr)) > u01<real>(wd[k & 3])) uf_unite(parent, p, q);
+            uint32_t wd[4];
+            rng_bond(w.key, w.replica0 + r, w.step, (uint32_t)ip, (uint32_t)iq, wd);
+            if ((real(1) - r_exp<real>(corr)) > u01<real>(wd[0])) uf_unite(parent, p, q);
         }
     }
 }
 
-__global__ void __launch_bounds__(256) k_wolff_flatten(int N, int32_t *parentAll) {
+static __global__ void __launch_bounds__(256) k_wolff_flatten(int N, int32_t *parentAll) {
     int r = blockIdx.y;
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= N) return;
@@ -114,38 +153,37 @@ __global__ void __launch_bounds__(256) k_wolff_flatten(int N, int32_t *parentAll
 }
 
 // residual energy of reflecting the seed's cluster, and its size
-template <int NC, typename real, bool FULLJ>
-__global__ void __launch_bounds__(256) k_wolff_residual(GenArgs a, WolffArgs w) {
-    constexpr int JW = NC == 1 ? 1 : 9;
+template <int NC, typename real, bool FULLJ, typename TOPO>
+__global__ void __launch_bounds__(256) k_wolff_residual(TOPO topo, WolffArgs w) {
     __shared__ double smem[2 * 32];
     int r = blockIdx.y;
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     double v[2] = {0.0, 0.0};
     real n[3], uAcc; int seed;
-    wolff_seed<NC, real>(a, r, w.step, n, seed, uAcc);
-    const int32_t *parent = w.parent + (size_t)r * a.N;
-    if (p < a.N) {
-        int root = parent[w.pos_of[seed]];
+    wolff_seed<NC, real>(w, r, n, seed, uAcc);
+    const int32_t *parent = w.parent + (size_t)r * w.N;
+    if (p < w.N) {
+        int root = parent[topo.pos_of_site(seed)];
         if (parent[p] == root) {
-            const real *sp = (const real *)a.spin + (size_t)r * NC * a.N;
-            real beta = (real)a.beta[r], hf = (real)(a.beta[r] * a.field[r]);
+            const real *sp = (const real *)w.spin + (size_t)r * NC * w.N;
+            real beta = (real)w.beta[r], hf = (real)(w.beta[r] * w.field[r]);
             v[1] = 1.0;
             if (NC == 1) {
                 v[0] = 2.0 * (double)hf * (double)sp[p];                         // getDeltaOnsiteEnergy isingLib.c:129-131
             } else {
-                const real *Jtab = (const real *)a.Jtab;
-                const real *proj = (const real *)w.proj + (size_t)r * a.N;
+                const real *proj = (const real *)w.proj + (size_t)r * w.N;
+                auto c = topo.begin(p);
                 real s[3];
-                load_spin<NC, real>(sp, a.N, p, s);
+                load_spin<NC, real>(sp, w.N, p, s);
                 real ap = proj[p];
                 real perp_p[3] = {s[0] + ap * n[0], s[1] + ap * n[1], s[2] + ap * n[2]};
                 double res = 0.0;
-                for (int k = 0; k < a.maxL; k++) {
-                    int q = a.nbrp[(size_t)k * a.N + p];
-                    if (q == p) continue;
-                    const real *J = Jtab + (size_t)a.jtype[(size_t)k * a.N + p] * JW;
+                const int nl = topo.nlinks(c);
+                for (int k = 0; k < nl; k++) {
+                    int q; const real *J;
+                    if (!topo.link(c, k, q, J)) continue;
                     real t[3];
-                    load_spin<NC, real>(sp, a.N, q, t);
+                    load_spin<NC, real>(sp, w.N, q, t);
                     real aq = proj[q];
                     real perp_q[3] = {t[0] + aq * n[0], t[1] + aq * n[1], t[2] + aq * n[2]};
                     real src = ap * beta * quad_form<NC, real, FULLJ>(J, n, perp_q);          // heisenbergLib.c:407
@@ -153,7 +191,8 @@ __global__ void __launch_bounds__(256) k_wolff_residual(GenArgs a, WolffArgs w) 
                     if (parent[q] == root) res += (double)(aq * beta * quad_form<NC, real, FULLJ>(J, perp_p, n));   // :411
                     else res += (double)src;                                                   // :413
                 }
-                const real *D = (const real *)a.clsD + 3 * a.cls[p];
+                real D[3];
+                topo.D(c, D);
                 real tr[3] = {real(2) * ap * n[0], real(2) * ap * n[1], real(2) * ap * n[2]};
                 real t1[3] = {s[0] + tr[0], s[1] + tr[1], s[2] + tr[2]};
                 real dOn = D[0] * (t1[0] * t1[0] - s[0] * s[0]) + D[1] * (t1[1] * t1[1] - s[1] * s[1]);
@@ -166,39 +205,50 @@ __global__ void __launch_bounds__(256) k_wolff_residual(GenArgs a, WolffArgs w) 
     block_accumulate<2>(v, w.wres + 2 * r, smem);
 }
 
-template <int NC, typename real>
-__global__ void __launch_bounds__(256) k_wolff_flip(GenArgs a, WolffArgs w) {
+template <int NC, typename real, typename TOPO>
+__global__ void __launch_bounds__(256) k_wolff_flip(TOPO topo, WolffArgs w) {
     int r = blockIdx.y;
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= a.N) return;
+    if (p >= w.N) return;
     real n[3], uAcc; int seed;
-    wolff_seed<NC, real>(a, r, w.step, n, seed, uAcc);
-    const int32_t *parent = w.parent + (size_t)r * a.N;
-    int seedPos = w.pos_of[seed];
+    wolff_seed<NC, real>(w, r, n, seed, uAcc);
+    const int32_t *parent = w.parent + (size_t)r * w.N;
+    int seedPos = topo.pos_of_site(seed);
     int root = parent[seedPos];
     double res = w.wres[2 * r];
     bool accept = res <= 0.0 || r_exp<real>((real)-res) > uAcc;     // heisenbergLib.c:423 / isingLib.c:225
     if (p == seedPos) {
-        atomicAdd(a.cnt + (size_t)r * NCNT + CNT_WSTEPS, 1ull);
+        atomicAdd(w.cnt + (size_t)r * NCNT + CNT_WSTEPS, 1ull);
         if (accept) {
-            atomicAdd(a.cnt + (size_t)r * NCNT + CNT_ACCEPT, 1ull);
-            atomicAdd(a.cnt + (size_t)r * NCNT + CNT_CLUSTER, (unsigned long long)(w.wres[2 * r + 1] + 0.5));
+            atomicAdd(w.cnt + (size_t)r * NCNT + CNT_ACCEPT, 1ull);
+            atomicAdd(w.cnt + (size_t)r * NCNT + CNT_CLUSTER, (unsigned long long)(w.wres[2 * r + 1] + 0.5));
         }
-        atomicAdd(a.cnt + (size_t)r * NCNT + CNT_ATTEMPT, 1ull);
+        atomicAdd(w.cnt + (size_t)r * NCNT + CNT_ATTEMPT, 1ull);
     }
     if (!accept || parent[p] != root) return;
-    real *sp = (real *)a.spin + (size_t)r * NC * a.N;
+    real *sp = (real *)w.spin + (size_t)r * NC * w.N;
     if (NC == 1) { sp[p] = -sp[p]; return; }
-    real ap = ((const real *)w.proj)[(size_t)r * a.N + p];
+    real ap = ((const real *)w.proj)[(size_t)r * w.N + p];
     real s[3];
-    load_spin<NC, real>(sp, a.N, p, s);
+    load_spin<NC, real>(sp, w.N, p, s);
     s[0] += real(2) * ap * n[0]; s[1] += real(2) * ap * n[1]; s[2] += real(2) * ap * n[2];   // heisenbergLib.c:425-426
     if (sizeof(real) == 4) {
-        real S = ((const real *)a.clsS)[a.cls[p]];
+        real S = topo.S(topo.begin(p));
         real f = S * r_rsqrt<real>(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]);
         s[0] *= f; s[1] *= f; s[2] *= f;
     }
-    store_spin<NC, real>(sp, a.N, p, s);
+    store_spin<NC, real>(sp, w.N, p, s);
+}
+
+// launch sequence of one cluster update, shared by both paths
+template <int NC, typename real, bool FJ, typename TOPO>
+static void wolff_launch_step(const TOPO &topo, const WolffArgs &w, cudaStream_t stream) {
+    dim3 g((unsigned)((w.N + 255) / 256), (unsigned)w.R);
+    k_wolff_init<NC, real, TOPO><<<g, 256, 0, stream>>>(topo, w);
+    k_wolff_bonds<NC, real, FJ, TOPO><<<g, 256, 0, stream>>>(topo, w);
+    k_wolff_flatten<<<g, 256, 0, stream>>>(w.N, w.parent);
+    k_wolff_residual<NC, real, FJ, TOPO><<<g, 256, 0, stream>>>(topo, w);
+    k_wolff_flip<NC, real, TOPO><<<g, 256, 0, stream>>>(topo, w);
 }
 
 }  // namespace mcg

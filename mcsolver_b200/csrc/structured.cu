@@ -24,6 +24,7 @@
 #include "structured.hpp"
 #include "struct_pass.cuh"
 #include "jit.hpp"
+#include "kernels_wolff.cuh"
 
 namespace mcg {
 
@@ -62,6 +63,46 @@ __device__ __forceinline__ int struct_site_id(const StructArgs &a, int p) {
     int x = X * a.px + c.a, y = Y * a.py + c.b, z = Z * a.pz + c.c;
     return ((x * a.Ly + y) * a.Lz + z) * a.norb + c.o;
 }
+
+
+// ---- topology of the structured path for the Wolff kernels (kernels_wolff.cuh) ----
+template <int NC, typename real> struct StructTopo {
+    StructArgs a;
+    struct Ctx { int p, q, X, Y, Z; };
+    __device__ __forceinline__ Ctx begin(int p) const {
+        Ctx c;
+        c.p = p; c.q = p / a.ncellc;
+        int cell = p - c.q * a.ncellc;
+        c.Z = cell % a.Zd; c.Y = (cell / a.Zd) % a.Yd; c.X = cell / (a.Zd * a.Yd);
+        return c;
+    }
+    __device__ __forceinline__ int site_id(const Ctx &c) const {
+        const SClassD &cl = a.classes[c.q];
+        return (((c.X * a.px + cl.a) * a.Ly + (c.Y * a.py + cl.b)) * a.Lz + (c.Z * a.pz + cl.c)) * a.norb + cl.o;
+    }
+    __device__ __forceinline__ int site_id_of(int q) const { return struct_site_id(a, q); }
+    __device__ __forceinline__ int pos_of_site(int id) const {
+        int o = id % a.norb, cell = id / a.norb;
+        int z = cell % a.Lz, y = (cell / a.Lz) % a.Ly, x = cell / (a.Lz * a.Ly);
+        return struct_pos(a, x, y, z, o);
+    }
+    __device__ __forceinline__ int nlinks(const Ctx &c) const { return a.classes[c.q].nlink; }
+    __device__ __forceinline__ bool link(const Ctx &c, int k, int &q, const real *&J) const {
+        const SLinkD L = a.links[c.q * MAXLINK + k];
+        if (L.self) return false;
+        int Xn = c.X + L.cX; if (Xn >= a.Xd) Xn -= a.Xd;
+        int Yn = c.Y + L.cY; if (Yn >= a.Yd) Yn -= a.Yd;
+        int Zn = c.Z + L.cZ; if (Zn < 0) Zn += a.Zd; if (Zn >= a.Zd) Zn -= a.Zd;
+        q = ((L.qn * a.Xd + Xn) * a.Yd + Yn) * a.Zd + Zn;
+        J = (const real *)a.J + (size_t)(c.q * MAXLINK + k) * (NC == 1 ? 1 : 9);
+        return true;
+    }
+    __device__ __forceinline__ real S(const Ctx &c) const { return (real)fabs(a.classes[c.q].S); }
+    __device__ __forceinline__ void D(const Ctx &c, real (&d)[3]) const {
+        const SClassD &cl = a.classes[c.q];
+        d[0] = (real)cl.D[0]; d[1] = (real)cl.D[1]; d[2] = (real)cl.D[2];
+    }
+};
 
 // MODE 0: update only   1: update + fused measurement   2: measurement only (no update)
 template <int NC, typename real, bool FULLJ, int MODE, int V>
@@ -925,6 +966,14 @@ static void fold_and_extras(mcg_system *s) {
         else k_struct_topo<float><<<g, 256, 0, s->stream>>>(a, st->ncircuit, st->d_circuits, s->d_sums);
     }
     MCG_CUDA(cudaGetLastError());
+}
+
+void structured_wolff_step(mcg_system *s, const WolffArgs &w) {
+    StructArgs a = struct_args(s);
+    sdispatch(s, [&]<int NC, typename real, bool FJ>() {
+        StructTopo<NC, real> topo{a};
+        wolff_launch_step<NC, real, FJ>(topo, w, s->stream);
+    });
 }
 
 void structured_measure_sums(mcg_system *s) {

@@ -45,7 +45,7 @@ def loadMC(rpath, precision=None, seed=None, rank=0, world=1, device=-1, workdir
     algo = engine.WOLFF if p.algorithm == "Wolff" else engine.METROPOLIS
     prec = engine.default_precision() if precision is None else precision
     sd = engine.default_seed() if seed is None else seed
-    use_tables = algo == engine.WOLFF or spec.nsite <= table_limit     # full tuples (block-spin, groups) when affordable
+    use_tables = spec.nsite <= table_limit     # full tuples (block-spin, groups) when affordable
     ninterval = spec.nsite if p.ninterval <= 0 else p.ninterval
     idx, rows, frames = scan.run_points(spec, model, T, H, p.nthermal, p.nsweep, ninterval=ninterval, algorithm=algo, precision=prec,
                                         seed=sd, rank=rank, world=world, device=device, spin_frames=p.spinFrame, tables=use_tables,

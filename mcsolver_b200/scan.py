@@ -26,7 +26,7 @@ def run_points(spec, model, T, H, nthermal, nsweep, ninterval=0, algorithm=engin
     """Run the points (T[i], H[i]) owned by `rank` and return (indices, results[n,27|10], frames).
 
     spec: LatticeSpec (bond templates + supercell).  ninterval<=0 means N (mcMain.py:145).
-    tables=True forces the table-driven engine (needed for Wolff); default is the structured path.
+    tables=True forces the table-driven engine (full tuples incl. block-spin/group slots); default is the structured path.
     Result rows have the reference's tuple layout with E, E2 still in beta units (caller rescales
     exactly as mcMain.py:251 does)."""
     T = np.atleast_1d(np.asarray(T, dtype=float))
@@ -42,7 +42,7 @@ def run_points(spec, model, T, H, nthermal, nsweep, ninterval=0, algorithm=engin
     beta, field = 1.0 / Tl, H[lo:hi]
     N = spec.nsite
     nint = N if ninterval <= 0 else int(ninterval)
-    if tables or algorithm == engine.WOLFF:
+    if tables:
         from .lattice import build_tables
         t = build_tables(spec, 1.0, model)     # unscaled tables, beta per replica
         sysm = engine.System.from_tables(t, precision=precision, nReplica=idx.size, beta=beta, field=field, seed=seed,

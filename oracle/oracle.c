@@ -309,20 +309,14 @@ static void on_attempt_philox(const orc_sys *s, double *sp, int i, const uint32_
  * uniform of a bond is keyed by its lower-id endpoint and that endpoint's link slot, seed site
  * and plane normal come from stream WSEED; halfMove=0 evaluates the residual with the full move. */
 static uint32_t bond_uniform_word(const orc_sys *s, uint64_t seed, uint32_t replica, uint64_t step, int a, int k) {
-    /* bond seen from a through slot k; owner = lower id; owner's matching slot = m-th link to a */
+    /* one Philox word per bond, keyed by (lower site id, higher site id, step, replica): engine convention rng_bond() */
     int b = s->nbr[(size_t)a * s->maxL + k];
-    int owner = a, slot = k;
-    if (b < a) {
-        int m = 0;
-        for (int q = 0; q < k; q++) if (s->nbr[(size_t)a * s->maxL + q] == b) m++;
-        owner = b; slot = -1;
-        for (int q = 0; q < s->nlink[b]; q++)
-            if (s->nbr[(size_t)b * s->maxL + q] == a) { if (m == 0) { slot = q; break; } m--; }
-        if (slot < 0) { owner = a; slot = k; } /* asymmetric table: fall back to own slot */
-    }
-    uint32_t r[4];
-    rng4(seed, replica, STREAM_WBOND, (uint32_t)(slot >> 2), step, (uint32_t)owner, r);
-    return r[slot & 3];
+    uint32_t lo = (uint32_t)(a < b ? a : b), hi = (uint32_t)(a < b ? b : a);
+    uint32_t ctr[4] = {lo, hi, ((uint32_t)STREAM_WBOND << 24) | (uint32_t)((step >> 16) & 0xFFFFFFu),
+                       (replica & 0xFFFFu) | ((uint32_t)(step & 0xFFFFu) << 16)};
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, out[4];
+    orc_philox4x32(ctr, key, out);
+    return out[0];
 }
 
 static void on_block_update(const orc_sys *s, double *sp, orc_state *st, int mode, uint64_t seed, uint32_t replica,

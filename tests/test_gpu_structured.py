@@ -122,3 +122,26 @@ def test_structured_fp32_vector_path_statistics():
     # <e> at T=1.2 on 8x8x16: statistical agreement (two different chains, ~1% tolerance)
     assert abs(res[32][8] - res[64][8]) < 0.02 * abs(res[64][8])
     assert abs(res[32][10] - res[64][10]) < 0.05
+
+
+WOLFF_S = [("square", (8, 8, 1), 0.9, 2, 0.0), ("cubic", (6, 6, 8), 1.4, 3, 0.0), ("aniso", (6, 6, 1), 0.7, 3, 0.3),
+           ("square", (8, 16, 1), 2.3, 1, 0.05), ("cubic", (6, 6, 6), 4.4, 1, 0.0), ("skyrmion", (6, 6, 1), 0.3, 3, 0.2)]
+
+
+@pytest.mark.parametrize("case", WOLFF_S, ids=lambda c: "%s-%s-m%d" % (c[0], "x".join(map(str, c[1])), c[3]))
+def test_structured_wolff_trajectory_matches_oracle_fp64(case):
+    """Wolff on the structured path (neighbours computed, not stored) selects the same clusters as the
+    oracle's FIFO growth: the bond uniforms are keyed by site-id pairs, not by layout."""
+    eng = _eng()
+    name, L, T, model, h = case
+    spec = spec_of(name, L)
+    t = util.tables_for(dict(spec=name, L=L, T=T, model=model))
+    o = util.oracle_system(t, h / T)
+    with eng.System.from_spec(spec, model, precision=64, beta=[1.0 / T], field=[h], seed=77) as s:
+        start = _start(o, t, model, 77)
+        s.set_spins(start)
+        r = o.run(3, 30, 1, 1, seed=77, spins=start)
+        s.wolff_steps(31)
+        got = s.get_spins()
+        assert np.max(np.abs(got - r["spins"].reshape(got.shape))) < 1e-9
+        assert s.counters() == tuple(int(v) for v in r["counters"])
