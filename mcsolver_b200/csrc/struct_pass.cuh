@@ -97,7 +97,7 @@ __device__ __forceinline__ void load_shifted(const real *__restrict__ row, int Z
 }
 
 // ---- link / class tables of one colour pass ----
-constexpr int PT_MAXC = 8, PT_MAXL = 16;
+constexpr int PT_MAXC = 8, PT_MAXL = 32;
 template <typename real> struct PLink {
     int delta;                  // (qn-q)*ncellc + (cX*Yd + cY)*Zd with signed cX,cY in {-1,0,1}
     int mxp, mxm, myp, mym;     // 0/1: which per-row wrap correction applies

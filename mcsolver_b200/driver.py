@@ -28,18 +28,21 @@ def _write_out_line(f, model, T, h, r, extra=None):
                 r[17], np.dot(sir, sjr), Er, E2r, r[26]))
 
 
-def loadMC(rpath, precision=None, seed=None, rank=0, world=1, device=-1, workdir=".", table_limit=200000, quiet=False):
+def loadMC(rpath, precision=None, seed=None, rank=0, world=1, device=-1, workdir=".", table_limit=200000, quiet=False, dipole_rcut=2.0):
     """Run the simulation described by a reference parameter file.  Returns the result table
     (dict of columns, as written to result.txt).  With world > 1 each rank runs its share of the
     grid and returns only its rows; rank 0 should gather and write (see scripts/)."""
     t0 = time.time()
     p = paramfile.parse(rpath)
-    if abs(p.dipoleAlpha) > 1e-5:
-        raise NotImplementedError("dipole coupling: the reference's own path raises (Lattice.py:298); not built in this round")
     if p.algorithm not in ("Metropolis", "Wolff"):
         raise ValueError("only Metropolis and Wolff algorithm is supported")
     model = p.model
     spec = p.spec()
+    if abs(p.dipoleAlpha) > 1e-5:
+        # mcMain.py:37-40 would call generateDipoleBondings (all pairs, open boundary; raises in the reference).
+        # Here: periodic cut-off stencil of radius dipole_rcut (units of LMatrix), SURVEY 8 f2.
+        from .lattice import add_dipole_stencil
+        spec = add_dipole_stencil(spec, p.dipoleAlpha, dipole_rcut, ising=(model == engine.ISING))
     T, H = p.grid()
     Tf = np.maximum(T, 0.1)
     algo = engine.WOLFF if p.algorithm == "Wolff" else engine.METROPOLIS

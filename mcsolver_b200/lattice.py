@@ -345,3 +345,89 @@ def positions(spec: LatticeSpec) -> np.ndarray:
     frac = np.asarray(spec.pos, dtype=float)
     p = (cell[:, None, :] + frac[None, :, :]).reshape(-1, 3)
     return p @ np.asarray(spec.LMatrix, dtype=float)
+
+
+# ---------------------------------------------------------------------------------------------
+# dipole-dipole coupling
+# ---------------------------------------------------------------------------------------------
+def dipole_tensor(r, alpha, ising=False):
+    """J_dip = alpha/|r|^3 (1 - 3 r^ r^T) in the 9-vector order xx,yy,zz,xy,xz,yz,yx,zx,zy
+    (Lattice.py:300-305); Ising keeps only alpha/|r|^3 (Lattice.py:296-298)."""
+    r = np.asarray(r, dtype=float)
+    d = float(np.sqrt(np.dot(r, r)))
+    a = alpha / d ** 3
+    if ising:
+        return a
+    x, y, z = r / d
+    return np.array([a * (1 - 3 * x * x), a * (1 - 3 * y * y), a * (1 - 3 * z * z), -3 * a * x * y, -3 * a * x * z, -3 * a * y * z,
+                     -3 * a * y * x, -3 * a * z * x, -3 * a * z * y])
+
+
+def add_dipole_all_pairs(spec: LatticeSpec, t: Tables, alpha_over_T: float) -> Tables:
+    """The reference's DEFINITION of the dipole term (Lattice.py:286-305): every ordered pair of distinct
+    orbitals gets an extra link appended (forceAdd: never merged) with open-boundary Cartesian separation
+    r = r_source - r_target.  O(N^2) links: reference-feasible sizes only (the reference's own code path
+    raises TypeError; tests pin this against the reference loop with the missing `distance` argument supplied)."""
+    N = t.N
+    ising = t.model == 1
+    pos = positions(spec)
+    extra = N - 1
+    maxL = t.maxL + extra
+    jd = () if ising else (9,)
+    nbr = np.full((N, maxL), -1, dtype=np.int32)
+    J = np.zeros((N, maxL) + jd)
+    nlink = t.nlink.copy()
+    nbr[:, :t.maxL] = t.nbr
+    J[:, :t.maxL] = t.J
+    for i in range(N):
+        k = nlink[i]
+        for j in range(N):
+            if i == j:
+                continue
+            nbr[i, k] = j
+            J[i, k] = dipole_tensor(pos[i] - pos[j], alpha_over_T, ising)
+            k += 1
+        nlink[i] = k
+    ignore = t.ignoreOffDiag
+    if not ising and np.any(np.abs(J[:, :, 3:]) > 1e-6):
+        ignore = 0
+    rNbr = np.full((t.rNbr.shape[0], maxL), -1, dtype=np.int32)
+    rNbr[:, :t.rNbr.shape[1]] = t.rNbr
+    return Tables(model=t.model, N=N, maxL=maxL, S=t.S, D=t.D, nlink=nlink.astype(np.int32), J=J, nbr=nbr, tri=t.tri, pairs=t.pairs,
+                  groups=t.groups, nG=t.nG, maxG=t.maxG, rOrb=t.rOrb, rCluster=t.rCluster, rNbr=rNbr, ignoreOffDiag=ignore, T=t.T)
+
+
+def add_dipole_stencil(spec: LatticeSpec, alpha: float, rcut: float, ising=False) -> LatticeSpec:
+    """Cut-off, periodic (minimum-image) reading of the dipole term for lattices the all-pairs definition
+    cannot reach: one extra bond template per unordered orbital pair with 0 < |r| <= rcut (Cartesian, in the
+    units of LMatrix).  Templates that coincide with an exchange bond are merged by the engine (J adds up)."""
+    LM = np.asarray(spec.LMatrix, dtype=float)
+    frac = np.asarray(spec.pos, dtype=float)
+    no = spec.norb
+    inv = np.linalg.inv(LM)
+    need = [int(np.floor(rcut * np.linalg.norm(inv[:, k]) + 1e-9)) for k in range(3)]   # cells a bond can span along axis k
+    reach = [0, 0, 0]
+    for k in range(3):
+        if spec.L[k] == 1:
+            continue
+        if 2 * need[k] + 1 > spec.L[k]:    # an image and its mirror would be the same site
+            raise ValueError("dipole cutoff %g needs a supercell of at least %d cells along axis %d" % (rcut, 2 * need[k] + 1, k))
+        reach[k] = min(need[k] + 1, (spec.L[k] - 1) // 2)
+    bonds = list(spec.bonds)
+    for o in range(no):
+        for o2 in range(no):
+            for dx in range(-reach[0], reach[0] + 1):
+                for dy in range(-reach[1], reach[1] + 1):
+                    for dz in range(-reach[2], reach[2] + 1):
+                        # each unordered pair once: (o,o2,d) and (o2,o,-d) are the same bond
+                        if o2 < o or (o2 == o and (dx, dy, dz) <= (0, 0, 0)):
+                            continue
+                        r = (np.array([dx, dy, dz]) + frac[o2] - frac[o]) @ LM
+                        d = np.sqrt(np.dot(r, r))
+                        if d < 1e-9 or d > rcut + 1e-9:
+                            continue
+                        Jd = dipole_tensor(r, alpha, ising)
+                        J9 = [float(Jd)] + [0.0] * 8 if ising else [float(v) for v in Jd]
+                        bonds.append((o, o2, (dx, dy, dz), J9))
+    return LatticeSpec(L=spec.L, S=spec.S, D=spec.D, bonds=bonds, LMatrix=spec.LMatrix, pos=spec.pos, pair=spec.pair, groups=spec.groups,
+                       groupInSC=spec.groupInSC, circuits=spec.circuits)

@@ -101,7 +101,7 @@ class CapturedArgs(Exception):
 
 def reference_tables(LMatrix, pos, S, D, bonds, T, L, ki=(0, 0, (0, 0, 0)), orbGroupList=(),
                      groupInSC=False, h=0.0, On=3, spinFrame=0, circuits=(), algo="Metropolis",
-                     nsweep=1, nthermal=0, ninterval=0, flunc=0.0):
+                     nsweep=1, nthermal=0, ninterval=0, flunc=0.0, dipoleAlpha=0.0):
     """Build the positional argument tuple the reference's mcMain.py would hand to MCMainFunction,
     by running the reference's own MC.__init__ + mainLoopViaCLib[_On] with the engine import
     intercepted.  bonds: list of (src, tgt, (n1,n2,n3), J9) with J9 in the reference order
@@ -113,7 +113,7 @@ def reference_tables(LMatrix, pos, S, D, bonds, T, L, ki=(0, 0, (0, 0, 0)), orbG
     mc = mcMain.MC(0, np.array(LMatrix, dtype=float), pos=np.array(pos, dtype=float), S=list(S),
                    D=[list(d) for d in D], bondList=bondList, T=T, Lx=L[0], Ly=L[1], Lz=L[2],
                    ki_s=ki[0], ki_t=ki[1], ki_overLat=list(ki[2]), orbGroupList=list(orbGroupList),
-                   groupInSC=groupInSC, h=h, dipoleAlpha=0, On=On, spinFrame=spinFrame,
+                   groupInSC=groupInSC, h=h, dipoleAlpha=dipoleAlpha, On=On, spinFrame=spinFrame,
                    localCircuitList=list(circuits))
     captured = {}
 
@@ -140,6 +140,21 @@ def reference_tables(LMatrix, pos, S, D, bonds, T, L, ki=(0, 0, (0, 0, 0)), orbG
         else:
             del sys.modules[name]
     return captured["args"]
+
+
+def patch_reference_dipole():
+    """Runtime shim that makes the reference's OWN dipole loop (Lattice.py:286-308) runnable for Ising:
+    it calls addLinking(target, J, forceAdd=True) without the required `distance` argument (TypeError at
+    Lattice.py:298 vs :34).  We wrap the method to default that argument; no reference source is modified."""
+    Lattice, _, _, _ = load_reference_host()
+    if getattr(Lattice.Orbital, "_mcg_patched", False):
+        return
+    orig = Lattice.Orbital.addLinking
+
+    def addLinking(self, targetOrb, strength, distance=None, quiet=False, forceAdd=False):
+        return orig(self, targetOrb, strength, distance, quiet=quiet, forceAdd=forceAdd)
+    Lattice.Orbital.addLinking = addLinking
+    Lattice.Orbital._mcg_patched = True
 
 
 def run_ref_engine(On, args, seed=None):

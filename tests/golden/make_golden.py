@@ -190,8 +190,26 @@ def make_stats():
     print("stats:", len(out), "points")
 
 
+def make_dipole():
+    """Ising + dipole through the reference's own all-pairs loop (with the missing `distance` argument
+    supplied at run time, refharness.patch_reference_dipole): the flattened tables."""
+    rh.patch_reference_dipole()
+    out = []
+    arrays = {}
+    for idx, (name, L, T, alpha, seed) in enumerate([("square", (4, 4, 1), 2.0, 0.3, 21), ("cubic", (3, 3, 2), 3.0, 0.5, 22)]):
+        spec = spec_of(name, L)
+        with contextlib.redirect_stdout(io.StringIO()):
+            a = list(rh.reference_tables(spec.LMatrix, spec.pos, spec.S, spec.D, spec.bonds, T=T, L=spec.L, ki=spec.pair,
+                                         orbGroupList=spec.groups, groupInSC=spec.groupInSC, h=0.0, On=1, dipoleAlpha=alpha))
+        # The reference ENGINE cannot run these tables: the block-spin link table is -1 padded up to the
+        # new maxNLinking and isingLib.c:111-113 dereferences lattice[-1] (segfault).  Only the tables are pinned.
+        out.append(dict(spec=name, L=L, T=T, alpha=alpha, args=_jsonable(a)))
+    json.dump(out, open(os.path.join(HERE, "dipole.json"), "w"))
+    print("dipole:", len(out), "cases")
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["tables", "kat", "runs", "stats"]
+    what = sys.argv[1:] or ["tables", "kat", "runs", "stats", "dipole"]
     assert rh.have_reference_host() and rh.have_ref_engine(), "needs /root/reference and oracle/_ref (make -f oracle/Makefile)"
     for w in what:
-        {"tables": make_tables, "kat": make_kat, "runs": make_runs, "stats": make_stats}[w]()
+        {"tables": make_tables, "kat": make_kat, "runs": make_runs, "stats": make_stats, "dipole": make_dipole}[w]()

