@@ -32,6 +32,7 @@ struct SClassD {
 struct StructArgs {
     int Xd, Yd, Zd, Zc, ncellc, nclass, nrows, N;
     int px, py, pz, norb, Lx, Ly, Lz;
+    int psx, psy, psz;       // log2 of the colouring period per axis, or -1 if it is not a power of two
     const SClassD *classes;
     const SLinkD *links;
     const void *J;

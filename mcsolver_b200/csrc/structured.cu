@@ -35,6 +35,7 @@ struct StructuredSystem {
     int pair_s, pair_t, pair_d[3];
     int ncircuit = 0;
     std::vector<int> circuits;           // [ncircuit][3][4] internal axes
+    std::vector<int> tvertsHost, ttrisHost;
     std::vector<SClassD> classes;        // sorted by colour
     std::vector<int> classOf;            // [(a*py+b)*pz+c)*norb+o] -> class index
     std::vector<int> colourClassStart;   // [C+1]
@@ -46,15 +47,23 @@ struct StructuredSystem {
     SClassD *d_classes = nullptr;
     SLinkD *d_links = nullptr;
     void *d_J = nullptr;
-    int *d_classOf = nullptr, *d_circuits = nullptr;
+    int *d_classOf = nullptr, *d_circuits = nullptr, *d_tverts = nullptr, *d_ttris = nullptr;
+    int nvert = 0;
     double *d_classSums = nullptr;       // [R][nclass][4]
     double *d_stage = nullptr;           // [3N] host<->device staging, allocated on demand
 };
 
+__device__ __forceinline__ void split_period(int v, int p, int ps, int &rem, int &quo) {
+    if (ps >= 0) { rem = v & (p - 1); quo = v >> ps; }      // periods are almost always 1, 2 or 4
+    else { quo = v / p; rem = v - quo * p; }
+}
 __device__ __forceinline__ int struct_pos(const StructArgs &a, int x, int y, int z, int o) {
-    int ca = x % a.px, cb = y % a.py, cc = z % a.pz;
+    int ca, cb, cc, X, Y, Z;
+    split_period(x, a.px, a.psx, ca, X);
+    split_period(y, a.py, a.psy, cb, Y);
+    split_period(z, a.pz, a.psz, cc, Z);
     int q = a.classOf[((ca * a.py + cb) * a.pz + cc) * a.norb + o];
-    return ((q * a.Xd + x / a.px) * a.Yd + y / a.py) * a.Zd + z / a.pz;
+    return ((q * a.Xd + X) * a.Yd + Y) * a.Zd + Z;
 }
 __device__ __forceinline__ int struct_site_id(const StructArgs &a, int p) {
     int q = p / a.ncellc, cell = p - q * a.ncellc;
@@ -323,6 +332,67 @@ __global__ void __launch_bounds__(256) k_struct_topo(StructArgs a, int ncirc, co
     block_accumulate<1>(v, sums + (size_t)r * NSUM + SUM_AREA, smem);
 }
 
+
+// Topological charge, one thread per CELL: the ncircuit triangles of a cell share vertices (the four
+// circuits of samples/SkyrmionOnHexLattice touch 5 distinct sites), so the distinct vertices are loaded
+// once and the triangles index into them.  fp32 engines evaluate the solid angle in fp32 (sum in fp64);
+// fp64 engines keep the reference's double arithmetic (parity <= 1e-12).   calcSignedArea heisenbergLib.c:114-127
+template <typename T> __device__ __forceinline__ T tri_area(const T (&a)[3], const T (&b)[3], const T (&c)[3], T la, T lb, T lc) {
+    T ab = (a[0] * b[0] + a[1] * b[1] + a[2] * b[2]) / la / lb;
+    T bc = (b[0] * c[0] + b[1] * c[1] + b[2] * c[2]) / lb / lc;
+    T ca = (c[0] * a[0] + c[1] * a[1] + c[2] * a[2]) / lc / la;
+    T cx = b[1] * c[2] - b[2] * c[1], cy = b[2] * c[0] - b[0] * c[2], cz = b[0] * c[1] - b[1] * c[0];
+    T re = T(1) + ab + bc + ca;
+    T im = (a[0] * cx + a[1] * cy + a[2] * cz) / la / lb / lc;
+    if (fabs(re) < T(1e-6)) return im > 0 ? T(MCG_REF_PI) : T(-MCG_REF_PI);
+    return T(2) * atan(im / re);
+}
+// same quantity for vertices already normalised to unit length (fp32 engines)
+template <typename T> __device__ __forceinline__ T tri_area_unit(const T (&a)[3], const T (&b)[3], const T (&c)[3]) {
+    T cx = b[1] * c[2] - b[2] * c[1], cy = b[2] * c[0] - b[0] * c[2], cz = b[0] * c[1] - b[1] * c[0];
+    T re = T(1) + (a[0] * b[0] + a[1] * b[1] + a[2] * b[2]) + (b[0] * c[0] + b[1] * c[1] + b[2] * c[2]) + (c[0] * a[0] + c[1] * a[1] + c[2] * a[2]);
+    T im = a[0] * cx + a[1] * cy + a[2] * cz;
+    if (fabs(re) < T(1e-6)) return im > 0 ? T(MCG_REF_PI) : T(-MCG_REF_PI);
+    return T(2) * atan(im / re);
+}
+constexpr int TOPO_MAXV = 12;
+template <typename real>
+__global__ void __launch_bounds__(256) k_struct_topo_cells(StructArgs a, int ncirc, int nvert, const int *__restrict__ verts,
+                                                           const int *__restrict__ tris, double *sums) {
+    __shared__ double smem[32];
+    int r = blockIdx.y;
+    int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    double v[1] = {0.0};
+    int ncell = a.Lx * a.Ly * a.Lz;
+    if (cell < ncell) {
+        int z = cell % a.Lz, y = (cell / a.Lz) % a.Ly, x = cell / (a.Lz * a.Ly);
+        const real *sp = (const real *)a.spin + (size_t)r * 3 * a.N;
+        real s[TOPO_MAXV][3], l[TOPO_MAXV];
+        for (int k = 0; k < nvert; k++) {
+            const int *e = verts + 4 * k;
+            int xx = x + e[1]; if (xx >= a.Lx) xx -= a.Lx;
+            int yy = y + e[2]; if (yy >= a.Ly) yy -= a.Ly;
+            int zz = z + e[3]; if (zz >= a.Lz) zz -= a.Lz;
+            int p = struct_pos(a, xx, yy, zz, e[0]);
+            s[k][0] = sp[p]; s[k][1] = sp[(size_t)a.N + p]; s[k][2] = sp[2 * (size_t)a.N + p];
+            l[k] = (real)fabs(a.classes[a.classOf[e[0]]].S);   // |S| depends on the orbital only (class (0,0,0,o))
+            if (sizeof(real) == 4) {   // fp32: normalise once per vertex instead of dividing in every triangle
+                real inv = real(1) / l[k];
+                s[k][0] *= inv; s[k][1] *= inv; s[k][2] *= inv;
+                l[k] = real(1);
+            }
+        }
+        double acc = 0.0;
+        for (int t = 0; t < ncirc; t++) {
+            int i0 = tris[3 * t], i1 = tris[3 * t + 1], i2 = tris[3 * t + 2];
+            if (sizeof(real) == 4) acc += (double)tri_area_unit<real>(s[i0], s[i1], s[i2]);
+            else acc += (double)tri_area<real>(s[i0], s[i1], s[i2], l[i0], l[i1], l[i2]);
+        }
+        v[0] = acc;
+    }
+    block_accumulate<1>(v, sums + (size_t)r * NSUM + SUM_AREA, smem);
+}
+
 template <int NC, typename real>
 __global__ void __launch_bounds__(256) k_struct_init(StructArgs a, double flunc) {
     int r = blockIdx.y;
@@ -570,7 +640,9 @@ static StructArgs struct_args(const mcg_system *s) {
     StructArgs a;
     a.Xd = st->Xd; a.Yd = st->Yd; a.Zd = st->Zd; a.Zc = st->Zd / st->V; a.ncellc = st->ncellc; a.nclass = st->nclass;
     a.nrows = st->nrows; a.N = s->N;
-    a.px = st->p[0]; a.py = st->p[1]; a.pz = st->p[2]; a.norb = st->norb; a.Lx = st->L[0]; a.Ly = st->L[1]; a.Lz = st->L[2];
+    a.px = st->p[0]; a.py = st->p[1]; a.pz = st->p[2]; a.norb = st->norb;
+    auto lg = [](int p) { int s = 0; while ((1 << s) < p) s++; return (1 << s) == p ? s : -1; };
+    a.psx = lg(a.px); a.psy = lg(a.py); a.psz = lg(a.pz); a.Lx = st->L[0]; a.Ly = st->L[1]; a.Lz = st->L[2];
     a.classes = st->d_classes; a.links = st->d_links; a.J = st->d_J; a.classOf = st->d_classOf;
     a.spin = s->d_spin; a.beta = s->d_beta; a.field = s->d_field; a.cnt = s->d_cnt; a.classSums = st->d_classSums;
     a.key = make_rng_key(s->seed);
@@ -789,6 +861,18 @@ static void structured_build_host(mcg_system *s, const mcg_lattice_desc *d, std:
         st->circuits.push_back(e[0]);
         for (int k = 0; k < 3; k++) st->circuits.push_back(mod(dd[k], L[k]));
     }
+    // distinct vertices of the circuit templates (cell-relative) and triangles as indices into them
+    std::vector<int> tverts, ttris;
+    for (int i = 0; i < st->ncircuit * 3; i++) {
+        const int *e = st->circuits.data() + 4 * i;
+        int found = -1;
+        for (int k = 0; k < (int)tverts.size() / 4; k++)
+            if (tverts[4 * k] == e[0] && tverts[4 * k + 1] == e[1] && tverts[4 * k + 2] == e[2] && tverts[4 * k + 3] == e[3]) found = k;
+        if (found < 0) { found = (int)tverts.size() / 4; tverts.insert(tverts.end(), e, e + 4); }
+        ttris.push_back(found);
+    }
+    st->nvert = (int)tverts.size() / 4;
+    st->tvertsHost = tverts; st->ttrisHost = ttris;
     s->S_host.clear();
     s->maxL = 0;
     for (int o = 0; o < no; o++) s->maxL = std::max(s->maxL, (int)tm[o].size());
@@ -809,6 +893,8 @@ void structured_create(mcg_system *s, const mcg_lattice_desc *d) {
     else { std::vector<float> jf(Jt.begin(), Jt.end()); st->d_J = up(jf.data(), jf.size() * sizeof(float)); }
     st->d_classOf = (int *)up(st->classOf.data(), st->classOf.size() * sizeof(int));
     st->d_circuits = (int *)up(st->circuits.data(), st->circuits.size() * sizeof(int));
+    st->d_tverts = (int *)up(st->tvertsHost.data(), st->tvertsHost.size() * sizeof(int));
+    st->d_ttris = (int *)up(st->ttrisHost.data(), st->ttrisHost.size() * sizeof(int));
     size_t cs = (size_t)s->R * st->nclass * 4 * sizeof(double);
     MCG_CUDA(cudaMalloc(&st->d_classSums, cs));
     MCG_CUDA(cudaMemset(st->d_classSums, 0, cs));
@@ -842,7 +928,7 @@ int structured_jit_check(const mcg_lattice_desc *d, int precision, std::string &
 
 void structured_destroy(StructuredSystem *st) {
     if (!st) return;
-    void *bufs[] = {st->d_classes, st->d_links, st->d_J, st->d_classOf, st->d_circuits, st->d_classSums, st->d_stage};
+    void *bufs[] = {st->d_classes, st->d_links, st->d_J, st->d_classOf, st->d_circuits, st->d_classSums, st->d_stage, st->d_tverts, st->d_ttris};
     for (void *b : bufs) if (b) cudaFree(b);
     delete st;
 }
@@ -960,8 +1046,15 @@ static void fold_and_extras(mcg_system *s) {
         });
     }
     if (st->ncircuit > 0 && s->NC == 3) {
-        dim3 g((s->nTri + 255) / 256, s->R);
         s->launches++;
+        if (st->nvert <= TOPO_MAXV) {
+            dim3 gc((s->nLat + 255) / 256, s->R);
+            if (s->prec == 64) k_struct_topo_cells<double><<<gc, 256, 0, s->stream>>>(a, st->ncircuit, st->nvert, st->d_tverts, st->d_ttris, s->d_sums);
+            else k_struct_topo_cells<float><<<gc, 256, 0, s->stream>>>(a, st->ncircuit, st->nvert, st->d_tverts, st->d_ttris, s->d_sums);
+            MCG_CUDA(cudaGetLastError());
+            return;
+        }
+        dim3 g((s->nTri + 255) / 256, s->R);
         if (s->prec == 64) k_struct_topo<double><<<g, 256, 0, s->stream>>>(a, st->ncircuit, st->d_circuits, s->d_sums);
         else k_struct_topo<float><<<g, 256, 0, s->stream>>>(a, st->ncircuit, st->d_circuits, s->d_sums);
     }
