@@ -98,6 +98,9 @@ typedef struct {
     int32_t pair_d[3];
     int32_t ncircuit;         /* triangles per cell */
     const int32_t *circuits;  /* [ncircuit*3*4]: per vertex (orb, dx, dy, dz) - Lattice.py:223-234 */
+    int32_t ngroup;           /* orbital groups (fileio orbGroupList); 0 = none */
+    const int32_t *group_mask;/* [ngroup*norb] 1 if the orbital belongs to the group */
+    int32_t group_in_sc;      /* 1: "Supergroup" - a group spans the whole supercell (Lattice.py:208-209); 0: cell (0,0,0) only */
 } mcg_lattice_desc;
 
 typedef struct {

@@ -579,6 +579,11 @@ MCG_API int mcg_create_lattice(const mcg_lattice_desc *d, const mcg_config *cfg,
         sys->prec = cfg->precision; sys->R = cfg->nReplica; sys->seed = cfg->seed; sys->replica0 = (uint32_t)cfg->replica_offset;
         structured_create(sys.get(), d);
         alloc_replica_state(sys.get(), cfg);
+        if (sys->nG > 0) {
+            size_t n = (size_t)(sys->nG + 2) * (sys->nG + 1);
+            sys->d_gacc = dalloc<double>((size_t)sys->R * n);
+            MCG_CUDA(cudaMemset(sys->d_gacc, 0, sizeof(double) * sys->R * n));
+        }
         MCG_CUDA(cudaStreamCreateWithFlags(&sys->stream, cudaStreamNonBlocking));
         *out = sys.release();
     });

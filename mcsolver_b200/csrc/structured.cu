@@ -47,7 +47,9 @@ struct StructuredSystem {
     SClassD *d_classes = nullptr;
     SLinkD *d_links = nullptr;
     void *d_J = nullptr;
-    int *d_classOf = nullptr, *d_circuits = nullptr, *d_tverts = nullptr, *d_ttris = nullptr;
+    int *d_classOf = nullptr, *d_circuits = nullptr, *d_tverts = nullptr, *d_ttris = nullptr, *d_gmask = nullptr;
+    std::vector<int> gmaskHost;
+    bool groupInSC = true;
     int nvert = 0;
     double *d_classSums = nullptr;       // [R][nclass][4]
     double *d_stage = nullptr;           // [3N] host<->device staging, allocated on demand
@@ -259,12 +261,13 @@ __global__ void __launch_bounds__(256) k_struct(StructArgs a, int q0, int nqc, i
 
 
 // classSums -> the raw per-sweep sums the common finalize kernel consumes; clears classSums
-__global__ void k_struct_fold(StructArgs a, int R, int pair_s, int pair_t, int selfPairs, double nLat, double *sums) {
+__global__ void k_struct_fold(StructArgs a, int R, int NC, int prec, int pair_s, int pair_t, int selfPairs, double nLat, double *sums, int nG,
+                              const int *__restrict__ gmask, int groupInSC, double *gacc, const int32_t *slot) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
     double *s = sums + (size_t)r * NSUM;
     for (int q = 0; q < a.nclass; q++) {
-        double *c = a.classSums + ((size_t)r * a.nclass + q) * 4;
+        const double *c = a.classSums + ((size_t)r * a.nclass + q) * 4;
         const SClassD &cl = a.classes[q];
         for (int k = 0; k < 3; k++) {
             s[SUM_TOT + k] += c[k];
@@ -273,6 +276,41 @@ __global__ void k_struct_fold(StructArgs a, int R, int pair_s, int pair_t, int s
         }
         s[SUM_E] += c[3];
         if (selfPairs && cl.o == pair_s) s[SUM_SIJ] += cl.S * cl.S * (nLat / (a.nclass / a.norb));
+    }
+    // orbital-group statistics (heisenbergLib.c:806-830): group sums are sums of class sums ("Supergroup")
+    // or the listed orbitals of cell (0,0,0); the last "group" is totSpin/nLat
+    if (nG > 0) {
+        const int n1 = nG + 1;
+        double *G = gacc + (size_t)slot[r] * (n1 + 1) * n1;
+        double g[17][3];
+        for (int x = 0; x < nG; x++) {
+            g[x][0] = g[x][1] = g[x][2] = 0.0;
+            if (groupInSC) {
+                for (int q = 0; q < a.nclass; q++)
+                    if (gmask[x * a.norb + a.classes[q].o]) {
+                        const double *c = a.classSums + ((size_t)r * a.nclass + q) * 4;
+                        g[x][0] += c[0]; g[x][1] += c[1]; g[x][2] += c[2];
+                    }
+            } else {
+                for (int o = 0; o < a.norb; o++)
+                    if (gmask[x * a.norb + o]) {
+                        int p = struct_pos(a, 0, 0, 0, o);
+                        for (int k = 0; k < NC; k++)
+                            g[x][k] += prec == 32 ? (double)((const float *)a.spin)[((size_t)r * NC + k) * a.N + p]
+                                                  : ((const double *)a.spin)[((size_t)r * NC + k) * a.N + p];
+                    }
+            }
+        }
+        for (int k = 0; k < 3; k++) g[nG][k] = s[SUM_TOT + k] / nLat;
+        for (int x = 0; x < n1; x++)
+            for (int y = 0; y < n1; y++) {
+                double d = g[x][0] * g[y][0] + g[x][1] * g[y][1] + g[x][2] * g[y][2];
+                G[x * n1 + y] += d;
+                if (x == y) G[n1 * n1 + x] += d * d;
+            }
+    }
+    for (int q = 0; q < a.nclass; q++) {
+        double *c = a.classSums + ((size_t)r * a.nclass + q) * 4;
         c[0] = c[1] = c[2] = c[3] = 0.0;
     }
 }
@@ -845,6 +883,14 @@ static void structured_build_host(mcg_system *s, const mcg_lattice_desc *d, std:
     for (int c = 0; c < bestC; c++) {
         if (s->prec == 32) build_pass(float(0), c); else build_pass(double(0), c);
     }
+    // orbital groups
+    s->nG = (d->model != 1 && d->ngroup > 0) ? d->ngroup : 0;
+    MCG_REQUIRE(s->nG <= 16, "at most 16 orbital groups on the structured path");
+    if (s->nG > 0) {
+        MCG_REQUIRE(d->group_mask, "group_mask is NULL");
+        st->gmaskHost.assign(d->group_mask, d->group_mask + (size_t)s->nG * no);
+        st->groupInSC = d->group_in_sc != 0;
+    }
     // measurement templates
     st->pair_s = d->pair_s; st->pair_t = d->pair_t;
     conv(d->pair_d, st->pair_d);
@@ -893,6 +939,7 @@ void structured_create(mcg_system *s, const mcg_lattice_desc *d) {
     else { std::vector<float> jf(Jt.begin(), Jt.end()); st->d_J = up(jf.data(), jf.size() * sizeof(float)); }
     st->d_classOf = (int *)up(st->classOf.data(), st->classOf.size() * sizeof(int));
     st->d_circuits = (int *)up(st->circuits.data(), st->circuits.size() * sizeof(int));
+    st->d_gmask = (int *)up(st->gmaskHost.data(), st->gmaskHost.size() * sizeof(int));
     st->d_tverts = (int *)up(st->tvertsHost.data(), st->tvertsHost.size() * sizeof(int));
     st->d_ttris = (int *)up(st->ttrisHost.data(), st->ttrisHost.size() * sizeof(int));
     size_t cs = (size_t)s->R * st->nclass * 4 * sizeof(double);
@@ -928,7 +975,7 @@ int structured_jit_check(const mcg_lattice_desc *d, int precision, std::string &
 
 void structured_destroy(StructuredSystem *st) {
     if (!st) return;
-    void *bufs[] = {st->d_classes, st->d_links, st->d_J, st->d_classOf, st->d_circuits, st->d_classSums, st->d_stage, st->d_tverts, st->d_ttris};
+    void *bufs[] = {st->d_classes, st->d_links, st->d_J, st->d_classOf, st->d_circuits, st->d_classSums, st->d_stage, st->d_tverts, st->d_ttris, st->d_gmask};
     for (void *b : bufs) if (b) cudaFree(b);
     delete st;
 }
@@ -1037,7 +1084,8 @@ static void fold_and_extras(mcg_system *s) {
     StructuredSystem *st = s->st;
     StructArgs a = struct_args(s);
     s->launches++;
-    k_struct_fold<<<(s->R + 63) / 64, 64, 0, s->stream>>>(a, s->R, st->pair_s, st->pair_t, st->selfPairs ? 1 : 0, (double)s->nLat, s->d_sums);
+    k_struct_fold<<<(s->R + 63) / 64, 64, 0, s->stream>>>(a, s->R, s->NC, s->prec, st->pair_s, st->pair_t, st->selfPairs ? 1 : 0, (double)s->nLat, s->d_sums,
+                                                          s->nG, st->d_gmask, st->groupInSC ? 1 : 0, s->d_gacc, s->d_slot);
     if (!st->selfPairs) {
         dim3 g((s->nLat + 255) / 256, s->R);
         s->launches++;

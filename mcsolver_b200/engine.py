@@ -137,6 +137,11 @@ class System:
         d.pair_s, d.pair_t = spec.pair[0], spec.pair[1]
         d.pair_d = (C.c_int32 * 3)(*spec.pair[2])
         d.ncircuit, d.circuits = len(spec.circuits), ptr(circ)
+        mask = np.zeros((len(spec.groups), spec.norb), dtype=np.int32)
+        for k, grp in enumerate(spec.groups):
+            mask[k, list(grp)] = 1
+        keep.append(mask)
+        d.ngroup, d.group_mask, d.group_in_sc = (len(spec.groups) if model != ISING else 0), ptr(mask), int(bool(spec.groupInSC))
         return d
 
     @classmethod
@@ -147,7 +152,7 @@ class System:
         cfg = _config(precision, nReplica, beta, field, seed, replica_offset, device, keep)
         h = C.c_void_p()
         check(_ffi.lib().mcg_create_lattice(C.byref(d), C.byref(cfg), C.byref(h)))
-        return cls(h, int(model), spec.nsite, nReplica, 0)
+        return cls(h, int(model), spec.nsite, nReplica, len(spec.groups) if model != ISING else 0)
 
     def close(self):
         if self._h is not None:

@@ -77,10 +77,13 @@ def test_structured_whole_run_fused_measurement_matches_oracle(case):
         order = s.colour_order()
         s.init_spins(0.3)
         fr = s.run(0, 4, 15, 2 * t.N, spinFrame=3)
-        out, _ = s.results()
+        out, grp = s.results()
     r = o.run(2, 4, 15, 2 * t.N, flunc=0.3, spinFrame=3, order=order, seed=17)
     for k in util.ON_CORE_SLOTS + [7]:
         assert abs(out[k] - r["out"][k]) <= 1e-9 * max(1.0, abs(r["out"][k])), (k, out[k], r["out"][k])
+    if t.nG:      # slot 28: orbital-group statistics from the fused class sums
+        assert grp.shape == r["group"].shape
+        assert np.max(np.abs(grp - r["group"]) / np.maximum(1.0, np.abs(r["group"]))) < 1e-9
     assert np.max(np.abs(fr[0] - r["frames"])) < 1e-9
 
 
@@ -145,3 +148,21 @@ def test_structured_wolff_trajectory_matches_oracle_fp64(case):
         got = s.get_spins()
         assert np.max(np.abs(got - r["spins"].reshape(got.shape))) < 1e-9
         assert s.counters() == tuple(int(v) for v in r["counters"])
+
+
+def test_structured_groups_in_cell_zero_only():
+    """groupInSC = False: a group holds the listed orbitals of cell (0,0,0) only (Lattice.py:211)."""
+    eng = _eng()
+    spec = spec_of("aniso", (6, 6, 1), groupInSC=False)
+    t = util.tables_for(dict(spec="aniso", L=(6, 6, 1), T=0.7, model=3))
+    from mcsolver_b200.lattice import build_tables
+    t = build_tables(spec, 0.7, 3)
+    assert t.maxG == 1 and t.groups.tolist() == [[0], [1]]
+    o = util.oracle_system(t, 0.3 / 0.7)
+    with eng.System.from_spec(spec, 3, precision=64, beta=[1 / 0.7], field=[0.3], seed=5) as s:
+        order = s.colour_order()
+        s.init_spins(0.4)
+        s.run(0, 2, 6, t.N)
+        out, grp = s.results()
+    r = o.run(2, 2, 6, t.N, flunc=0.4, order=order, seed=5)
+    assert np.max(np.abs(grp - r["group"]) / np.maximum(1.0, np.abs(r["group"]))) < 1e-9
