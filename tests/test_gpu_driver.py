@@ -38,3 +38,39 @@ def test_loadmc_skyrmion_field_scan_with_frames(tmp_path):
     assert frames == ["OnSpinDistribution.T0.300.H0.000.0.txt", "OnSpinDistribution.T0.300.H0.300.0.txt", "OnSpinDistribution.T0.300.H0.600.0.txt"]
     fr = np.loadtxt(tmp_path / frames[0])
     assert fr.shape == (288, 6) and np.allclose(np.linalg.norm(fr[:, 3:], axis=1), 1.0, atol=1e-5)
+
+
+def test_shims_inside_a_forked_process_pool_like_win_py(tmp_path):
+    """win.py:90-91,131-132 farms grid points over multiprocessing.Pool (fork).  The parent never touches
+    the library, each forked worker creates its own CUDA context on first call: run exactly that pattern
+    in a fresh interpreter (this pytest process may already hold a context, which must not be forked)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "pool.py"
+    script.write_text('''
+import sys, json
+sys.path.insert(0, %r)
+sys.path.insert(0, %r)
+from multiprocessing import Pool
+from mcsolver_b200.lattice import build_tables
+from tests.specs import spec_of
+
+def work(T):
+    from heisenberglib import MCMainFunction          # the shim, imported inside the worker as mcMain.py does
+    t = build_tables(spec_of("cubic", (6, 6, 6)), T, 3)
+    out = MCMainFunction(*t.on_args(0, 50, 100, t.N, 0.0, 0.0, 0))
+    return T, out[8] * T, out[10]
+
+if __name__ == "__main__":
+    with Pool(processes=3) as pool:
+        res = sorted(pool.imap_unordered(work, [0.8, 1.4, 3.0]))
+    print(json.dumps(res))
+''' % (root, os.path.join(root, "mcsolver_b200", "lib")))
+    out = subprocess.run([sys.executable, str(script)], check=True, capture_output=True, text=True, timeout=300).stdout
+    import json
+    res = json.loads(out.strip().splitlines()[-1])
+    assert [r[0] for r in res] == [0.8, 1.4, 3.0]
+    assert res[0][1] < res[1][1] < res[2][1] < 0          # energy rises with temperature
+    assert res[0][2] > 0.99 and res[2][2] < 0.9            # U4: ordered vs disordered
