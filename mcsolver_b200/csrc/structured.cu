@@ -484,6 +484,7 @@ __global__ void __launch_bounds__(256) k_struct_frame(StructArgs a, int r, doubl
 #include <cuda.h>
 #include <dlfcn.h>
 #include <nvrtc.h>
+#include <unistd.h>
 
 #include <map>
 #include <mutex>
@@ -594,10 +595,45 @@ struct JitPass {
 static std::mutex g_jit_mutex;
 static std::map<std::pair<int, std::string>, JitPass> g_jit_cache;   // (device, prologue) -> loaded kernels
 
+// ---- on-disk cubin cache: $MCG_CACHE_DIR or <library dir>/build/jitcache/<fnv1a(prologue + kernel headers)>.cubin ----
+static uint64_t fnv1a(const std::string &s, uint64_t h = 1469598103934665603ull) {
+    for (unsigned char c : s) { h ^= c; h *= 1099511628211ull; }
+    return h;
+}
+static std::string read_file(const std::string &path) {
+    std::string out;
+    if (FILE *f = fopen(path.c_str(), "rb")) {
+        char buf[65536];
+        size_t n;
+        while ((n = fread(buf, 1, sizeof buf, f)) > 0) out.append(buf, n);
+        fclose(f);
+    }
+    return out;
+}
+static std::string cache_path(const std::string &src) {
+    const char *dir = getenv("MCG_CACHE_DIR");
+    std::string d;
+    if (dir && dir[0]) d = dir;
+    else d = csrc_dir() + "/../build/jitcache";
+    if (getenv("MCG_NO_DISK_CACHE")) return "";
+    uint64_t h = fnv1a(src);
+    for (const char *f : {"/struct_pass.cuh", "/devmath.cuh", "/rng.cuh"}) h = fnv1a(read_file(csrc_dir() + f), h);
+    std::string mk = "mkdir -p '" + d + "' 2>/dev/null";
+    if (system(mk.c_str()) != 0) return "";
+    char name[64];
+    snprintf(name, sizeof name, "/%016llx.cubin", (unsigned long long)h);
+    return d + name;
+}
+
 // compile (or fetch) the specialised kernels; also usable without a GPU up to the cubin (tests)
 std::vector<char> jit_compile_cubin(const std::string &src, std::string &log) {
     JitApi &api = jit_api();
     if (!api.rtc_ok) { log = api.why; return {}; }
+    const std::string cpath = cache_path(src);
+    if (!cpath.empty()) {
+        std::string c = read_file(cpath);
+        if (c.size() > 1024) return std::vector<char>(c.begin(), c.end());
+    }
     nvrtcProgram prog;
     if (api.createProgram(&prog, src.c_str(), "mcg_pass.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) { log = "nvrtcCreateProgram failed"; return {}; }
     std::string inc = "-I" + csrc_dir();
@@ -612,6 +648,14 @@ std::vector<char> jit_compile_cubin(const std::string &src, std::string &log) {
         api.getCUBINSize(prog, &cs);
         cubin.resize(cs);
         api.getCUBIN(prog, cubin.data());
+        if (!cpath.empty()) {   // write-then-rename so concurrent ranks never read a partial file
+            std::string tmp = cpath + "." + std::to_string((long long)getpid());
+            if (FILE *f = fopen(tmp.c_str(), "wb")) {
+                bool ok = fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+                fclose(f);
+                if (!ok || rename(tmp.c_str(), cpath.c_str()) != 0) remove(tmp.c_str());
+            }
+        }
         if (const char *dump = getenv("MCG_JIT_DUMP")) {   // debugging aid: keep the last cubin for cuobjdump -sass
             if (FILE *f = fopen(dump, "wb")) { fwrite(cubin.data(), 1, cubin.size(), f); fclose(f); }
         }
