@@ -671,9 +671,22 @@ static bool jit_enabled(const mcg_system *s) {
     return (long long)s->N * s->R >= (1ll << 20);   // creation-time compile (~seconds) only pays for big jobs
 }
 
+// Full unrolling only pays while the specialised body stays inside the instruction cache: measured on the
+// 32-link dipole stencil (4 classes x 32 links x 4 sites unrolled) the JIT kernel ran 3x SLOWER than the
+// runtime-table kernel and took minutes to compile.  Budget: <= 16 links per class, <= 64 link bodies per module.
+static bool jit_worthwhile(const mcg_system *s, int colour) {
+    const StructuredSystem *st = s->st;
+    int q0 = st->colourClassStart[colour], nqc = st->colourClassStart[colour + 1] - q0, total = 0;
+    for (int j = 0; j < nqc; j++) {
+        if (st->classes[q0 + j].nlink > 16) return false;
+        total += st->classes[q0 + j].nlink;
+    }
+    return total <= 64;
+}
+
 bool jit_launch_pass(mcg_system *s, int colour, int mode, const StructArgs &a, int q0, int rowsPerBlock, int nrb, uint64_t sweep,
                      double pAtt, dim3 grid, dim3 block) {
-    if (!jit_enabled(s)) return false;
+    if (!jit_enabled(s) || !jit_worthwhile(s, colour)) return false;
     JitApi &api = jit_api();
     if (!api.ok) return false;
     JitPass *jp;
@@ -1006,7 +1019,7 @@ int structured_jit_check(const mcg_lattice_desc *d, int precision, std::string &
     o << "colours=" << tmp.C << " classes=" << tmp.st->nclass << " period=" << tmp.st->p[0] << "x" << tmp.st->p[1] << "x" << tmp.st->p[2]
       << " V=" << tmp.st->V << "\n";
     for (int c = 0; c < tmp.C; c++) {
-        if (!tmp.st->fastOK[c] || tmp.st->V == 1) { o << "colour " << c << ": not eligible for the fast path\n"; continue; }
+        if (!tmp.st->fastOK[c] || tmp.st->V == 1 || !jit_worthwhile(&tmp, c)) { o << "colour " << c << ": not eligible for specialisation\n"; continue; }
         std::string log;
         std::vector<char> cubin = jit_compile_cubin(jit_prologue(&tmp, c), log);
         o << "colour " << c << ": cubin " << cubin.size() << " bytes" << (log.empty() ? "" : " log: " + log.substr(0, 1500)) << "\n";

@@ -1,0 +1,17 @@
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from mcsolver_b200 import engine
+from mcsolver_b200.lattice import LatticeSpec, add_dipole_stencil
+J = [-1, -1, -1] + [0] * 6
+cu = lambda L: LatticeSpec(L=(L, L, L), S=[1.0], bonds=[(0, 0, (1, 0, 0), J), (0, 0, (0, 1, 0), J), (0, 0, (0, 0, 1), J)])
+spec = add_dipole_stencil(cu(128), 0.1, 2.0)
+R = 8
+for jit, minb in [("0", "4"), ("1", "4"), ("1", "2"), ("1", "1")]:
+    os.environ["MCG_JIT"] = jit
+    os.environ["MCG_JIT_MINB"] = minb
+    with engine.System.from_spec(spec, 3, precision=32, nReplica=R, beta=1 / np.linspace(1.2, 1.9, R), seed=1) as s:
+        s.init_spins(0.0)
+        s.timed_sweeps(2, with_measure=False)
+        ms = s.timed_sweeps(4, with_measure=False)
+        print("dipole r<=2 128^3 jit=%s minb=%s colours=%d: %.3f ms/sweep %.3e attempts/s" % (jit, minb, s.num_colours(), ms / 4, R * spec.nsite * 4 / ms * 1e3), flush=True)
