@@ -158,7 +158,9 @@ template <int I, int N, typename F> __device__ __forceinline__ void ct_for(F &&f
 
 // One colour pass over the rows [rb*rowsPerBlock, ...) of class q = q0 + j for replica r.
 // MODE 0: update only   1: update + fused measurement (classSums += M, E contributions)
-template <int NC, typename real, bool FULLJ, int MODE, int V, typename CLS>
+// PARTIAL: sweeps in which a site attempts only with probability pAtt (ninterval < N); the common
+// full sweep drops the fourth uniform, its compare and the attempt counter from the per-site code.
+template <int NC, typename real, bool FULLJ, int MODE, int V, bool PARTIAL, typename CLS>
 __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, int q, int r, int rb, int rowsPerBlock, uint64_t sweep,
                                           real pAtt, double *red) {
     const int Xd = MCG_DIM(a, Xd), Yd = MCG_DIM(a, Yd), Zd = MCG_DIM(a, Zd), Zc = MCG_DIM(a, Zc), N = MCG_DIM(a, N);
@@ -227,7 +229,7 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                 const real hx = H[0][v], hy = H[1][v], hz = H[2][v];
                 uint32_t w[4];
                 rng4(a.key, a.replica0 + r, STREAM_METRO, 0, sweep, id0 + (uint32_t)(v * idStrideZ), w);
-                const bool att = !(pAtt < real(1)) || u01<real>(w[3]) < pAtt;
+                const bool att = PARTIAL ? (u01<real>(w[3]) < pAtt) : true;
                 bool acc;
                 if (NC == 1) {
                     const real corr = real(2) * (beta * sx * hx - hf * sx);                     // isingLib.c:242
@@ -253,7 +255,7 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                         sx *= f; sy *= f; sz *= f;
                     }
                 }
-                natt += att ? 1 : 0;
+                if (PARTIAL) natt += att ? 1 : 0;
                 nacc += acc ? 1 : 0;
                 s[0][v] = sx; s[1][v] = sy; s[2][v] = sz;
                 if (MODE == 1) {
@@ -267,6 +269,7 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                     accE += beta * eb + eon;
                 }
             }
+            if (!PARTIAL) natt += V;
             real *ownw = sp + rowBase + Z0;
 #pragma unroll
             for (int c = 0; c < NC; c++) vstore<real, V>(ownw + (size_t)c * N, s[c]);
@@ -300,7 +303,7 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
 
 #ifndef MCG_JIT
 // offline entry: tables as a __grid_constant__ parameter
-template <int NC, typename real, bool FULLJ, int MODE, int V>
+template <int NC, typename real, bool FULLJ, int MODE, int V, bool PARTIAL>
 __global__ void __launch_bounds__(256, 4)
 k_struct_fast(const __grid_constant__ StructArgs a, const __grid_constant__ PassTable<real> T, int q0, int rowsPerBlock, int nrb,
               uint64_t sweep, real pAtt) {
@@ -308,10 +311,10 @@ k_struct_fast(const __grid_constant__ StructArgs a, const __grid_constant__ Pass
     const int nqc = T.nqc;
     const int bid = blockIdx.x;
     const int j = bid % nqc, tq = bid / nqc, rb = tq % nrb, r = tq / nrb;
-    pass_body<NC, real, FULLJ, MODE, V>(a, RtClass<real>{T, j}, q0 + j, r, rb, rowsPerBlock, sweep, pAtt, red);
+    pass_body<NC, real, FULLJ, MODE, V, PARTIAL>(a, RtClass<real>{T, j}, q0 + j, r, rb, rowsPerBlock, sweep, pAtt, red);
 }
 #else
-// ---- JIT entry points: JIT_NC, jit_real, JIT_FULLJ, JIT_V, JIT_NQC, JIT_NL, JIT_MINB, CtLinkData<J,K>, CtClassData<J>
+// ---- JIT entry points: JIT_NC, jit_real, JIT_FULLJ, JIT_V, JIT_NQC, JIT_PARTIAL, JIT_MINB, CtLinkData<J,K>, CtClassData<J>
 // come from the generated prologue ----
 template <int JJ, int K> struct CtLink {
     typedef CtLinkData<JJ, K> D;
@@ -343,7 +346,7 @@ template <int MODE, int J>
 __device__ __forceinline__ void jit_case(const StructArgs &a, int j, int q0, int r, int rb, int rowsPerBlock, uint64_t sweep,
                                          jit_real pAtt, double *red) {
     if constexpr (J < JIT_NQC) {
-        if (j == J) pass_body<JIT_NC, jit_real, JIT_FULLJ, MODE, JIT_V>(a, CtClass<J>{}, q0 + J, r, rb, rowsPerBlock, sweep, pAtt, red);
+        if (j == J) pass_body<JIT_NC, jit_real, JIT_FULLJ, MODE, JIT_V, JIT_PARTIAL>(a, CtClass<J>{}, q0 + J, r, rb, rowsPerBlock, sweep, pAtt, red);
         else jit_case<MODE, J + 1>(a, j, q0, r, rb, rowsPerBlock, sweep, pAtt, red);
     }
 }

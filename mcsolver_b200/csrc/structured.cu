@@ -44,6 +44,7 @@ struct StructuredSystem {
     std::vector<double> JHost;           // [nclass][MAXLINK][JW]
     std::vector<char> fastOK;            // per colour: pass table fits the __grid_constant__ fast path
     std::vector<std::vector<char>> passTables;   // per colour: PassTable<real> bytes
+    std::vector<void *> jitResolved;     // [colour*2 + partial] -> JitPass* once looked up (nullptr = not yet)
     SClassD *d_classes = nullptr;
     SLinkD *d_links = nullptr;
     void *d_J = nullptr;
@@ -553,7 +554,7 @@ static std::string lit(double v, bool f32) {
     return buf;
 }
 
-std::string jit_prologue(const mcg_system *s, int colour) {
+std::string jit_prologue(const mcg_system *s, int colour, bool partial) {
     const StructuredSystem *st = s->st;
     const bool f32 = s->prec == 32;
     const int q0 = st->colourClassStart[colour], nqc = st->colourClassStart[colour + 1] - q0;
@@ -561,7 +562,7 @@ std::string jit_prologue(const mcg_system *s, int colour) {
     std::ostringstream o;
     o << "#define MCG_JIT 1\ntypedef " << (f32 ? "float" : "double") << " jit_real;\n";
     o << "#define JIT_NC " << s->NC << "\n#define JIT_FULLJ " << (s->fullJ ? "true" : "false") << "\n#define JIT_V " << st->V
-      << "\n#define JIT_NQC " << nqc << "\n#define JIT_MINB " << (getenv("MCG_JIT_MINB") ? atoi(getenv("MCG_JIT_MINB")) : (f32 ? 4 : 2)) << "\n";
+      << "\n#define JIT_PARTIAL " << (partial ? "true" : "false") << "\n#define JIT_NQC " << nqc << "\n#define JIT_MINB " << (getenv("MCG_JIT_MINB") ? atoi(getenv("MCG_JIT_MINB")) : (f32 ? 4 : 2)) << "\n";
     o << "#define JIT_Xd " << st->Xd << "\n#define JIT_Yd " << st->Yd << "\n#define JIT_Zd " << st->Zd << "\n#define JIT_Zc "
       << st->Zd / st->V << "\n#define JIT_N " << s->N << "\n#define JIT_px " << st->p[0] << "\n#define JIT_py " << st->p[1]
       << "\n#define JIT_pz " << st->p[2] << "\n#define JIT_norb " << st->norb << "\n#define JIT_Ly " << st->L[1]
@@ -689,10 +690,13 @@ bool jit_launch_pass(mcg_system *s, int colour, int mode, const StructArgs &a, i
     if (!jit_enabled(s) || !jit_worthwhile(s, colour)) return false;
     JitApi &api = jit_api();
     if (!api.ok) return false;
-    JitPass *jp;
-    {
+    StructuredSystem *st = s->st;
+    const int slotIdx = colour * 2 + (pAtt < 1.0 ? 1 : 0);
+    if (st->jitResolved.empty()) st->jitResolved.assign((size_t)s->C * 2, nullptr);
+    JitPass *jp = static_cast<JitPass *>(st->jitResolved[slotIdx]);
+    if (!jp) {
         std::lock_guard<std::mutex> lock(g_jit_mutex);
-        auto key = std::make_pair(s->device, jit_prologue(s, colour));
+        auto key = std::make_pair(s->device, jit_prologue(s, colour, pAtt < 1.0));
         auto it = g_jit_cache.find(key);
         if (it == g_jit_cache.end()) {
             JitPass np;
@@ -707,7 +711,8 @@ bool jit_launch_pass(mcg_system *s, int colour, int mode, const StructArgs &a, i
             }
             it = g_jit_cache.emplace(key, np).first;
         }
-        jp = &it->second;
+        jp = &it->second;               // std::map nodes are stable: the pointer stays valid
+        st->jitResolved[slotIdx] = jp;
     }
     if (jp->failed) return false;
     float pf = (float)pAtt;
@@ -1021,7 +1026,7 @@ int structured_jit_check(const mcg_lattice_desc *d, int precision, std::string &
     for (int c = 0; c < tmp.C; c++) {
         if (!tmp.st->fastOK[c] || tmp.st->V == 1 || !jit_worthwhile(&tmp, c)) { o << "colour " << c << ": not eligible for specialisation\n"; continue; }
         std::string log;
-        std::vector<char> cubin = jit_compile_cubin(jit_prologue(&tmp, c), log);
+        std::vector<char> cubin = jit_compile_cubin(jit_prologue(&tmp, c, false), log);
         o << "colour " << c << ": cubin " << cubin.size() << " bytes" << (log.empty() ? "" : " log: " + log.substr(0, 1500)) << "\n";
         if (cubin.empty()) { report = o.str(); return -1; }
         ncompiled++;
@@ -1125,7 +1130,8 @@ template <int MODE> static void launch_pass(mcg_system *s, int colour, uint64_t 
                 if constexpr (MODE != 2) {
                     constexpr int VV = sizeof(real) == 4 ? 4 : 2;
                     const PassTable<real> &P = *reinterpret_cast<const PassTable<real> *>(st->passTables[colour].data());
-                    k_struct_fast<NC, real, FJ, MODE, VV><<<grid, block, 0, s->stream>>>(a, P, q0, rowsPerBlock, nrb, sweep, (real)pAtt);
+                    if (pAtt < 1.0) k_struct_fast<NC, real, FJ, MODE, VV, true><<<grid, block, 0, s->stream>>>(a, P, q0, rowsPerBlock, nrb, sweep, (real)pAtt);
+                    else k_struct_fast<NC, real, FJ, MODE, VV, false><<<grid, block, 0, s->stream>>>(a, P, q0, rowsPerBlock, nrb, sweep, (real)pAtt);
                 }
             });
     } else
