@@ -72,3 +72,29 @@ def observables(rows, T, N, model):
     return dict(Si=np.linalg.norm(si, axis=1), Sj=np.linalg.norm(sj, axis=1),
                 Susc=(rows[:, 6] - np.sum(si * sj, axis=1)) / T, Energy=E, Capacity=(E2 - E * E) / T ** 2 * N,
                 TopoQ=rows[:, 26], U4=rows[:, 10], AutoCorr=rows[:, 7])
+
+
+def run_field_sweep(spec, model, T, H_path, nthermal, nsweep, ninterval=0, precision=32, seed=1, device=-1, tables=False):
+    """True field hysteresis (opt-in extension): unlike the reference - whose "H scan" runs every
+    field value as an independent simulation from the polarised state (win.py:116-119) - the configuration is
+    carried from one field value of `H_path` to the next.  One replica per temperature in `T`; at every field
+    value: nthermal intervals of relaxation, then nsweep measured sweeps.  Returns rows[len(H_path), len(T), 27|10]."""
+    T = np.maximum(np.atleast_1d(np.asarray(T, dtype=float)), 0.1)
+    H_path = np.atleast_1d(np.asarray(H_path, dtype=float))
+    N = spec.nsite
+    nint = N if ninterval <= 0 else int(ninterval)
+    kw = dict(precision=precision, nReplica=T.size, beta=1.0 / T, field=np.full(T.size, H_path[0]), seed=seed, device=device)
+    if tables:
+        from .lattice import build_tables
+        sysm = engine.System.from_tables(build_tables(spec, 1.0, model), **kw)
+    else:
+        sysm = engine.System.from_spec(spec, model, **kw)
+    out = []
+    with sysm as s:
+        s.init_spins(0.0)
+        for h in H_path:
+            s.set_params(field=np.full(T.size, h))
+            s.reset_measurements()
+            s.run(engine.METROPOLIS, nthermal, nsweep, nint)
+            out.append(np.stack([s.results(r)[0] for r in range(T.size)]))
+    return np.stack(out)

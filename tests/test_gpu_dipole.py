@@ -81,4 +81,4 @@ def test_dipole_stencil_fp32_jit_path_runs_and_lowers_symmetry():
             assert np.all(np.isfinite(out[:11]))
         sp = s.get_spins(0)
         assert np.allclose(np.linalg.norm(sp, axis=1), 1.0, atol=2e-5)
-        assert s.results(0)[0][8] < s.results(1)[0][8] * 0.5 / 1.0 * 2.0 or True
+        assert s.results(0)[0][8] * 1.0 < s.results(1)[0][8] * 2.0      # energy (in K) rises with temperature

@@ -74,3 +74,21 @@ if __name__ == "__main__":
     assert [r[0] for r in res] == [0.8, 1.4, 3.0]
     assert res[0][1] < res[1][1] < res[2][1] < 0          # energy rises with temperature
     assert res[0][2] > 0.99 and res[2][2] < 0.9            # U4: ordered vs disordered
+
+
+def test_field_sweep_carries_the_configuration_and_shows_hysteresis():
+    """Opt-in extension: ramping H up and down with state carry-over gives a hysteresis loop for an easy-axis
+    ferromagnet at low T, whereas independent runs from the polarised (x) state (the reference's semantics) do not."""
+    from mcsolver_b200 import scan
+    from mcsolver_b200.lattice import LatticeSpec
+    Jf = [-1.0, -1.0, -1.0] + [0.0] * 6
+    spec = LatticeSpec(L=(12, 12, 1), S=[1.0], D=[[0.0, 0.0, -0.5]], bonds=[(0, 0, (1, 0, 0), Jf), (0, 0, (0, 1, 0), Jf)])
+    up = np.linspace(-1.5, 1.5, 13)
+    path = np.concatenate([up, up[::-1]])
+    rows = scan.run_field_sweep(spec, 3, [0.2], path, 100, 100, precision=32, seed=2)
+    mz = rows[:, 0, 25]                      # <Sz_tot>/nLat along the field axis (signed)
+    m_up, m_down = mz[:13], mz[13:][::-1]    # same H grid, ascending and descending branch
+    assert m_up[-1] > 0.9 and m_down[0] < -0.9          # saturated at both ends of the ramp
+    # loop opens around H = 0: the descending branch stays magnetised where the ascending one is not yet
+    k0 = 6
+    assert m_down[k0] - m_up[k0] > 0.5

@@ -63,8 +63,6 @@ def test_ragged_link_counts_and_empty_optional_tables():
         s.run(0, 3, 4, t.N)
         out, g = s.results()
         assert np.all(out[11:20] == 0.0) and g.size == 2                     # no block-spin tables -> zeros; nG=0
-        oo, _ = o.observe(s.get_spins())
-        assert abs(out[8] - oo[8]) > 0 or True
     with eng.System.from_spec(spec, 3, precision=64, beta=[1 / 1.1], seed=8) as s2:
         s2.set_spins(sp)
         assert abs(s2.energy() - o.total_energy(sp)) < 1e-12 * abs(o.total_energy(sp))
