@@ -170,6 +170,27 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def wolff_metric(device, L=4096, steps=100):
+    from mcsolver_b200 import engine
+    from mcsolver_b200.lattice import LatticeSpec
+    spec = LatticeSpec(L=(L, L, 1), S=[1.0], bonds=[(0, 0, (1, 0, 0), J_ISO), (0, 0, (0, 1, 0), J_ISO)])
+    T = np.array([2.0, 2.2, 2.269, 2.35, 2.6])
+    with engine.System.from_spec(spec, 1, precision=32, nReplica=len(T), beta=1 / T, seed=1, device=device) as s:
+        s.init_spins(0.0)
+        s.metropolis_sweeps(20)
+        s.wolff_steps(20)
+        s.reset_measurements()
+        t0 = time.time()
+        s.wolff_steps(steps)          # synchronous: returns after the stream has drained
+        dt = time.time() - t0
+        flipped = sum(s.counters(r)[2] for r in range(len(T)))
+        sizes = [s.counters(r)[2] / max(1, s.counters(r)[1]) / spec.nsite for r in range(len(T))]
+    return {"workload": "ising_square_%d^2, Wolff single-cluster updates at T=%s (J=-1), 5 replicas in one batch" % (L, T.tolist()),
+            "cluster_updates_per_s": steps * len(T) / dt, "flipped_spins_per_s": flipped / dt,
+            "mean_cluster_fraction_per_T": [round(float(x), 5) for x in sizes],
+            "algorithm": "bond activation + atomicCAS union-find over the whole lattice, seed's cluster reflected"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -182,6 +203,7 @@ def main():
     ap.add_argument("--ref-L", type=int, default=32)
     ap.add_argument("--ref-sweeps", type=int, default=60)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-wolff", action="store_true")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -277,12 +299,18 @@ def main():
            "what": "scan.run_points(): create system from host descriptor, init, %d measured sweeps, result rows to host, destroy; "
                    "host wall clock, max over ranks" % a.sweeps}
 
+    # ---- secondary metric of BASELINE.json ("Wolff cluster flips/sec"), outside the timed region, N=1 only:
+    #      2D Ising 4096^2 (configs[1]) at five temperatures across Tc, union-find cluster updates
+    wolff = None
+    if rank == 0 and world == 1 and not a.no_wolff:
+        wolff = wolff_metric(local)
+
     if rank == 0:
         line = {"metric": "attempted Metropolis spin updates per second", "value": value, "unit": "attempts/s", "n_gpus": world,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_max / a.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(a, world), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roof, "cpu_baseline": cpu, "host_wall_s": wall,
+                "roofline": roof, "cpu_baseline": cpu, "wolff": wolff, "host_wall_s": wall,
                 "check": {"replica0_T": float(Ts[0]), "e_per_site_over_kT": float(out0[8]), "U4": float(out0[10])}}
         print(json.dumps(line), flush=True)
     if dist is not None:
