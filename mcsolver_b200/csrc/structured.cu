@@ -442,6 +442,12 @@ __global__ void __launch_bounds__(256) k_struct_init(StructArgs a, double flunc)
     double S = a.classes[q].S;   // signed S of the orbital
     double aS = fabs(S);
     if (NC == 1) { sp[p] = (real)S; return; }
+    if (flunc == 0.0) {   // the reference's default start (win.py never passes flunc): polarised along x, no RNG needed
+        sp[p] = (real)S;
+        sp[(size_t)a.N + p] = real(0);
+        if (NC == 3) sp[2 * (size_t)a.N + p] = real(0);
+        return;
+    }
     uint32_t w[4];
     rng4(a.key, a.replica0 + r, STREAM_INIT, 0, 0, (uint32_t)struct_site_id(a, p), w);
     double n[3];
