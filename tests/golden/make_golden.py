@@ -208,8 +208,36 @@ def make_dipole():
     print("dipole:", len(out), "cases")
 
 
+U4_T = [1.30, 1.36, 1.42, 1.48, 1.54, 1.60]
+U4_SIZES = [6, 10]
+U4_SWEEPS = (2000, 8000)
+U4_K = 6
+
+
+def _u4_job(job):
+    L, T, seed = job
+    t = build_tables(spec_of("cubic", (L, L, L)), T, 3)
+    res = rh.run_ref_engine(3, t.on_args(0, U4_SWEEPS[0], U4_SWEEPS[1], t.N, 0.0, 0.0, 0), seed=seed)
+    return L, T, seed, res[10], res[8] * T
+
+
+def make_u4cross():
+    """Tc from the U4 crossing (north_star): the reference's 3D Heisenberg runs at two sizes over a T grid,
+    K seeds each.  U4 here is the reference's <M^2>^2/<M^4> (heisenbergLib.c:833)."""
+    import multiprocessing as mp
+    jobs = [(L, T, k) for L in U4_SIZES for T in U4_T for k in range(1, U4_K + 1)]
+    t0 = time.time()
+    with mp.get_context("fork").Pool(processes=min(8, os.cpu_count() or 1)) as pool:
+        res = pool.map(_u4_job, jobs, chunksize=1)
+    out = dict(T=U4_T, sizes=U4_SIZES, nthermal=U4_SWEEPS[0], nsweep=U4_SWEEPS[1], K=U4_K,
+               U4={str(L): [[r[3] for r in res if r[0] == L and r[1] == T] for T in U4_T] for L in U4_SIZES},
+               E={str(L): [[r[4] for r in res if r[0] == L and r[1] == T] for T in U4_T] for L in U4_SIZES})
+    json.dump(out, open(os.path.join(HERE, "u4cross.json"), "w"))
+    print("u4cross: %d runs in %.0fs" % (len(jobs), time.time() - t0))
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["tables", "kat", "runs", "stats", "dipole"]
     assert rh.have_reference_host() and rh.have_ref_engine(), "needs /root/reference and oracle/_ref (make -f oracle/Makefile)"
     for w in what:
-        {"tables": make_tables, "kat": make_kat, "runs": make_runs, "stats": make_stats, "dipole": make_dipole}[w]()
+        {"tables": make_tables, "kat": make_kat, "runs": make_runs, "stats": make_stats, "dipole": make_dipole, "u4cross": make_u4cross}[w]()

@@ -80,3 +80,51 @@ def test_parallel_tempering_matches_independent_scan():
         mu, sd = ref[:, :, k].mean(axis=0), ref[:, :, k].std(axis=0, ddof=1)
         tol = 4.0 * sd * np.sqrt(1 + 1 / 6.0) + 1e-3 * np.abs(mu) + 1e-6
         assert np.all(np.abs(rows[:, k] - mu) <= tol), (k, rows[:, k], mu, sd)
+
+
+def _u4_crossing(T, U_small, U_large):
+    """Temperature where the U4 curves of two sizes cross (linear interpolation of their difference)."""
+    d = np.asarray(U_large) - np.asarray(U_small)
+    for i in range(len(T) - 1):
+        if d[i] > 0 >= d[i + 1]:
+            return T[i] + (T[i + 1] - T[i]) * d[i] / (d[i] - d[i + 1])
+    return np.nan
+
+
+def _crossing_with_error(T, U, sizes, rng):
+    """U[str(L)][iT] = list of K per-seed U4 values.  Returns (Tc of the means, bootstrap sigma)."""
+    a, b = (np.array(U[str(L)]) for L in sizes)          # [nT, K]
+    tc = _u4_crossing(T, a.mean(axis=1), b.mean(axis=1))
+    boots = []
+    K = a.shape[1]
+    for _ in range(400):
+        ia, ib = rng.randint(0, K, size=a.shape), rng.randint(0, K, size=b.shape)
+        t = _u4_crossing(T, np.take_along_axis(a, ia, 1).mean(axis=1), np.take_along_axis(b, ib, 1).mean(axis=1))
+        if np.isfinite(t):
+            boots.append(t)
+    return tc, np.std(boots)
+
+
+def test_tc_from_u4_crossing_matches_reference():
+    """north_star: 'Tc from the U4 crossing must agree with the reference's own CPU run within 3 sigma'.
+    3D Heisenberg sc, L = 6 and 10, same T grid / sweep counts / number of seeds as the reference fixture
+    (tests/golden/u4cross.json, produced by the reference's compiled engine)."""
+    from mcsolver_b200 import scan
+    ref = util.load_json("u4cross.json")
+    T, sizes, K = ref["T"], ref["sizes"], ref["K"]
+    rng = np.random.RandomState(7)
+    tc_ref, sd_ref = _crossing_with_error(T, ref["U4"], sizes, rng)
+    assert 1.35 < tc_ref < 1.55, tc_ref                   # literature: Tc = 1.443 |J| (finite-size shifted)
+    gpu = {}
+    for L in sizes:
+        spec = spec_of("cubic", (L, L, L))
+        Tg = np.repeat(T, K)
+        _, rows, _ = scan.run_points(spec, 3, Tg, np.zeros_like(Tg), ref["nthermal"], ref["nsweep"], precision=32, seed=99)
+        gpu[str(L)] = rows[:, 10].reshape(len(T), K).tolist()
+        # the U4 curves themselves agree point by point (3 sigma of the combined standard error, + fp32 slack)
+        r = np.array(ref["U4"][str(L)])
+        g = np.array(gpu[str(L)])
+        se = np.sqrt(r.var(axis=1, ddof=1) / K + g.var(axis=1, ddof=1) / K)
+        assert np.all(np.abs(r.mean(axis=1) - g.mean(axis=1)) <= 3.5 * se + 2e-3), (L, r.mean(axis=1), g.mean(axis=1), se)
+    tc_gpu, sd_gpu = _crossing_with_error(T, gpu, sizes, rng)
+    assert abs(tc_gpu - tc_ref) <= 3.0 * np.hypot(sd_gpu, sd_ref) + 1e-3, (tc_gpu, sd_gpu, tc_ref, sd_ref)
