@@ -233,7 +233,9 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                 bool acc;
                 if (NC == 1) {
                     const real corr = real(2) * (beta * sx * hx - hf * sx);                     // isingLib.c:242
-                    acc = att & ((corr >= real(0)) | (r_exp<real>(corr) > u01<real>(w[2])));   // no short-circuit: branch-free
+                    // isingLib.c:244-252 accepts if corr >= 0 or exp(corr) > u; since u < 1 <= exp(corr) for corr >= 0 the
+                    // second test alone decides identically
+                    acc = att & (r_exp<real>(corr) > u01<real>(w[2]));
                     sx = acc ? -sx : sx;
                 } else {
                     real n[3];
@@ -248,7 +250,8 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                         dE += dOn;
                     }
                     dE = beta * dE - hf * (NC == 3 ? tz : tx);
-                    acc = att & ((dE <= real(0)) | (r_exp<real>(-dE) > u01<real>(w[2])));       // heisenbergLib.c:461, branch-free
+                    // heisenbergLib.c:461 accepts if dE <= 0 or exp(-dE) > u; u < 1 <= exp(-dE) for dE <= 0, so one test decides
+                    acc = att & (r_exp<real>(-dE) > u01<real>(w[2]));
                     sx = acc ? nx : sx; sy = acc ? ny : sy; sz = acc ? nz : sz;
                     if (renorm) {   // every site, accepted or not
                         const real f = S * r_rsqrt<real>(sx * sx + sy * sy + sz * sz);
