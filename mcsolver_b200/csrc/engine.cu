@@ -228,6 +228,14 @@ static mcg_system *create_from_tables(const mcg_tables *t, const mcg_config *cfg
         cls[p] = (uint16_t)ic->second;
     }
     s->nJ = (int)jmap.size(); s->ncls = (int)cmap.size();
+    s->isoNoOnsite = true;
+    for (double dv : clsD) if (dv != 0.0) s->isoNoOnsite = false;
+    for (size_t j = 0; j + JW <= Jtab.size() && t->model != 1; j += JW) {
+        const double *Jv = Jtab.data() + j;
+        bool iso = Jv[0] == Jv[1] && (t->model == 2 || Jv[1] == Jv[2]);
+        for (int c = 3; c < 9; c++) if (Jv[c] != 0.0 && (t->model == 3 || c == 3 || c == 6)) iso = false;
+        if (!iso) s->isoNoOnsite = false;
+    }
     s->S_host.assign(t->S, t->S + N);
     std::vector<double> signS(N);
     for (int p = 0; p < N; p++) signS[p] = t->S[s->site_of[p]];
@@ -308,6 +316,7 @@ static mcg_system *create_from_tables(const mcg_tables *t, const mcg_config *cfg
 static dim3 grid_for(int n, int R) { return dim3((unsigned)((n + 255) / 256), (unsigned)R, 1); }
 
 static void init_spins(mcg_system *s, double flunc) {
+    s->wolffPrimed = false;
     if (s->structured) { structured_init_spins(s, flunc); return; }
     GenArgs a = gen_args(s);
     dispatch(s, [&]<int NC, typename real, bool FJ>() {
@@ -317,6 +326,7 @@ static void init_spins(mcg_system *s, double flunc) {
 }
 
 static void set_spins(mcg_system *s, int r, const double *spins) {
+    s->wolffPrimed = false;
     MCG_REQUIRE(r >= 0 && r < s->R && spins, "bad replica index or NULL spins");
     if (s->structured) { structured_set_spins(s, r, spins); return; }
     size_t n = (size_t)s->N * (s->NC == 1 ? 1 : 3);
@@ -410,6 +420,7 @@ static void energy(mcg_system *s, int r, double *Etot, double *eb, double *eo) {
 static void metropolis_sweeps(mcg_system *s, int64_t n, double pAtt) {
     MCG_REQUIRE(n >= 0, "negative sweep count");
     MCG_REQUIRE(pAtt > 0.0 && pAtt <= 1.0, "pAttempt must be in (0,1]");
+    s->wolffPrimed = false;
     if (s->structured) { structured_sweeps(s, n, pAtt, false); return; }
     GenArgs a = gen_args(s);
     for (int64_t it = 0; it < n; it++) {
@@ -431,25 +442,34 @@ static void metropolis_sweeps(mcg_system *s, int64_t n, double pAtt) {
 
 static void wolff_steps(mcg_system *s, int64_t n) {
     MCG_REQUIRE(n >= 0, "negative step count");
+    const size_t RN = (size_t)s->R * s->N;
     if (!s->d_parent) {
-        s->d_parent = dalloc<int32_t>((size_t)s->R * s->N);
-        MCG_CUDA(cudaMalloc(&s->d_proj, (size_t)s->R * s->N * s->real_size()));
+        s->d_parent = dalloc<int32_t>(2 * RN);
+        MCG_CUDA(cudaMalloc(&s->d_proj, 2 * RN * s->real_size()));
         s->d_wres = dalloc<double>(2 * (size_t)s->R);
+        s->wolffPrimed = false;
     }
+    // residual energy of a reflection vanishes identically for isotropic exchange without D and field
+    bool anyField = false;
+    for (double h : s->field_host) anyField = anyField || h != 0.0;
+    const bool needResidual = anyField || (s->model != MCG_ISING && !s->isoNoOnsite);
     WolffArgs w;
-    w.parent = s->d_parent; w.proj = s->d_proj; w.wres = s->d_wres; w.N = s->N; w.R = s->R; w.spin = s->d_spin;
+    w.wres = s->d_wres; w.N = s->N; w.R = s->R; w.spin = s->d_spin;
     w.beta = s->d_beta; w.field = s->d_field; w.cnt = s->d_cnt; w.key = make_rng_key(s->seed); w.replica0 = s->replica0;
     for (int64_t it = 0; it < n; it++) {
         w.step = s->wolffCtr++;
-        s->launches += 5;
-        if (s->structured) structured_wolff_step(s, w);
+        const int b = (int)(w.step & 1);
+        w.parent = s->d_parent + (size_t)b * RN; w.parentNext = s->d_parent + (size_t)(1 - b) * RN;
+        w.proj = (char *)s->d_proj + (size_t)b * RN * s->real_size(); w.projNext = (char *)s->d_proj + (size_t)(1 - b) * RN * s->real_size();
+        if (s->structured) s->launches += structured_wolff_step(s, w, s->wolffPrimed, needResidual);
         else {
             GenArgs a = gen_args(s);
             dispatch(s, [&]<int NC, typename real, bool FJ>() {
                 TableTopo<NC, real> topo{a, s->d_pos_of};
-                wolff_launch_step<NC, real, FJ>(topo, w, s->stream);
+                s->launches += wolff_launch_step<NC, real, FJ>(topo, w, s->stream, s->wolffPrimed, needResidual);
             });
         }
+        s->wolffPrimed = true;
     }
     MCG_CUDA(cudaGetLastError());
 }
@@ -481,7 +501,7 @@ static void run(mcg_system *s, int algorithm, int64_t nthermal, int64_t nsweep, 
     if (spinFrame > 0) per = std::max<int64_t>(1, nsweep / spinFrame);
     size_t fsz = (size_t)s->N * (s->NC == 1 ? 1 : 3);
     for (int64_t i = 0; i < nsweep; i++) {
-        if (fused) structured_sweeps(s, nsub, pAtt, true);
+        if (fused) { s->wolffPrimed = false; structured_sweeps(s, nsub, pAtt, true); }
         else updates(1);
         if (spinFrame > 0 && i % per == 0 && iFrame < spinFrame) {   // heisenbergLib.c:664-675, capped
             for (int r = 0; r < s->R; r++) capture_frame(s, r, frames + ((size_t)r * spinFrame + iFrame) * fsz);
@@ -653,6 +673,7 @@ MCG_API int mcg_timed_sweeps(mcg_system *sys, int64_t nsweeps, double pAttempt, 
         else
             for (int64_t i = 0; i < nsweeps; i++) {
                 if (sys->structured) {
+                    sys->wolffPrimed = false;
                     structured_sweeps(sys, 1, pAttempt, true);
                     sys->launches++;
                     k_finalize_sweep<<<(sys->R + 63) / 64, 64, 0, sys->stream>>>(sys->model, sys->R, sys->N, sys->nLat, sys->d_sums, sys->d_acc, sys->d_slot, sys->d_last);

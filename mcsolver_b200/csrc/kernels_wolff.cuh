@@ -23,8 +23,10 @@
 namespace mcg {
 
 struct WolffArgs {
-    int32_t *parent;      // [R][N]
-    void *proj;           // [R][N] real: a_p = -(s_p . n)
+    int32_t *parent;      // [R][N] union-find forest of THIS step (identity on entry)
+    int32_t *parentNext;  // [R][N] the other buffer: reset to identity by this step's flip kernel
+    void *proj;           // [R][N] real: a_p = -(s_p . n) for this step's plane normal
+    void *projNext;       // [R][N] real: the same for the next step, written by this step's flip kernel
     double *wres;         // [R][2]: residual energy, cluster size
     uint64_t step;
     int N, R;
@@ -115,6 +117,7 @@ template <int NC, typename real, bool FULLJ, typename TOPO>
 __global__ void __launch_bounds__(256) k_wolff_bonds(TOPO topo, WolffArgs w) {
     int r = blockIdx.y;
     int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p == 0) { w.wres[2 * r] = 0.0; w.wres[2 * r + 1] = 0.0; }
     if (p >= w.N) return;
     const real *sp = (const real *)w.spin + (size_t)r * NC * w.N;
     const real *proj = (const real *)w.proj + (size_t)r * w.N;
@@ -205,50 +208,85 @@ __global__ void __launch_bounds__(256) k_wolff_residual(TOPO topo, WolffArgs w) 
     block_accumulate<2>(v, w.wres + 2 * r, smem);
 }
 
-template <int NC, typename real, typename TOPO>
+// Reflect the seed's cluster and prepare the next step in the same pass: the OTHER parent buffer is reset to the
+// identity and the projections on the next step's plane normal are written, so a step costs two passes over the
+// lattice (bonds, flip) when no residual energy has to be reduced first.
+//   FLAT = true : parent[] was flattened (residual mode), membership is parent[p] == parent[seed];
+//   FLAT = false: membership by find() on the unflattened forest; the cluster is always accepted (residual == 0).
+template <int NC, typename real, bool FLAT, typename TOPO>
 __global__ void __launch_bounds__(256) k_wolff_flip(TOPO topo, WolffArgs w) {
     int r = blockIdx.y;
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= w.N) return;
     real n[3], uAcc; int seed;
     wolff_seed<NC, real>(w, r, n, seed, uAcc);
-    const int32_t *parent = w.parent + (size_t)r * w.N;
-    int seedPos = topo.pos_of_site(seed);
-    int root = parent[seedPos];
-    double res = w.wres[2 * r];
-    bool accept = res <= 0.0 || r_exp<real>((real)-res) > uAcc;     // heisenbergLib.c:423 / isingLib.c:225
+    int32_t *parent = w.parent + (size_t)r * w.N;
+    const int seedPos = topo.pos_of_site(seed);
+    bool accept = true, inCluster = false;
+    if (p < w.N) {
+        if (FLAT) {
+            double res = w.wres[2 * r];
+            accept = res <= 0.0 || r_exp<real>((real)-res) > uAcc;     // heisenbergLib.c:423 / isingLib.c:225
+            inCluster = parent[p] == parent[seedPos];
+        } else {
+            inCluster = uf_find(parent, p) == uf_find(parent, seedPos);
+        }
+    }
+    if (!FLAT) {   // cluster size by block counts (the residual kernel counts it in the other mode)
+        int nIn = __syncthreads_count(inCluster ? 1 : 0);
+        if (threadIdx.x == 0 && nIn) atomicAdd(w.cnt + (size_t)r * NCNT + CNT_CLUSTER, (unsigned long long)nIn);
+    }
+    if (p >= w.N) return;
     if (p == seedPos) {
         atomicAdd(w.cnt + (size_t)r * NCNT + CNT_WSTEPS, 1ull);
+        atomicAdd(w.cnt + (size_t)r * NCNT + CNT_ATTEMPT, 1ull);
         if (accept) {
             atomicAdd(w.cnt + (size_t)r * NCNT + CNT_ACCEPT, 1ull);
-            atomicAdd(w.cnt + (size_t)r * NCNT + CNT_CLUSTER, (unsigned long long)(w.wres[2 * r + 1] + 0.5));
+            if (FLAT) atomicAdd(w.cnt + (size_t)r * NCNT + CNT_CLUSTER, (unsigned long long)(w.wres[2 * r + 1] + 0.5));
         }
-        atomicAdd(w.cnt + (size_t)r * NCNT + CNT_ATTEMPT, 1ull);
     }
-    if (!accept || parent[p] != root) return;
     real *sp = (real *)w.spin + (size_t)r * NC * w.N;
-    if (NC == 1) { sp[p] = -sp[p]; return; }
-    real ap = ((const real *)w.proj)[(size_t)r * w.N + p];
     real s[3];
     load_spin<NC, real>(sp, w.N, p, s);
-    s[0] += real(2) * ap * n[0]; s[1] += real(2) * ap * n[1]; s[2] += real(2) * ap * n[2];   // heisenbergLib.c:425-426
-    if (sizeof(real) == 4) {
-        real S = topo.S(topo.begin(p));
-        real f = S * r_rsqrt<real>(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]);
-        s[0] *= f; s[1] *= f; s[2] *= f;
+    if (accept && inCluster) {
+        if (NC == 1) s[0] = -s[0];
+        else {
+            real ap = ((const real *)w.proj)[(size_t)r * w.N + p];
+            s[0] += real(2) * ap * n[0]; s[1] += real(2) * ap * n[1]; s[2] += real(2) * ap * n[2];   // heisenbergLib.c:425-426
+            if (sizeof(real) == 4) {
+                real S = topo.S(topo.begin(p));
+                real f = S * r_rsqrt<real>(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]);
+                s[0] *= f; s[1] *= f; s[2] *= f;
+            }
+        }
+        store_spin<NC, real>(sp, w.N, p, s);
     }
-    store_spin<NC, real>(sp, w.N, p, s);
+    // next step: fresh forest in the other buffer, projections on the next plane normal
+    w.parentNext[(size_t)r * w.N + p] = p;
+    if (NC > 1) {
+        WolffArgs wn = w;
+        wn.step = w.step + 1;
+        real n2[3], u2; int seed2;
+        wolff_seed<NC, real>(wn, r, n2, seed2, u2);
+        ((real *)w.projNext)[(size_t)r * w.N + p] = -(s[0] * n2[0] + s[1] * n2[1] + s[2] * n2[2]);
+    }
 }
 
-// launch sequence of one cluster update, shared by both paths
+// launch sequence of one cluster update, shared by both paths.  primed: the forest/projection buffers of this
+// step were prepared by the previous step's flip kernel; needResidual: anisotropic exchange, D or field present.
 template <int NC, typename real, bool FJ, typename TOPO>
-static void wolff_launch_step(const TOPO &topo, const WolffArgs &w, cudaStream_t stream) {
+static int wolff_launch_step(const TOPO &topo, const WolffArgs &w, cudaStream_t stream, bool primed, bool needResidual) {
     dim3 g((unsigned)((w.N + 255) / 256), (unsigned)w.R);
-    k_wolff_init<NC, real, TOPO><<<g, 256, 0, stream>>>(topo, w);
+    int launches = 0;
+    if (!primed) { k_wolff_init<NC, real, TOPO><<<g, 256, 0, stream>>>(topo, w); launches++; }
     k_wolff_bonds<NC, real, FJ, TOPO><<<g, 256, 0, stream>>>(topo, w);
-    k_wolff_flatten<<<g, 256, 0, stream>>>(w.N, w.parent);
-    k_wolff_residual<NC, real, FJ, TOPO><<<g, 256, 0, stream>>>(topo, w);
-    k_wolff_flip<NC, real, TOPO><<<g, 256, 0, stream>>>(topo, w);
+    if (needResidual) {
+        k_wolff_flatten<<<g, 256, 0, stream>>>(w.N, w.parent);
+        k_wolff_residual<NC, real, FJ, TOPO><<<g, 256, 0, stream>>>(topo, w);
+        k_wolff_flip<NC, real, true, TOPO><<<g, 256, 0, stream>>>(topo, w);
+        return launches + 4;
+    }
+    k_wolff_flip<NC, real, false, TOPO><<<g, 256, 0, stream>>>(topo, w);
+    return launches + 2;
 }
 
 }  // namespace mcg

@@ -816,6 +816,15 @@ static void structured_build_host(mcg_system *s, const mcg_lattice_desc *d, std:
         }
     }
     s->fullJ = full;
+    s->isoNoOnsite = true;
+    for (int o = 0; o < no; o++) {
+        for (int k = 0; k < 3 && d->D && d->model != 1; k++) if (d->D[3 * o + k] != 0.0) s->isoNoOnsite = false;
+        for (auto &t : tm[o]) {
+            bool iso = d->model == 1 || (t.J[0] == t.J[1] && (d->model == 2 || t.J[1] == t.J[2]));
+            for (int k = 3; k < 9 && d->model != 1; k++) if (t.J[k] != 0.0 && (d->model == 3 || k == 3 || k == 6)) iso = false;
+            if (!iso) s->isoNoOnsite = false;
+        }
+    }
 
     // ---- colouring period search ----
     auto candidates = [&](int Ld) {
@@ -1178,12 +1187,14 @@ static void fold_and_extras(mcg_system *s) {
     MCG_CUDA(cudaGetLastError());
 }
 
-void structured_wolff_step(mcg_system *s, const WolffArgs &w) {
+int structured_wolff_step(mcg_system *s, const WolffArgs &w, bool primed, bool needResidual) {
     StructArgs a = struct_args(s);
+    int launches = 0;
     sdispatch(s, [&]<int NC, typename real, bool FJ>() {
         StructTopo<NC, real> topo{a};
-        wolff_launch_step<NC, real, FJ>(topo, w, s->stream);
+        launches = wolff_launch_step<NC, real, FJ>(topo, w, s->stream, primed, needResidual);
     });
+    return launches;
 }
 
 void structured_measure_sums(mcg_system *s) {

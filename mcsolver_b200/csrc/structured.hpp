@@ -13,6 +13,6 @@ void structured_measure_sums(mcg_system *s);
 void structured_sweeps(mcg_system *s, int64_t n, double pAtt, bool fusedMeasure);
 void structured_colour_order(const mcg_system *s, int32_t *order);
 struct WolffArgs;
-void structured_wolff_step(mcg_system *s, const WolffArgs &w);
+int structured_wolff_step(mcg_system *s, const WolffArgs &w, bool primed, bool needResidual);   // returns kernels launched
 int structured_jit_check(const mcg_lattice_desc *d, int precision, std::string &report);
 }  // namespace mcg

@@ -72,8 +72,10 @@ struct mcg_system {
     double rg_ci = 0, rg_cj = 0, rg_cij = 0;
     uint64_t measCtr = 0;
     // wolff
-    int32_t *d_parent = nullptr;         // [R][N]
-    void *d_proj = nullptr;              // [R][N] real
+    int32_t *d_parent = nullptr;         // [2][R][N] double-buffered union-find forest
+    void *d_proj = nullptr;              // [2][R][N] real
+    bool wolffPrimed = false;            // buffers of the next step were prepared by the previous step's flip kernel
+    bool isoNoOnsite = false;            // every J is a multiple of the identity and every D is 0 (no exchange-anisotropy residual)
     double *d_wres = nullptr;            // [R][2] residual, cluster size
     std::vector<double> beta_host, field_host;
     cudaStream_t stream = nullptr;
