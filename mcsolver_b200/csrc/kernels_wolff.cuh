@@ -53,6 +53,20 @@ __device__ __forceinline__ void wolff_seed(const WolffArgs &w, int r, real (&n)[
     else random_dir<NC, real>(ww[0], ww[1], n);
 }
 
+// seed site, plane normal and acceptance uniform are the same for every thread of a replica: one thread per
+// block draws them (one Philox call instead of one per thread) and shares them through shared memory
+template <int NC, typename real> struct SeedShared { real n[3]; real uAcc; int seed; };
+template <int NC, typename real>
+__device__ __forceinline__ void wolff_seed_block(const WolffArgs &w, int r, SeedShared<NC, real> &sh, real (&n)[3], int &seedSite, real &uAcc) {
+    if (threadIdx.x == 0) {
+        real nn[3], u; int sd;
+        wolff_seed<NC, real>(w, r, nn, sd, u);
+        sh.n[0] = nn[0]; sh.n[1] = nn[1]; sh.n[2] = nn[2]; sh.uAcc = u; sh.seed = sd;
+    }
+    __syncthreads();
+    n[0] = sh.n[0]; n[1] = sh.n[1]; n[2] = sh.n[2]; uAcc = sh.uAcc; seedSite = sh.seed;
+}
+
 __device__ __forceinline__ int uf_find(int32_t *parent, int x) {
     for (;;) {
         int p = parent[x];
@@ -89,6 +103,11 @@ template <int NC, typename real> struct TableTopo {
         J = (const real *)a.Jtab + (size_t)a.jtype[(size_t)k * a.N + c.p] * (NC == 1 ? 1 : 9);
         return true;
     }
+    // bond ownership: the endpoint with the lower reference id activates the bond; returns the neighbour's id
+    __device__ __forceinline__ bool owns(const Ctx &c, int k, int q, int ip, int &iq) const {
+        iq = a.site_of[q];
+        return iq >= ip;
+    }
     __device__ __forceinline__ real S(const Ctx &c) const { return ((const real *)a.clsS)[a.cls[c.p]]; }
     __device__ __forceinline__ void D(const Ctx &c, real (&d)[3]) const {
         const real *D = (const real *)a.clsD + 3 * a.cls[c.p];
@@ -100,12 +119,13 @@ template <int NC, typename real, typename TOPO>
 __global__ void __launch_bounds__(256) k_wolff_init(TOPO topo, WolffArgs w) {
     int r = blockIdx.y;
     int p = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ SeedShared<NC, real> sh;
+    real n[3], u; int seed;
+    wolff_seed_block<NC, real>(w, r, sh, n, seed, u);
     if (p == 0) { w.wres[2 * r] = 0.0; w.wres[2 * r + 1] = 0.0; }
     if (p >= w.N) return;
     w.parent[(size_t)r * w.N + p] = p;
     if (NC > 1) {
-        real n[3], u; int seed;
-        wolff_seed<NC, real>(w, r, n, seed, u);
         const real *sp = (const real *)w.spin + (size_t)r * NC * w.N;
         real s[3];
         load_spin<NC, real>(sp, w.N, p, s);
@@ -117,14 +137,15 @@ template <int NC, typename real, bool FULLJ, typename TOPO>
 __global__ void __launch_bounds__(256) k_wolff_bonds(TOPO topo, WolffArgs w) {
     int r = blockIdx.y;
     int p = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ SeedShared<NC, real> sh;
+    real n[3], uAcc; int seed;
+    wolff_seed_block<NC, real>(w, r, sh, n, seed, uAcc);
     if (p == 0) { w.wres[2 * r] = 0.0; w.wres[2 * r + 1] = 0.0; }
     if (p >= w.N) return;
     const real *sp = (const real *)w.spin + (size_t)r * NC * w.N;
     const real *proj = (const real *)w.proj + (size_t)r * w.N;
     int32_t *parent = w.parent + (size_t)r * w.N;
     real beta = (real)w.beta[r];
-    real n[3], uAcc; int seed;
-    wolff_seed<NC, real>(w, r, n, seed, uAcc);
     auto c = topo.begin(p);
     const int ip = topo.site_id(c);
     real ap = NC == 1 ? sp[p] : proj[p];
@@ -132,14 +153,14 @@ __global__ void __launch_bounds__(256) k_wolff_bonds(TOPO topo, WolffArgs w) {
     for (int k = 0; k < nl; k++) {
         int q; const real *J;
         if (!topo.link(c, k, q, J)) continue;
-        const int iq = topo.site_id_of(q);
-        if (iq < ip) continue;                        // bond owned by the lower reference id
+        int iq;
+        if (!topo.owns(c, k, q, ip, iq)) continue;    // every bond is activated by exactly one of its endpoints
         real corr;
         if (NC == 1) corr = real(2) * beta * J[0] * ap * sp[q];                       // isingLib.c:183-185
         else corr = real(2) * ap * proj[q] * beta * quad_form<NC, real, FULLJ>(J, n, n);   // heisenbergLib.c:355
         if (corr < real(0)) {
             uint32_t wd[4];
-            rng_bond(w.key, w.replica0 + r, w.step, (uint32_t)ip, (uint32_t)iq, wd);
+            rng_bond(w.key, w.replica0 + r, w.step, (uint32_t)min(ip, iq), (uint32_t)max(ip, iq), wd);
             if ((real(1) - r_exp<real>(corr)) > u01<real>(wd[0])) uf_unite(parent, p, q);
         }
     }
@@ -162,8 +183,9 @@ __global__ void __launch_bounds__(256) k_wolff_residual(TOPO topo, WolffArgs w) 
     int r = blockIdx.y;
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     double v[2] = {0.0, 0.0};
+    __shared__ SeedShared<NC, real> sh;
     real n[3], uAcc; int seed;
-    wolff_seed<NC, real>(w, r, n, seed, uAcc);
+    wolff_seed_block<NC, real>(w, r, sh, n, seed, uAcc);
     const int32_t *parent = w.parent + (size_t)r * w.N;
     if (p < w.N) {
         int root = parent[topo.pos_of_site(seed)];
@@ -217,10 +239,21 @@ template <int NC, typename real, bool FLAT, typename TOPO>
 __global__ void __launch_bounds__(256) k_wolff_flip(TOPO topo, WolffArgs w) {
     int r = blockIdx.y;
     int p = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ SeedShared<NC, real> sh, shNext;
+    __shared__ int shSeedPos;
     real n[3], uAcc; int seed;
-    wolff_seed<NC, real>(w, r, n, seed, uAcc);
+    wolff_seed_block<NC, real>(w, r, sh, n, seed, uAcc);
+    real n2[3] = {0, 0, 0};
+    if (NC > 1) {
+        WolffArgs wn = w;
+        wn.step = w.step + 1;
+        real u2; int seed2;
+        wolff_seed_block<NC, real>(wn, r, shNext, n2, seed2, u2);
+    }
+    if (threadIdx.x == 0) shSeedPos = topo.pos_of_site(seed);
+    __syncthreads();
     int32_t *parent = w.parent + (size_t)r * w.N;
-    const int seedPos = topo.pos_of_site(seed);
+    const int seedPos = shSeedPos;
     bool accept = true, inCluster = false;
     if (p < w.N) {
         if (FLAT) {
@@ -262,13 +295,7 @@ __global__ void __launch_bounds__(256) k_wolff_flip(TOPO topo, WolffArgs w) {
     }
     // next step: fresh forest in the other buffer, projections on the next plane normal
     w.parentNext[(size_t)r * w.N + p] = p;
-    if (NC > 1) {
-        WolffArgs wn = w;
-        wn.step = w.step + 1;
-        real n2[3], u2; int seed2;
-        wolff_seed<NC, real>(wn, r, n2, seed2, u2);
-        ((real *)w.projNext)[(size_t)r * w.N + p] = -(s[0] * n2[0] + s[1] * n2[1] + s[2] * n2[2]);
-    }
+    if (NC > 1) ((real *)w.projNext)[(size_t)r * w.N + p] = -(s[0] * n2[0] + s[1] * n2[1] + s[2] * n2[2]);
 }
 
 // launch sequence of one cluster update, shared by both paths.  primed: the forest/projection buffers of this

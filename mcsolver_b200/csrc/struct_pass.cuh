@@ -23,6 +23,8 @@ struct SLinkD {
     int cZ;          // coarse Z offset in (-Zd/2, Zd/2]
     int low;         // neighbour class has a lower colour (its spins are final in this sweep)
     int self;        // link to the site itself (supercell dimension 1)
+    int fwd;         // this endpoint is the bond template's source: it activates the bond in the Wolff pass
+    int o2, dx, dy, dz;   // neighbour orbital and cell offset reduced to [0,L): its reference id without decoding
 };
 struct SClassD {
     int a, b, c, o, colour, nlink, lowmode, pad;

@@ -80,17 +80,33 @@ __device__ __forceinline__ int struct_site_id(const StructArgs &a, int p) {
 // ---- topology of the structured path for the Wolff kernels (kernels_wolff.cuh) ----
 template <int NC, typename real> struct StructTopo {
     StructArgs a;
-    struct Ctx { int p, q, X, Y, Z; };
+    int sZ, sY, sC;      // log2 of Zd, Yd, ncellc when they are powers of two (else -1): p decodes with shifts
+    struct Ctx { int p, q, X, Y, Z, x, y, z; };
     __device__ __forceinline__ Ctx begin(int p) const {
         Ctx c;
-        c.p = p; c.q = p / a.ncellc;
-        int cell = p - c.q * a.ncellc;
-        c.Z = cell % a.Zd; c.Y = (cell / a.Zd) % a.Yd; c.X = cell / (a.Zd * a.Yd);
+        c.p = p;
+        int cell;
+        if (sC >= 0) { c.q = p >> sC; cell = p & (a.ncellc - 1); } else { c.q = p / a.ncellc; cell = p - c.q * a.ncellc; }
+        int t;
+        if (sZ >= 0) { c.Z = cell & (a.Zd - 1); t = cell >> sZ; } else { t = cell / a.Zd; c.Z = cell - t * a.Zd; }
+        if (sY >= 0) { c.Y = t & (a.Yd - 1); c.X = t >> sY; } else { c.X = t / a.Yd; c.Y = t - c.X * a.Yd; }
+        const SClassD &cl = a.classes[c.q];
+        c.x = c.X * a.px + cl.a; c.y = c.Y * a.py + cl.b; c.z = c.Z * a.pz + cl.c;
         return c;
     }
     __device__ __forceinline__ int site_id(const Ctx &c) const {
-        const SClassD &cl = a.classes[c.q];
-        return (((c.X * a.px + cl.a) * a.Ly + (c.Y * a.py + cl.b)) * a.Lz + (c.Z * a.pz + cl.c)) * a.norb + cl.o;
+        return ((c.x * a.Ly + c.y) * a.Lz + c.z) * a.norb + a.classes[c.q].o;
+    }
+    // the bond template's source endpoint activates the bond; the neighbour's reference id follows from the
+    // link's cell offset without decoding its storage position
+    __device__ __forceinline__ bool owns(const Ctx &c, int k, int q, int ip, int &iq) const {
+        const SLinkD &L = a.links[c.q * MAXLINK + k];
+        if (!L.fwd) return false;
+        int xn = c.x + L.dx; if (xn >= a.Lx) xn -= a.Lx;
+        int yn = c.y + L.dy; if (yn >= a.Ly) yn -= a.Ly;
+        int zn = c.z + L.dz; if (zn >= a.Lz) zn -= a.Lz;
+        iq = ((xn * a.Ly + yn) * a.Lz + zn) * a.norb + L.o2;
+        return true;
     }
     __device__ __forceinline__ int site_id_of(int q) const { return struct_site_id(a, q); }
     __device__ __forceinline__ int pos_of_site(int id) const {
@@ -737,6 +753,7 @@ struct Tmpl {
     int d[3];       // internal axes, reduced mod L into (-L/2, L/2]
     double J[9];
     bool self;
+    bool fwd;       // created from the bond's source side
 };
 
 static int mod(int a, int m) { int r = a % m; return r < 0 ? r + m : r; }
@@ -788,6 +805,7 @@ static void structured_build_host(mcg_system *s, const mcg_lattice_desc *d, std:
         static const int T9[9] = {0, 1, 2, 6, 7, 8, 3, 4, 5};
         for (int k = 0; k < 9; k++) t.J[k] = d->model == 1 ? (k == 0 ? J9[0] : 0.0) : J9[transpose ? T9[k] : k];
         t.self = (o2 == o && t.d[0] == 0 && t.d[1] == 0 && t.d[2] == 0);
+        t.fwd = !transpose;
         if (t.self && transpose) return;   // Lattice.py:261: no back link to oneself
         for (auto &e : tm[o])
             if (e.o2 == t.o2 && e.d[0] == t.d[0] && e.d[1] == t.d[1] && e.d[2] == t.d[2]) {
@@ -886,7 +904,7 @@ static void structured_build_host(mcg_system *s, const mcg_lattice_desc *d, std:
     for (int i = 0; i < bestN; i++) st->colourClassStart[bestColour[i] + 1]++;
     for (int c = 0; c < bestC; c++) st->colourClassStart[c + 1] += st->colourClassStart[c];
     st->classes.resize(bestN);
-    links.assign((size_t)bestN * MAXLINK, SLinkD{0, 0, 0, 0, 0, 0});
+    links.assign((size_t)bestN * MAXLINK, SLinkD{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0});
     st->cXs.assign((size_t)bestN * MAXLINK, 0);
     st->cYs.assign((size_t)bestN * MAXLINK, 0);
     const int JW = d->model == 1 ? 1 : 9;
@@ -913,6 +931,8 @@ static void structured_build_host(mcg_system *s, const mcg_lattice_desc *d, std:
             { int v = mod(cX, st->Xd); if (v > st->Xd / 2) v -= st->Xd; st->cXs[(size_t)q * MAXLINK + k] = v; }
             { int v = mod(cY, st->Yd); if (v > st->Yd / 2) v -= st->Yd; st->cYs[(size_t)q * MAXLINK + k] = v; }
             l.self = t.self ? 1 : 0;
+            l.fwd = t.fwd ? 1 : 0;
+            l.o2 = t.o2; l.dx = mod(t.d[0], L[0]); l.dy = mod(t.d[1], L[1]); l.dz = mod(t.d[2], L[2]);
             l.low = (!t.self && bestColour[nid] < bestColour[id]) ? 1 : 0;
             if (!t.self) { nreal++; nlow += l.low; }
             for (int e = 0; e < JW; e++) Jt[((size_t)q * MAXLINK + k) * JW + e] = t.J[e];
@@ -1191,7 +1211,8 @@ int structured_wolff_step(mcg_system *s, const WolffArgs &w, bool primed, bool n
     StructArgs a = struct_args(s);
     int launches = 0;
     sdispatch(s, [&]<int NC, typename real, bool FJ>() {
-        StructTopo<NC, real> topo{a};
+        auto lg = [](int v) { int sh = 0; while ((1 << sh) < v) sh++; return (1 << sh) == v ? sh : -1; };
+        StructTopo<NC, real> topo{a, lg(a.Zd), lg(a.Yd), lg(a.ncellc)};
         launches = wolff_launch_step<NC, real, FJ>(topo, w, s->stream, primed, needResidual);
     });
     return launches;
