@@ -211,7 +211,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
     if a.impl == "reference":
-        a.steps = min(a.steps, 3)      # each step is a bounded multi-second CPU sample
+        a.steps = min(a.steps, 100)    # each step is a bounded ~1.5 s CPU sample: K steps stay within a few minutes
         run_reference_arm(a, rank, world)
         return
 
