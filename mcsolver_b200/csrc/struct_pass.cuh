@@ -242,16 +242,17 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                 } else {
                     real n[3];
                     random_dir<NC, real>(w[0], w[1], n);
+                    // heisenbergLib.c:451-456: transSpin = s1n * n with s1n = -2 (s.n);  dE = transSpin . H + on-site difference.
+                    // transSpin . H = s1n * (n . H): the proposal vector itself is only formed when the D terms need it.
                     const real s1n = real(-2) * (sx * n[0] + sy * n[1] + (NC == 3 ? sz * n[2] : real(0)));
-                    const real tx = n[0] * s1n, ty = n[1] * s1n, tz = NC == 3 ? n[2] * s1n : real(0);
-                    real dE = tx * hx + ty * hy + (NC == 3 ? tz * hz : real(0));
-                    real nx = sx + tx, ny = sy + ty, nz = sz + tz;
+                    const real nH = n[0] * hx + n[1] * hy + (NC == 3 ? n[2] * hz : real(0));
+                    real nx = sx + s1n * n[0], ny = sy + s1n * n[1], nz = NC == 3 ? sz + s1n * n[2] : real(0);
+                    real dE = s1n * (beta * nH - hf * (NC == 3 ? n[2] : n[0]));
                     if (hasD) {
                         real dOn = D0 * (nx * nx - sx * sx) + D1 * (ny * ny - sy * sy);
                         if (NC == 3) dOn += D2 * (nz * nz - sz * sz);
-                        dE += dOn;
+                        dE += beta * dOn;
                     }
-                    dE = beta * dE - hf * (NC == 3 ? tz : tx);
                     // heisenbergLib.c:461 accepts if dE <= 0 or exp(-dE) > u; u < 1 <= exp(-dE) for dE <= 0, so one test decides
                     acc = att & (r_exp<real>(-dE) > u01<real>(w[2]));
                     sx = acc ? nx : sx; sy = acc ? ny : sy; sz = acc ? nz : sz;
