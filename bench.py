@@ -291,12 +291,15 @@ def main():
     desc_bytes = 8 * (len(spec.S) * 4 + len(spec.bonds) * 14) + 16 * R
     barrier_max(0.0)
     t0 = time.time()
+    e2e_job_s = []
     for _ in range(e2e_steps):
+        tj = time.time()
         idx, rows, _ = scan.run_points(spec, 3, ladder(R * world), np.zeros(R * world), 0, a.sweeps, precision=32, seed=1,
                                        rank=rank, world=world, device=local)
+        e2e_job_s.append(round(time.time() - tj, 4))
     e2e_t = barrier_max(time.time() - t0)
     e2e = {"value": world * R * N * a.sweeps * e2e_steps / e2e_t, "unit": "attempts/s", "h2d_bytes_per_step": desc_bytes,
-           "d2h_bytes_per_step": int(rows.nbytes),
+           "d2h_bytes_per_step": int(rows.nbytes), "job_seconds": e2e_job_s,
            "what": "scan.run_points(): create system from host descriptor, init, %d measured sweeps, result rows to host, destroy; "
                    "host wall clock, max over ranks" % a.sweeps}
 

@@ -19,6 +19,12 @@ struct Error : std::runtime_error {
 
 void set_last_error(const std::string &m);
 
+// Large per-system buffers (spin planes, Wolff forests) come from the device's stream-ordered memory pool with
+// the release threshold lifted, so that back-to-back jobs (one system per MCMainFunction-like call) reuse the
+// same pages instead of paying a multi-millisecond cudaMalloc/cudaFree of gigabytes each time.
+void *pool_alloc(size_t bytes);
+void pool_free(void *p);
+
 #define MCG_CUDA(call)                                                                                      \
     do {                                                                                                    \
         cudaError_t e_ = (call);                                                                            \

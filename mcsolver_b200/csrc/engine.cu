@@ -35,12 +35,29 @@ template <typename F> static int guarded(F &&f) {
     }
 }
 
-template <typename T> static T *dalloc(size_t n) {
-    T *p = nullptr;
-    if (n == 0) n = 1;
-    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
-    if (e != cudaSuccess) throw Error(MCG_ERR_ALLOC, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+void *pool_alloc(size_t bytes) {
+    int dev = 0;
+    MCG_CUDA(cudaGetDevice(&dev));
+    static thread_local int configured = -1;
+    cudaMemPool_t pool;
+    MCG_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    if (configured != dev) {
+        uint64_t keep = ~0ull;
+        MCG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        configured = dev;
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMallocFromPoolAsync(&p, bytes ? bytes : 16, pool, 0);
+    if (e != cudaSuccess) throw Error(MCG_ERR_ALLOC, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
+    MCG_CUDA(cudaStreamSynchronize(0));
     return p;
+}
+void pool_free(void *p) {
+    if (p) cudaFreeAsync(p, 0);
+}
+
+template <typename T> static T *dalloc(size_t n) {
+    return static_cast<T *>(pool_alloc((n ? n : 1) * sizeof(T)));
 }
 template <typename T> static T *dupload(const std::vector<T> &v) {
     T *p = dalloc<T>(v.size());
@@ -294,7 +311,7 @@ static mcg_system *create_from_tables(const mcg_tables *t, const mcg_config *cfg
     }
     if (s->prec == 64) { s->d_Jtab = dupload_real<double>(Jtab); s->d_clsS = dupload_real<double>(clsS); s->d_clsD = dupload_real<double>(clsD); }
     else { s->d_Jtab = dupload_real<float>(Jtab); s->d_clsS = dupload_real<float>(clsS); s->d_clsD = dupload_real<float>(clsD); }
-    MCG_CUDA(cudaMalloc(&s->d_spin, (size_t)s->R * s->NC * N * s->real_size()));
+    s->d_spin = pool_alloc((size_t)s->R * s->NC * N * s->real_size());
     s->d_scratch = dalloc<double>(3 * (size_t)N);
     alloc_replica_state(s, cfg);
     if (s->nR > 0) {
@@ -444,8 +461,8 @@ static void wolff_steps(mcg_system *s, int64_t n) {
     MCG_REQUIRE(n >= 0, "negative step count");
     const size_t RN = (size_t)s->R * s->N;
     if (!s->d_parent) {
-        s->d_parent = dalloc<int32_t>(2 * RN);
-        MCG_CUDA(cudaMalloc(&s->d_proj, 2 * RN * s->real_size()));
+        s->d_parent = (int32_t *)pool_alloc(2 * RN * sizeof(int32_t));
+        s->d_proj = pool_alloc(2 * RN * s->real_size());
         s->d_wres = dalloc<double>(2 * (size_t)s->R);
         s->wolffPrimed = false;
     }
@@ -553,10 +570,15 @@ static void results(mcg_system *s, int r, double *out, double *groupOut) {
 
 mcg_system::~mcg_system() {
     cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);   // nothing of this system may still be running when its pages go back to the pool
+    mcg::pool_free(d_spin);
+    mcg::pool_free(d_parent);
+    mcg::pool_free(d_proj);
+    d_spin = nullptr; d_parent = nullptr; d_proj = nullptr;
     void *bufs[] = {d_nbrp, d_site_of, d_pos_of, d_pairs, d_tri, d_mi, d_mj, d_jtype, d_cls, d_Jtab, d_clsS, d_clsD, d_spin,
                     d_signS, d_beta, d_field, d_sums, d_acc, d_cnt, d_scratch, d_parent, d_proj, d_wres, d_slot, d_last, d_rPos, d_rCl, d_rNbrRow, d_rNl, d_pairRowI, d_pairRowJ, d_groups, d_ms, d_rsums,
                     d_gsum, d_gacc};
-    for (void *b : bufs) if (b) cudaFree(b);
+    for (void *b : bufs) mcg::pool_free(b);
     if (st) mcg::structured_destroy(st);
     if (stream) cudaStreamDestroy(stream);
 }

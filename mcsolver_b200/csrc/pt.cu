@@ -32,15 +32,13 @@ MCG_API int mcg_pt_configure(mcg_system *sys, int nLabels) {
         MCG_REQUIRE(nLabels >= sys->R, "nLabels must be >= the number of local replicas");
         MCG_CUDA(cudaSetDevice(sys->device));
         MCG_CUDA(cudaStreamSynchronize(sys->stream));
-        if (sys->d_acc) cudaFree(sys->d_acc);
-        sys->d_acc = nullptr;
-        MCG_CUDA(cudaMalloc(&sys->d_acc, sizeof(double) * (size_t)nLabels * NACC));
+        pool_free(sys->d_acc);
+        sys->d_acc = (double *)pool_alloc(sizeof(double) * (size_t)nLabels * NACC);
         MCG_CUDA(cudaMemset(sys->d_acc, 0, sizeof(double) * (size_t)nLabels * NACC));
         if (sys->d_gacc) {   // per-label group accumulators follow
             size_t n = (size_t)(sys->nG + 2) * (sys->nG + 1);
-            cudaFree(sys->d_gacc);
-            sys->d_gacc = nullptr;
-            MCG_CUDA(cudaMalloc(&sys->d_gacc, sizeof(double) * nLabels * n));
+            pool_free(sys->d_gacc);
+            sys->d_gacc = (double *)pool_alloc(sizeof(double) * nLabels * n);
             MCG_CUDA(cudaMemset(sys->d_gacc, 0, sizeof(double) * nLabels * n));
         }
         sys->nLabel = nLabels;

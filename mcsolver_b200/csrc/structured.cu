@@ -1029,7 +1029,7 @@ void structured_create(mcg_system *s, const mcg_lattice_desc *d) {
     structured_build_host(s, d, links, Jt);
     StructuredSystem *st = s->st;
     // ---- upload ----
-    auto up = [&](const void *src, size_t bytes) { void *p = nullptr; MCG_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 16))); if (bytes) MCG_CUDA(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice)); return p; };
+    auto up = [&](const void *src, size_t bytes) { void *p = pool_alloc(std::max<size_t>(bytes, 16)); if (bytes) MCG_CUDA(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice)); return p; };
     st->d_classes = (SClassD *)up(st->classes.data(), st->classes.size() * sizeof(SClassD));
     st->d_links = (SLinkD *)up(links.data(), links.size() * sizeof(SLinkD));
     if (s->prec == 64) st->d_J = up(Jt.data(), Jt.size() * sizeof(double));
@@ -1040,9 +1040,9 @@ void structured_create(mcg_system *s, const mcg_lattice_desc *d) {
     st->d_tverts = (int *)up(st->tvertsHost.data(), st->tvertsHost.size() * sizeof(int));
     st->d_ttris = (int *)up(st->ttrisHost.data(), st->ttrisHost.size() * sizeof(int));
     size_t cs = (size_t)s->R * st->nclass * 4 * sizeof(double);
-    MCG_CUDA(cudaMalloc(&st->d_classSums, cs));
+    st->d_classSums = (double *)pool_alloc(cs);
     MCG_CUDA(cudaMemset(st->d_classSums, 0, cs));
-    MCG_CUDA(cudaMalloc(&s->d_spin, (size_t)s->R * s->NC * s->N * s->real_size()));
+    s->d_spin = pool_alloc((size_t)s->R * s->NC * s->N * s->real_size());
 }
 
 // host-only check used by the CPU tests: build the class tables of a descriptor and compile the
@@ -1073,7 +1073,7 @@ int structured_jit_check(const mcg_lattice_desc *d, int precision, std::string &
 void structured_destroy(StructuredSystem *st) {
     if (!st) return;
     void *bufs[] = {st->d_classes, st->d_links, st->d_J, st->d_classOf, st->d_circuits, st->d_classSums, st->d_stage, st->d_tverts, st->d_ttris, st->d_gmask};
-    for (void *b : bufs) if (b) cudaFree(b);
+    for (void *b : bufs) pool_free(b);
     delete st;
 }
 
@@ -1100,7 +1100,7 @@ void structured_init_spins(mcg_system *s, double flunc) {
 }
 
 static double *stage(mcg_system *s) {
-    if (!s->st->d_stage) MCG_CUDA(cudaMalloc(&s->st->d_stage, 3 * (size_t)s->N * sizeof(double)));
+    if (!s->st->d_stage) s->st->d_stage = (double *)pool_alloc(3 * (size_t)s->N * sizeof(double));
     return s->st->d_stage;
 }
 
