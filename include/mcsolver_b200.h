@@ -101,6 +101,9 @@ typedef struct {
     int32_t ngroup;           /* orbital groups (fileio orbGroupList); 0 = none */
     const int32_t *group_mask;/* [ngroup*norb] 1 if the orbital belongs to the group */
     int32_t group_in_sc;      /* 1: "Supergroup" - a group spans the whole supercell (Lattice.py:208-209); 0: cell (0,0,0) only */
+    int32_t block_spin;       /* 1: block-spin ("renormalised lattice") statistics every measured sweep - tuple slots 11-19,
+                                 Ising 6-7 (heisenbergLib.c:748-803); one more read of the configuration per sweep.
+                                 0: those slots stay 0.  Needs even supercell dims; the table path always computes them. */
 } mcg_lattice_desc;
 
 typedef struct {

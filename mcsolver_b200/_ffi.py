@@ -33,7 +33,7 @@ class LatticeDesc(C.Structure):
     _fields_ = [("model", C.c_int32), ("L", C.c_int32 * 3), ("norb", C.c_int32), ("S", C.c_void_p), ("D", C.c_void_p),
                 ("nbond", C.c_int32), ("bonds", C.c_void_p), ("pair_s", C.c_int32), ("pair_t", C.c_int32),
                 ("pair_d", C.c_int32 * 3), ("ncircuit", C.c_int32), ("circuits", C.c_void_p), ("ngroup", C.c_int32),
-                ("group_mask", C.c_void_p), ("group_in_sc", C.c_int32)]
+                ("group_mask", C.c_void_p), ("group_in_sc", C.c_int32), ("block_spin", C.c_int32)]
 
 
 class Config(C.Structure):

@@ -28,7 +28,8 @@ __device__ __forceinline__ double warp_sum(double v) {
 // smem: at least NV*32 doubles.  All threads of the block must call it.
 template <int NV>
 __device__ __forceinline__ void block_accumulate(double (&v)[NV], double *dst, double *smem) {
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    const int lt = threadIdx.y * blockDim.x + threadIdx.x;   // 1-D and 2-D blocks
+    int lane = lt & 31, w = lt >> 5, nw = (blockDim.x * blockDim.y + 31) >> 5;
 #pragma unroll
     for (int i = 0; i < NV; i++) {
         double s = warp_sum(v[i]);
@@ -41,6 +42,29 @@ __device__ __forceinline__ void block_accumulate(double (&v)[NV], double *dst, d
             double s = lane < nw ? smem[i * 32 + lane] : 0.0;
             s = warp_sum(s);
             if (lane == 0 && s != 0.0) atomicAdd(dst + i, s);
+        }
+    }
+    __syncthreads();
+}
+
+// Same reduction without atomics: thread 0 stores the block totals to dst[0..NV) (any memory it alone reads back, or
+// shared memory followed by the trailing barrier).  For kernels in which ONE block owns the destination.
+template <int NV>
+__device__ __forceinline__ void block_reduce_to(double (&v)[NV], double *dst, double *smem) {
+    const int lt = threadIdx.y * blockDim.x + threadIdx.x;   // 1-D and 2-D blocks
+    int lane = lt & 31, w = lt >> 5, nw = (blockDim.x * blockDim.y + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        double s = warp_sum(v[i]);
+        if (lane == 0) smem[i * 32 + w] = s;
+    }
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+            double s = lane < nw ? smem[i * 32 + lane] : 0.0;
+            s = warp_sum(s);
+            if (lane == 0) dst[i] = s;
         }
     }
     __syncthreads();

@@ -12,6 +12,7 @@
 
 #include "kernels_extra.cuh"
 #include "kernels_wolff.cuh"
+#include "kernels_resident.cuh"
 #include "structured.hpp"
 
 namespace mcg {
@@ -496,6 +497,83 @@ static void capture_frame(mcg_system *s, int r, double *dst) {
     get_spins(s, r, dst);
 }
 
+// Small table-built lattices: the whole loop runs inside k_resident (kernels_resident.cuh), one block per replica.
+static int resident_max_sites() {
+    if (getenv("MCG_NO_RESIDENT")) return 0;
+    const char *e = getenv("MCG_RESIDENT_MAXN");
+    return e ? atoi(e) : 4096;   // measured crossover with the launch-per-phase path (scripts/probe_resident.py)
+}
+
+static void run_resident(mcg_system *s, int algorithm, int64_t thermalUpdates, int64_t perSweep, double pAtt, int64_t nsweep, int spinFrame,
+                         double *frames) {
+    if (!s->d_colourStart) {
+        s->d_colourStart = dalloc<int>(s->colourStart.size());
+        MCG_CUDA(cudaMemcpy(s->d_colourStart, s->colourStart.data(), s->colourStart.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    bool needResidual = false;
+    if (algorithm == MCG_WOLFF) {
+        bool anyField = false;
+        for (double h : s->field_host) anyField = anyField || h != 0.0;
+        needResidual = anyField || (s->model != MCG_ISING && !s->isoNoOnsite);
+    }
+    s->wolffPrimed = false;   // the resident kernel keeps its forest in shared memory; the global buffers are not prepared
+    const size_t fsz = (size_t)s->N * (s->NC == 1 ? 1 : 3);
+    double *d_frames = nullptr;
+    if (spinFrame > 0) {
+        d_frames = dalloc<double>((size_t)s->R * spinFrame * fsz);
+        MCG_CUDA(cudaMemsetAsync(d_frames, 0, sizeof(double) * s->R * spinFrame * fsz, s->stream));   // frames never reached stay zero
+    }
+
+    GenArgs a = gen_args(s);
+    RgArgs g;
+    g.nR = s->nR; g.nC = s->nC; g.nLat = s->nLat; g.rPos = s->d_rPos; g.rCl = s->d_rCl; g.rNbrRow = s->d_rNbrRow; g.rNl = s->d_rNl;
+    g.pairRowI = s->d_pairRowI; g.pairRowJ = s->d_pairRowJ; g.ms = s->d_ms; g.rsums = s->d_rsums; g.meas = 0;
+    WolffArgs w;
+    w.parent = w.parentNext = nullptr; w.proj = w.projNext = nullptr;
+    w.wres = s->d_wres; w.N = s->N; w.R = s->R; w.spin = s->d_spin; w.step = 0;
+    w.beta = s->d_beta; w.field = s->d_field; w.cnt = s->d_cnt; w.key = make_rng_key(s->seed); w.replica0 = s->replica0;
+    ResidentPlan P;
+    P.algorithm = algorithm; P.model = s->model; P.pAtt = pAtt; P.C = s->C; P.colourStart = s->d_colourStart;
+    P.needResidual = needResidual ? 1 : 0;
+    P.spinFrame = spinFrame; P.per = spinFrame > 0 ? std::max<int64_t>(1, nsweep / spinFrame) : 1; P.frames = d_frames;
+    P.mi = s->d_mi; P.mj = s->d_mj; P.pairs = s->d_pairs; P.tri = s->d_tri; P.nLat = s->nLat; P.nTri = s->nTri;
+    P.nG = s->nG; P.maxG = s->maxG; P.groups = s->d_groups; P.gsum = s->d_gsum; P.gacc = s->d_gacc;
+    P.rg_ci = s->rg_ci; P.rg_cj = s->rg_cj; P.rg_cij = s->rg_cij; P.signS = s->d_signS;
+    P.acc = s->d_acc; P.last = s->d_last; P.slot = s->d_slot;
+    const bool extras = s->nR > 0 || s->nG > 0;
+    // threads per block: about one site of the largest colour class per thread (barriers and reductions scale with warps)
+    int biggest = 1;
+    for (int c = 0; c < s->C; c++) biggest = std::max(biggest, s->colourStart[c + 1] - s->colourStart[c]);
+    if (algorithm == MCG_WOLFF) biggest = s->N;
+    int nthreads = 64;
+    while (nthreads < biggest && nthreads < RES_THREADS) nthreads <<= 1;
+
+    auto launch = [&](int64_t thermal, int64_t i0, int64_t n) {
+        P.thermal = thermal; P.perSweep = perSweep; P.nsweep = n; P.i0 = i0;
+        P.sweep0 = s->sweepCtr; P.step0 = s->wolffCtr; P.meas0 = s->measCtr;
+        const size_t shm = algorithm == MCG_WOLFF ? resident_wolff_smem(s->N, s->real_size()) : 0;
+        dispatch(s, [&]<int NC, typename real, bool FJ>() {
+            if (shm > 40 * 1024) MCG_CUDA(cudaFuncSetAttribute(k_resident<NC, real, FJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+            k_resident<NC, real, FJ><<<s->R, nthreads, shm, s->stream>>>(a, g, w, s->d_pos_of, P);
+        });
+        MCG_CUDA(cudaGetLastError());
+        s->launches++;
+        const int64_t updates = thermal + n * perSweep;
+        if (algorithm == MCG_METROPOLIS) s->sweepCtr += updates;
+        else s->wolffCtr += updates;
+        if (extras) s->measCtr += n;
+    };
+    const int64_t chunk = 1 << 16;   // bounds the run time of one launch
+    for (int64_t done = 0; done < thermalUpdates; done += chunk) launch(std::min(chunk, thermalUpdates - done), 0, 0);
+    const int64_t mchunk = std::max<int64_t>(1, chunk / std::max<int64_t>(1, perSweep));
+    for (int64_t done = 0; done < nsweep; done += mchunk) launch(0, done, std::min(mchunk, nsweep - done));
+    if (spinFrame > 0) {
+        MCG_CUDA(cudaMemcpyAsync(frames, d_frames, sizeof(double) * s->R * spinFrame * fsz, cudaMemcpyDeviceToHost, s->stream));
+    }
+    MCG_CUDA(cudaStreamSynchronize(s->stream));
+    pool_free(d_frames);
+}
+
 static void run(mcg_system *s, int algorithm, int64_t nthermal, int64_t nsweep, int64_t ninterval, int spinFrame, double *frames) {
     MCG_REQUIRE(algorithm == MCG_METROPOLIS || algorithm == MCG_WOLFF, "algorithm must be 0 (Metropolis) or 1 (Wolff)");
     MCG_REQUIRE(nthermal >= 0 && nsweep >= 1 && ninterval >= 0, "need nthermal>=0, nsweep>=1, ninterval>=0");
@@ -506,6 +584,11 @@ static void run(mcg_system *s, int algorithm, int64_t nthermal, int64_t nsweep, 
         if (ninterval >= s->N) nsub = (ninterval + s->N / 2) / s->N;
         else if (ninterval > 0) pAtt = (double)ninterval / (double)s->N;
         else nsub = 0;
+    }
+    if (!s->structured && !s->profilePasses && s->N <= resident_max_sites()) {
+        const int64_t per = algorithm == MCG_METROPOLIS ? nsub : ninterval;
+        run_resident(s, algorithm, nthermal * per, per, pAtt, nsweep, spinFrame, frames);
+        return;
     }
     auto updates = [&](int64_t intervals) {
         if (algorithm == MCG_METROPOLIS) { if (nsub > 0) metropolis_sweeps(s, intervals * nsub, pAtt); }
@@ -577,7 +660,7 @@ mcg_system::~mcg_system() {
     d_spin = nullptr; d_parent = nullptr; d_proj = nullptr;
     void *bufs[] = {d_nbrp, d_site_of, d_pos_of, d_pairs, d_tri, d_mi, d_mj, d_jtype, d_cls, d_Jtab, d_clsS, d_clsD, d_spin,
                     d_signS, d_beta, d_field, d_sums, d_acc, d_cnt, d_scratch, d_parent, d_proj, d_wres, d_slot, d_last, d_rPos, d_rCl, d_rNbrRow, d_rNl, d_pairRowI, d_pairRowJ, d_groups, d_ms, d_rsums,
-                    d_gsum, d_gacc};
+                    d_gsum, d_gacc, d_colourStart};
     for (void *b : bufs) mcg::pool_free(b);
     if (st) mcg::structured_destroy(st);
     if (stream) cudaStreamDestroy(stream);

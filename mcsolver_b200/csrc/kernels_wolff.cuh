@@ -115,36 +115,22 @@ template <int NC, typename real> struct TableTopo {
     }
 };
 
-template <int NC, typename real, typename TOPO>
-__global__ void __launch_bounds__(256) k_wolff_init(TOPO topo, WolffArgs w) {
-    int r = blockIdx.y;
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    __shared__ SeedShared<NC, real> sh;
-    real n[3], u; int seed;
-    wolff_seed_block<NC, real>(w, r, sh, n, seed, u);
-    if (p == 0) { w.wres[2 * r] = 0.0; w.wres[2 * r + 1] = 0.0; }
-    if (p >= w.N) return;
-    w.parent[(size_t)r * w.N + p] = p;
+// ---- per-site bodies (shared by the per-phase kernels below and by the resident kernel) ----
+// All per-site bodies take replica-local pointers: sp [NC][N], proj [N], parent [N] (global memory in the per-phase
+// kernels, shared memory in the resident kernel).
+template <int NC, typename real>
+__device__ __forceinline__ void wolff_init_site(const real *sp, int N, int p, const real (&n)[3], int32_t *parent, real *proj) {
+    parent[p] = p;
     if (NC > 1) {
-        const real *sp = (const real *)w.spin + (size_t)r * NC * w.N;
         real s[3];
-        load_spin<NC, real>(sp, w.N, p, s);
-        ((real *)w.proj)[(size_t)r * w.N + p] = -(s[0] * n[0] + s[1] * n[1] + s[2] * n[2]);   // sDotN, heisenbergLib.c:324
+        load_spin<NC, real>(sp, N, p, s);
+        proj[p] = -(s[0] * n[0] + s[1] * n[1] + s[2] * n[2]);   // sDotN, heisenbergLib.c:324
     }
 }
 
 template <int NC, typename real, bool FULLJ, typename TOPO>
-__global__ void __launch_bounds__(256) k_wolff_bonds(TOPO topo, WolffArgs w) {
-    int r = blockIdx.y;
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    __shared__ SeedShared<NC, real> sh;
-    real n[3], uAcc; int seed;
-    wolff_seed_block<NC, real>(w, r, sh, n, seed, uAcc);
-    if (p == 0) { w.wres[2 * r] = 0.0; w.wres[2 * r + 1] = 0.0; }
-    if (p >= w.N) return;
-    const real *sp = (const real *)w.spin + (size_t)r * NC * w.N;
-    const real *proj = (const real *)w.proj + (size_t)r * w.N;
-    int32_t *parent = w.parent + (size_t)r * w.N;
+__device__ __forceinline__ void wolff_bonds_site(const TOPO &topo, const WolffArgs &w, int r, int p, const real (&n)[3], const real *sp,
+                                                 const real *proj, int32_t *parent) {
     real beta = (real)w.beta[r];
     auto c = topo.begin(p);
     const int ip = topo.site_id(c);
@@ -166,17 +152,120 @@ __global__ void __launch_bounds__(256) k_wolff_bonds(TOPO topo, WolffArgs w) {
     }
 }
 
-static __global__ void __launch_bounds__(256) k_wolff_flatten(int N, int32_t *parentAll) {
-    int r = blockIdx.y;
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= N) return;
-    int32_t *parent = parentAll + (size_t)r * N;
+__device__ __forceinline__ void wolff_flatten_site(int32_t *parent, int p) {
     int x = p;
     while (parent[x] != x) x = parent[x];
     parent[p] = x;
 }
 
-// residual energy of reflecting the seed's cluster, and its size
+// residual energy of reflecting the seed's cluster (v[0]) and its size (v[1]); parent[] flattened, root = parent[seed]
+template <int NC, typename real, bool FULLJ, typename TOPO>
+__device__ __forceinline__ void wolff_residual_site(const TOPO &topo, const WolffArgs &w, int r, int p, const real (&n)[3], int root, double (&v)[2],
+                                                    const real *sp, const real *proj, const int32_t *parent) {
+    if (parent[p] != root) return;
+    real beta = (real)w.beta[r], hf = (real)(w.beta[r] * w.field[r]);
+    v[1] += 1.0;
+    if (NC == 1) {
+        v[0] += 2.0 * (double)hf * (double)sp[p];                         // getDeltaOnsiteEnergy isingLib.c:129-131
+        return;
+    }
+    auto c = topo.begin(p);
+    real s[3];
+    load_spin<NC, real>(sp, w.N, p, s);
+    real ap = proj[p];
+    real perp_p[3] = {s[0] + ap * n[0], s[1] + ap * n[1], s[2] + ap * n[2]};
+    double res = 0.0;
+    const int nl = topo.nlinks(c);
+    for (int k = 0; k < nl; k++) {
+        int q; const real *J;
+        if (!topo.link(c, k, q, J)) continue;
+        real t[3];
+        load_spin<NC, real>(sp, w.N, q, t);
+        real aq = proj[q];
+        real perp_q[3] = {t[0] + aq * n[0], t[1] + aq * n[1], t[2] + aq * n[2]};
+        real src = ap * beta * quad_form<NC, real, FULLJ>(J, n, perp_q);          // heisenbergLib.c:407
+        res += (double)src;
+        if (parent[q] == root) res += (double)(aq * beta * quad_form<NC, real, FULLJ>(J, perp_p, n));   // :411
+        else res += (double)src;                                                   // :413
+    }
+    real D[3];
+    topo.D(c, D);
+    real tr[3] = {real(2) * ap * n[0], real(2) * ap * n[1], real(2) * ap * n[2]};
+    real t1[3] = {s[0] + tr[0], s[1] + tr[1], s[2] + tr[2]};
+    real dOn = D[0] * (t1[0] * t1[0] - s[0] * s[0]) + D[1] * (t1[1] * t1[1] - s[1] * s[1]);
+    if (NC == 3) dOn += D[2] * (t1[2] * t1[2] - s[2] * s[2]);
+    res += (double)(beta * dOn - hf * (NC == 3 ? tr[2] : tr[0]));
+    v[0] += res;
+}
+
+// reflect site p if it belongs to the accepted cluster, count the step at the seed, and (parentNext != nullptr) prepare
+// the next step: fresh forest in the other buffer, projections on the next plane normal n2
+template <int NC, typename real, bool FLAT, typename TOPO>
+__device__ __forceinline__ void wolff_flip_site(const TOPO &topo, const WolffArgs &w, int r, int p, const real (&n)[3], const real (&n2)[3],
+                                                int seedPos, bool accept, bool inCluster, double clusterSize, real *sp, const real *proj,
+                                                int32_t *parentNext, real *projNext) {
+    if (p == seedPos) {
+        atomicAdd(w.cnt + (size_t)r * NCNT + CNT_WSTEPS, 1ull);
+        atomicAdd(w.cnt + (size_t)r * NCNT + CNT_ATTEMPT, 1ull);
+        if (accept) {
+            atomicAdd(w.cnt + (size_t)r * NCNT + CNT_ACCEPT, 1ull);
+            if (FLAT) atomicAdd(w.cnt + (size_t)r * NCNT + CNT_CLUSTER, (unsigned long long)(clusterSize + 0.5));
+        }
+    }
+    real s[3];
+    if (parentNext || (accept && inCluster)) load_spin<NC, real>(sp, w.N, p, s);
+    if (accept && inCluster) {
+        if (NC == 1) s[0] = -s[0];
+        else {
+            real ap = proj[p];
+            s[0] += real(2) * ap * n[0]; s[1] += real(2) * ap * n[1]; s[2] += real(2) * ap * n[2];   // heisenbergLib.c:425-426
+            if (sizeof(real) == 4) {
+                real S = topo.S(topo.begin(p));
+                real f = S * r_rsqrt<real>(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]);
+                s[0] *= f; s[1] *= f; s[2] *= f;
+            }
+        }
+        store_spin<NC, real>(sp, w.N, p, s);
+    }
+    if (parentNext) {
+        parentNext[p] = p;
+        if (NC > 1) projNext[p] = -(s[0] * n2[0] + s[1] * n2[1] + s[2] * n2[2]);
+    }
+}
+
+// ---- one kernel per phase (lattices too large for one thread block) ----
+template <int NC, typename real, typename TOPO>
+__global__ void __launch_bounds__(256) k_wolff_init(TOPO topo, WolffArgs w) {
+    int r = blockIdx.y;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ SeedShared<NC, real> sh;
+    real n[3], u; int seed;
+    wolff_seed_block<NC, real>(w, r, sh, n, seed, u);
+    if (p == 0) { w.wres[2 * r] = 0.0; w.wres[2 * r + 1] = 0.0; }
+    if (p >= w.N) return;
+    wolff_init_site<NC, real>((const real *)w.spin + (size_t)r * NC * w.N, w.N, p, n, w.parent + (size_t)r * w.N, (real *)w.proj + (size_t)r * w.N);
+}
+
+template <int NC, typename real, bool FULLJ, typename TOPO>
+__global__ void __launch_bounds__(256) k_wolff_bonds(TOPO topo, WolffArgs w) {
+    int r = blockIdx.y;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ SeedShared<NC, real> sh;
+    real n[3], uAcc; int seed;
+    wolff_seed_block<NC, real>(w, r, sh, n, seed, uAcc);
+    if (p == 0) { w.wres[2 * r] = 0.0; w.wres[2 * r + 1] = 0.0; }
+    if (p >= w.N) return;
+    wolff_bonds_site<NC, real, FULLJ, TOPO>(topo, w, r, p, n, (const real *)w.spin + (size_t)r * NC * w.N, (const real *)w.proj + (size_t)r * w.N,
+                                            w.parent + (size_t)r * w.N);
+}
+
+static __global__ void __launch_bounds__(256) k_wolff_flatten(int N, int32_t *parentAll) {
+    int r = blockIdx.y;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    wolff_flatten_site(parentAll + (size_t)r * N, p);
+}
+
 template <int NC, typename real, bool FULLJ, typename TOPO>
 __global__ void __launch_bounds__(256) k_wolff_residual(TOPO topo, WolffArgs w) {
     __shared__ double smem[2 * 32];
@@ -186,46 +275,11 @@ __global__ void __launch_bounds__(256) k_wolff_residual(TOPO topo, WolffArgs w) 
     __shared__ SeedShared<NC, real> sh;
     real n[3], uAcc; int seed;
     wolff_seed_block<NC, real>(w, r, sh, n, seed, uAcc);
-    const int32_t *parent = w.parent + (size_t)r * w.N;
     if (p < w.N) {
+        const int32_t *parent = w.parent + (size_t)r * w.N;
         int root = parent[topo.pos_of_site(seed)];
-        if (parent[p] == root) {
-            const real *sp = (const real *)w.spin + (size_t)r * NC * w.N;
-            real beta = (real)w.beta[r], hf = (real)(w.beta[r] * w.field[r]);
-            v[1] = 1.0;
-            if (NC == 1) {
-                v[0] = 2.0 * (double)hf * (double)sp[p];                         // getDeltaOnsiteEnergy isingLib.c:129-131
-            } else {
-                const real *proj = (const real *)w.proj + (size_t)r * w.N;
-                auto c = topo.begin(p);
-                real s[3];
-                load_spin<NC, real>(sp, w.N, p, s);
-                real ap = proj[p];
-                real perp_p[3] = {s[0] + ap * n[0], s[1] + ap * n[1], s[2] + ap * n[2]};
-                double res = 0.0;
-                const int nl = topo.nlinks(c);
-                for (int k = 0; k < nl; k++) {
-                    int q; const real *J;
-                    if (!topo.link(c, k, q, J)) continue;
-                    real t[3];
-                    load_spin<NC, real>(sp, w.N, q, t);
-                    real aq = proj[q];
-                    real perp_q[3] = {t[0] + aq * n[0], t[1] + aq * n[1], t[2] + aq * n[2]};
-                    real src = ap * beta * quad_form<NC, real, FULLJ>(J, n, perp_q);          // heisenbergLib.c:407
-                    res += (double)src;
-                    if (parent[q] == root) res += (double)(aq * beta * quad_form<NC, real, FULLJ>(J, perp_p, n));   // :411
-                    else res += (double)src;                                                   // :413
-                }
-                real D[3];
-                topo.D(c, D);
-                real tr[3] = {real(2) * ap * n[0], real(2) * ap * n[1], real(2) * ap * n[2]};
-                real t1[3] = {s[0] + tr[0], s[1] + tr[1], s[2] + tr[2]};
-                real dOn = D[0] * (t1[0] * t1[0] - s[0] * s[0]) + D[1] * (t1[1] * t1[1] - s[1] * s[1]);
-                if (NC == 3) dOn += D[2] * (t1[2] * t1[2] - s[2] * s[2]);
-                res += (double)(beta * dOn - hf * (NC == 3 ? tr[2] : tr[0]));
-                v[0] = res;
-            }
-        }
+        wolff_residual_site<NC, real, FULLJ, TOPO>(topo, w, r, p, n, root, v, (const real *)w.spin + (size_t)r * NC * w.N,
+                                                   (const real *)w.proj + (size_t)r * w.N, parent);
     }
     block_accumulate<2>(v, w.wres + 2 * r, smem);
 }
@@ -269,33 +323,9 @@ __global__ void __launch_bounds__(256) k_wolff_flip(TOPO topo, WolffArgs w) {
         if (threadIdx.x == 0 && nIn) atomicAdd(w.cnt + (size_t)r * NCNT + CNT_CLUSTER, (unsigned long long)nIn);
     }
     if (p >= w.N) return;
-    if (p == seedPos) {
-        atomicAdd(w.cnt + (size_t)r * NCNT + CNT_WSTEPS, 1ull);
-        atomicAdd(w.cnt + (size_t)r * NCNT + CNT_ATTEMPT, 1ull);
-        if (accept) {
-            atomicAdd(w.cnt + (size_t)r * NCNT + CNT_ACCEPT, 1ull);
-            if (FLAT) atomicAdd(w.cnt + (size_t)r * NCNT + CNT_CLUSTER, (unsigned long long)(w.wres[2 * r + 1] + 0.5));
-        }
-    }
-    real *sp = (real *)w.spin + (size_t)r * NC * w.N;
-    real s[3];
-    load_spin<NC, real>(sp, w.N, p, s);
-    if (accept && inCluster) {
-        if (NC == 1) s[0] = -s[0];
-        else {
-            real ap = ((const real *)w.proj)[(size_t)r * w.N + p];
-            s[0] += real(2) * ap * n[0]; s[1] += real(2) * ap * n[1]; s[2] += real(2) * ap * n[2];   // heisenbergLib.c:425-426
-            if (sizeof(real) == 4) {
-                real S = topo.S(topo.begin(p));
-                real f = S * r_rsqrt<real>(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]);
-                s[0] *= f; s[1] *= f; s[2] *= f;
-            }
-        }
-        store_spin<NC, real>(sp, w.N, p, s);
-    }
-    // next step: fresh forest in the other buffer, projections on the next plane normal
-    w.parentNext[(size_t)r * w.N + p] = p;
-    if (NC > 1) ((real *)w.projNext)[(size_t)r * w.N + p] = -(s[0] * n2[0] + s[1] * n2[1] + s[2] * n2[2]);
+    wolff_flip_site<NC, real, FLAT, TOPO>(topo, w, r, p, n, n2, seedPos, accept, inCluster, FLAT ? w.wres[2 * r + 1] : 0.0,
+                                          (real *)w.spin + (size_t)r * NC * w.N, (const real *)w.proj + (size_t)r * w.N,
+                                          w.parentNext + (size_t)r * w.N, (real *)w.projNext + (size_t)r * w.N);
 }
 
 // launch sequence of one cluster update, shared by both paths.  primed: the forest/projection buffers of this

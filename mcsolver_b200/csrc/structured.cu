@@ -25,8 +25,16 @@
 #include "struct_pass.cuh"
 #include "jit.hpp"
 #include "kernels_wolff.cuh"
+#include "kernels_extra.cuh"
 
 namespace mcg {
+
+// Block-spin tables (see the kernels below).  RgEntD: one (bond, direction) entry of an orbital's link list in bond order.
+struct RgEntD {
+    int o2;         // orbital of the coarse neighbour
+    int off[3];     // +2d (forward) or -2d (backward), reduced into [0,L), internal axes
+};
+struct RgZones { int R[3], nz[3]; };   // per axis: coordinates closer than R to either edge are their own zone, the rest is "bulk"
 
 struct StructuredSystem {
     int L[3], p[3], Xd, Yd, Zd, ncellc, nclass, norb, V;
@@ -53,6 +61,19 @@ struct StructuredSystem {
     bool groupInSC = true;
     int nvert = 0;
     double *d_classSums = nullptr;       // [R][nclass][4]
+    // block-spin ("renormalised lattice") statistics, opt-in through mcg_lattice_desc.block_spin
+    bool rgOn = false;
+    int rgN[3] = {0, 0, 0}, nR = 0;      // chosen (all-even) cells per axis, chosen sites
+    double rg_ci = 0, rg_cj = 0, rg_cij = 0;
+    RgZones rgZ;
+    std::vector<RgEntD> rgEntHost;       // [norb][MAXLINK]
+    std::vector<int> rgNentHost;         // [norb]
+    std::vector<int> rgPermHost;         // [nsig][MAXLINK]: (2*bond + transposed) << 8 | entry giving the k-th coarse neighbour
+    std::vector<double> rgJHost;         // [nbond][9] unscaled, reference flat order
+    std::vector<double> rgSDHost;        // [norb][4] signed S, D
+    RgEntD *d_rgEnt = nullptr;
+    int *d_rgNent = nullptr, *d_rgPerm = nullptr;
+    double *d_rgJ = nullptr, *d_rgSD = nullptr, *d_ms = nullptr, *d_rsums = nullptr;
     double *d_stage = nullptr;           // [3N] host<->device staging, allocated on demand
 };
 
@@ -408,44 +429,204 @@ template <typename T> __device__ __forceinline__ T tri_area_unit(const T (&a)[3]
     T re = T(1) + (a[0] * b[0] + a[1] * b[1] + a[2] * b[2]) + (b[0] * c[0] + b[1] * c[1] + b[2] * c[2]) + (c[0] * a[0] + c[1] * a[1] + c[2] * a[2]);
     T im = a[0] * cx + a[1] * cy + a[2] * cz;
     if (fabs(re) < T(1e-6)) return im > 0 ? T(MCG_REF_PI) : T(-MCG_REF_PI);
-    return T(2) * atan(im / re);
+    if constexpr (sizeof(T) == 4) return T(2) * atanf(__fdividef(im, re));
+    else return T(2) * atan(im / re);
 }
 constexpr int TOPO_MAXV = 12;
+constexpr int TOPO_THREADS = 128;
+// The vertex table is indexed by runtime triangle indices, so it lives in shared memory ([vertex][component][thread],
+// conflict-free) rather than in a register array the compiler would have to demote to local memory.
+// A block handles cells of ONE sublattice parity (x%px, y%py, z%pz) and one coarse X: every vertex of its cells then lies
+// in a block-uniform class at a block-uniform coarse offset, so a vertex address costs three wrap-adds (the scheme of the
+// colour passes) instead of a full lattice -> storage decode.  Thread (tz, ty) of block (zc + nzc*(yc + nyc*parity), X, r)
+// handles coarse cell (X, yc*TY + ty, zc*TZ + tz).
 template <typename real>
-__global__ void __launch_bounds__(256) k_struct_topo_cells(StructArgs a, int ncirc, int nvert, const int *__restrict__ verts,
-                                                           const int *__restrict__ tris, double *sums) {
+__global__ void __launch_bounds__(TOPO_THREADS) k_struct_topo_cells(StructArgs a, int ncirc, int nvert, const int *__restrict__ verts,
+                                                                    const int *__restrict__ tris, int nzc, int nyc, double *sums) {
     __shared__ double smem[32];
-    int r = blockIdx.y;
-    int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ real ilen[TOPO_MAXV], lsh[TOPO_MAXV];
+    __shared__ int tsh[3 * 64], vbase[TOPO_MAXV], vcX[TOPO_MAXV], vcY[TOPO_MAXV], vcZ[TOPO_MAXV];
+    extern __shared__ __align__(16) unsigned char topo_dyn[];
+    real *sv = reinterpret_cast<real *>(topo_dyn);
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int par = blockIdx.x / (nzc * nyc), rest = blockIdx.x - par * (nzc * nyc);
+    const int yc = rest / nzc, zc = rest - yc * nzc;
+    if (tid < nvert) {
+        const int *e = verts + 4 * tid;   // (orbital, dx, dy, dz) with offsets already reduced into [0, L)
+        const int cc = par % a.pz, cb = (par / a.pz) % a.py, ca = par / (a.pz * a.py);
+        const int na = ca + e[1], nb = cb + e[2], nc = cc + e[3];
+        const int q = a.classOf[(((na % a.px) * a.py + nb % a.py) * a.pz + nc % a.pz) * a.norb + e[0]];
+        vbase[tid] = q * a.ncellc;
+        vcX[tid] = (na / a.px) % a.Xd; vcY[tid] = (nb / a.py) % a.Yd; vcZ[tid] = (nc / a.pz) % a.Zd;
+        lsh[tid] = (real)fabs(a.classes[q].S);   // |S| depends on the orbital only
+        ilen[tid] = real(1) / lsh[tid];
+    }
+    for (int i = tid; i < 3 * ncirc; i += TOPO_THREADS) tsh[i] = tris[i] * 3 * TOPO_THREADS;
+    __syncthreads();
+    const int r = blockIdx.z;
+    const int X = blockIdx.y, Y = yc * blockDim.y + threadIdx.y, Z = zc * blockDim.x + threadIdx.x;
     double v[1] = {0.0};
-    int ncell = a.Lx * a.Ly * a.Lz;
-    if (cell < ncell) {
-        int z = cell % a.Lz, y = (cell / a.Lz) % a.Ly, x = cell / (a.Lz * a.Ly);
+    if (Y < a.Yd && Z < a.Zd) {
         const real *sp = (const real *)a.spin + (size_t)r * 3 * a.N;
-        real s[TOPO_MAXV][3], l[TOPO_MAXV];
         for (int k = 0; k < nvert; k++) {
-            const int *e = verts + 4 * k;
-            int xx = x + e[1]; if (xx >= a.Lx) xx -= a.Lx;
-            int yy = y + e[2]; if (yy >= a.Ly) yy -= a.Ly;
-            int zz = z + e[3]; if (zz >= a.Lz) zz -= a.Lz;
-            int p = struct_pos(a, xx, yy, zz, e[0]);
-            s[k][0] = sp[p]; s[k][1] = sp[(size_t)a.N + p]; s[k][2] = sp[2 * (size_t)a.N + p];
-            l[k] = (real)fabs(a.classes[a.classOf[e[0]]].S);   // |S| depends on the orbital only (class (0,0,0,o))
-            if (sizeof(real) == 4) {   // fp32: normalise once per vertex instead of dividing in every triangle
-                real inv = real(1) / l[k];
-                s[k][0] *= inv; s[k][1] *= inv; s[k][2] *= inv;
-                l[k] = real(1);
-            }
+            int Xn = X + vcX[k]; if (Xn >= a.Xd) Xn -= a.Xd;
+            int Yn = Y + vcY[k]; if (Yn >= a.Yd) Yn -= a.Yd;
+            int Zn = Z + vcZ[k]; if (Zn >= a.Zd) Zn -= a.Zd;
+            const real *q = sp + (vbase[k] + (Xn * a.Yd + Yn) * a.Zd + Zn);
+            real s0 = q[0], s1 = q[a.N], s2 = q[2 * (size_t)a.N];
+            if (sizeof(real) == 4) { s0 *= ilen[k]; s1 *= ilen[k]; s2 *= ilen[k]; }   // fp32: unit vectors once per vertex
+            real *d = sv + (size_t)k * 3 * TOPO_THREADS + tid;
+            d[0] = s0; d[TOPO_THREADS] = s1; d[2 * TOPO_THREADS] = s2;
         }
         double acc = 0.0;
+        float accf = 0.f;
         for (int t = 0; t < ncirc; t++) {
-            int i0 = tris[3 * t], i1 = tris[3 * t + 1], i2 = tris[3 * t + 2];
-            if (sizeof(real) == 4) acc += (double)tri_area_unit<real>(s[i0], s[i1], s[i2]);
-            else acc += (double)tri_area<real>(s[i0], s[i1], s[i2], l[i0], l[i1], l[i2]);
+            const real *p0 = sv + tsh[3 * t] + tid, *p1 = sv + tsh[3 * t + 1] + tid, *p2 = sv + tsh[3 * t + 2] + tid;
+            real s0[3] = {p0[0], p0[TOPO_THREADS], p0[2 * TOPO_THREADS]};
+            real s1[3] = {p1[0], p1[TOPO_THREADS], p1[2 * TOPO_THREADS]};
+            real s2[3] = {p2[0], p2[TOPO_THREADS], p2[2 * TOPO_THREADS]};
+            if (sizeof(real) == 4) accf += (float)tri_area_unit<real>(s0, s1, s2);   // a cell's few triangles: fp32 partial sum
+            else {
+                int i0 = tsh[3 * t] / (3 * TOPO_THREADS), i1 = tsh[3 * t + 1] / (3 * TOPO_THREADS), i2 = tsh[3 * t + 2] / (3 * TOPO_THREADS);
+                acc += (double)tri_area<real>(s0, s1, s2, lsh[i0], lsh[i1], lsh[i2]);
+            }
         }
-        v[0] = acc;
+        v[0] = acc + (double)accf;
     }
     block_accumulate<1>(v, sums + (size_t)r * NSUM + SUM_AREA, smem);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Block-spin ("renormalised lattice") statistics on the structured path: tuple slots 11-19 (Ising 6, 7).
+//   chosen sites   = every orbital of the cells with all-even coordinates            Lattice.py:185-196
+//   cluster        = the same orbital in the 2x2x2 cells above it                    Lattice.py:198-205
+//   coarse links   = the bond templates with doubled cell offsets, in insertion order Lattice.py:265-271, 60-66
+//   coarse energy  = 1/2 sum_k m.J_k.m_k + onsite(un-renormalised spin), where J_k is the exchange of the
+//                    k-th ORIGINAL link of the site (getCorrEnergy_rnorm, heisenbergLib.c:255-286)
+// Both link lists are insertion-ordered by (id of the bond's source site, bond index): a forward entry is made
+// when the site itself is visited, a backward entry when the source site is.  Which comes first depends on the
+// periodic wrap, so the ranks are evaluated per site from the keys instead of being tabulated.
+// ---------------------------------------------------------------------------------------------
+struct RgS {
+    int nR, n0, n1, n2, nLat, fullJ;
+    RgZones Z;
+    const RgEntD *ent;
+    const int *nent, *perm;
+    const double *J, *SD;
+    double *ms, *rsums;
+    unsigned long long meas;
+    int ps, pt, pd0, pd1, pd2;
+};
+__host__ __device__ __forceinline__ int rg_zone(int x, int L, int R, int nz) {
+    if (nz == L) return x;                       // small axis: every coordinate is its own zone
+    return x < R ? x : (x >= L - R ? x - (L - R) + R + 1 : R);
+}
+__device__ __forceinline__ int wrap_add(int v, int d, int L) { v += d; return v >= L ? v - L : v; }
+__device__ __forceinline__ int rg_row(const StructArgs &a, const RgS &g, int x, int y, int z, int o) {
+    return (((x >> 1) * g.n1 + (y >> 1)) * g.n2 + (z >> 1)) * a.norb + o;
+}
+
+template <int NC, typename real>
+__global__ void __launch_bounds__(256) k_struct_rg_majority(StructArgs a, RgS g) {
+    int r = blockIdx.y;
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= g.nR) return;
+    int o = row % a.norb, c = row / a.norb;
+    int z = 2 * (c % g.n2), y = 2 * ((c / g.n2) % g.n1), x = 2 * (c / (g.n2 * g.n1));
+    const real *sp = (const real *)a.spin + (size_t)r * NC * a.N;
+    double s[3] = {0, 0, 0};
+    const int offs[8] = {0, 1, 2, 4, 3, 5, 6, 7};   // bit2 = x, bit1 = y, bit0 = z: the member order of Lattice.py:198-205
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        int dx = (offs[k] >> 2) & 1, dy = (offs[k] >> 1) & 1, dz = offs[k] & 1;
+        if ((dx && a.Lx == 1) || (dy && a.Ly == 1) || (dz && a.Lz == 1)) continue;   // addOrbIntoCluster skips repeated members
+        int p = struct_pos(a, wrap_add(x, dx, a.Lx), wrap_add(y, dy, a.Ly), wrap_add(z, dz, a.Lz), o);
+        s[0] += sp[p];
+        if (NC >= 2) s[1] += sp[(size_t)a.N + p];
+        if (NC == 3) s[2] += sp[2 * (size_t)a.N + p];
+    }
+    double *out = g.ms + ((size_t)r * g.nR + row) * 3;
+    if (NC == 1) {
+        int po = struct_pos(a, x, y, z, o);
+        double mag = fabs((double)sp[po]), v;
+        if (s[0] > 0) v = mag;
+        else if (s[0] < 0) v = -mag;
+        else {
+            uint32_t w[4];
+            rng4(a.key, a.replica0 + r, STREAM_RG, 0, g.meas, (uint32_t)(((x * a.Ly + y) * a.Lz + z) * a.norb + o), w);
+            v = u01<double>(w[0]) > 0.5 ? mag : -mag;
+        }
+        out[0] = v; out[1] = 0; out[2] = 0;
+        return;
+    }
+    double len = sqrt(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]);
+    if (!(len < 1e-5)) { double il = 1.0 / len; s[0] *= il; s[1] *= il; s[2] *= il; }
+    double S = g.SD[4 * o];
+    out[0] = s[0] * S; out[1] = s[1] * S; out[2] = s[2] * S;
+}
+
+template <int NC, typename real>
+__global__ void __launch_bounds__(128) k_struct_rg_sums(StructArgs a, RgS g, int evenShift) {
+    __shared__ double smem[NRS * 32];
+    int r = blockIdx.y;
+    double v[NRS];
+#pragma unroll
+    for (int i = 0; i < NRS; i++) v[i] = 0.0;
+    const double *ms = g.ms + (size_t)r * g.nR * 3;
+    const real *sp = (const real *)a.spin + (size_t)r * NC * a.N;
+    const double beta = a.beta[r], hf = a.beta[r] * a.field[r];
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < g.nR; t += gridDim.x * blockDim.x) {   // one chosen site per iteration
+        int o = t % a.norb, c = t / a.norb;
+        int z = 2 * (c % g.n2), y = 2 * ((c / g.n2) % g.n1), x = 2 * (c / (g.n2 * g.n1));
+        // the insertion orders of the two link lists depend on which images wrap: one precomputed permutation per edge zone
+        int sig = ((rg_zone(x, a.Lx, g.Z.R[0], g.Z.nz[0]) * g.Z.nz[1] + rg_zone(y, a.Ly, g.Z.R[1], g.Z.nz[1])) * g.Z.nz[2] +
+                   rg_zone(z, a.Lz, g.Z.R[2], g.Z.nz[2])) * a.norb + o;
+        const int *perm = g.perm + (size_t)sig * MAXLINK;
+        const RgEntD *ent = g.ent + (size_t)o * MAXLINK;
+        const int n = g.nent[o];
+        double m[3] = {ms[3 * t], ms[3 * t + 1], ms[3 * t + 2]};
+        double corr = 0;
+        for (int k = 0; k < n; k++) {
+            const int pk = perm[k];
+            const double *Jb = g.J + (size_t)(pk >> 9) * 9;
+            const bool tr = (pk >> 8) & 1;   // J^T on the target's list (Lattice.py:136-137)
+            const RgEntD E = ent[pk & 255];
+            int nr = rg_row(a, g, wrap_add(x, E.off[0], a.Lx), wrap_add(y, E.off[1], a.Ly), wrap_add(z, E.off[2], a.Lz), E.o2);
+            double nn[3] = {ms[3 * nr], ms[3 * nr + 1], ms[3 * nr + 2]};
+            if (NC == 1) corr += Jb[0] * m[0] * nn[0];
+            else if (NC == 2) {
+                corr += m[0] * nn[0] * Jb[0] + m[1] * nn[1] * Jb[1];
+                if (g.fullJ) corr += m[0] * nn[1] * Jb[tr ? 6 : 3] + m[1] * nn[0] * Jb[tr ? 3 : 6];
+            } else {
+                corr += m[0] * nn[0] * Jb[0] + m[1] * nn[1] * Jb[1] + m[2] * nn[2] * Jb[2];
+                if (g.fullJ)
+                    corr += m[0] * nn[1] * Jb[tr ? 6 : 3] + m[0] * nn[2] * Jb[tr ? 7 : 4] + m[1] * nn[2] * Jb[tr ? 8 : 5] +
+                            m[1] * nn[0] * Jb[tr ? 3 : 6] + m[2] * nn[0] * Jb[tr ? 4 : 7] + m[2] * nn[1] * Jb[tr ? 5 : 8];
+            }
+        }
+        // on-site part with the UN-renormalised spin of the chosen site (heisenbergLib.c:799, isingLib.c:390)
+        int p = struct_pos(a, x, y, z, o);
+        double s[3] = {(double)sp[p], NC >= 2 ? (double)sp[(size_t)a.N + p] : 0.0, NC == 3 ? (double)sp[2 * (size_t)a.N + p] : 0.0};
+        double eo;
+        if (NC == 1) eo = -hf * s[0];
+        else {
+            const double *D = g.SD + 4 * o + 1;
+            eo = beta * (D[0] * s[0] * s[0] + D[1] * s[1] * s[1] + (NC == 3 ? D[2] * s[2] * s[2] : 0.0)) - hf * (NC == 3 ? s[2] : s[0]);
+        }
+        v[RS_E] += 0.5 * beta * corr + eo;
+        // coarse pair statistics (heisenbergLib.c:748-790): a correlated pair contributes its i member (cell c, orbital ps) when c
+        // is a coarse cell, its j member (cell c + kl, orbital pt) when c + kl is one - as c runs over the lattice both are
+        // exactly the coarse cells - and the product when both are, i.e. for every coarse cell if kl is even
+        if (o == g.ps) {
+            v[RS_I] += m[0]; v[RS_I + 1] += m[1]; v[RS_I + 2] += m[2];
+            if (evenShift) {
+                int rj = rg_row(a, g, wrap_add(x, g.pd0, a.Lx), wrap_add(y, g.pd1, a.Ly), wrap_add(z, g.pd2, a.Lz), g.pt);
+                v[RS_IJ] += m[0] * ms[3 * rj] + m[1] * ms[3 * rj + 1] + m[2] * ms[3 * rj + 2];
+            }
+        }
+        if (o == g.pt) { v[RS_J] += m[0]; v[RS_J + 1] += m[1]; v[RS_J + 2] += m[2]; }
+    }
+    block_accumulate<NRS>(v, g.rsums + (size_t)r * NRS, smem);
 }
 
 template <int NC, typename real>
@@ -988,12 +1169,111 @@ static void structured_build_host(mcg_system *s, const mcg_lattice_desc *d, std:
         st->gmaskHost.assign(d->group_mask, d->group_mask + (size_t)s->nG * no);
         st->groupInSC = d->group_in_sc != 0;
     }
+    // block-spin statistics (opt-in): the bond templates in the reference's order with pre-reduced offsets
+    if (d->block_spin) {
+        for (int k = 0; k < 3; k++)
+            MCG_REQUIRE(L[k] == 1 || L[k] % 2 == 0, "block_spin needs even supercell dimensions on the structured path (odd sizes: table path)");
+        for (int mult = 1; mult <= 2; mult++)      // every image of the original and of the doubled bonds must be a distinct site
+            for (int o = 0; o < no; o++) {
+                std::vector<std::array<int, 4>> seen;
+                auto visit = [&](int o2, const int *dd, int sgn) {
+                    std::array<int, 4> e = {o2, mod(sgn * mult * dd[0], L[0]), mod(sgn * mult * dd[1], L[1]), mod(sgn * mult * dd[2], L[2])};
+                    bool self = o2 == o && e[1] == 0 && e[2] == 0 && e[3] == 0;
+                    MCG_REQUIRE(!self && std::find(seen.begin(), seen.end(), e) == seen.end(),
+                                "block_spin: bond images coincide on this supercell (merged links): use the table path");
+                    seen.push_back(e);
+                };
+                for (int b = 0; b < d->nbond; b++) {
+                    int dd[3];
+                    conv(d->bonds[b].d, dd);
+                    if (d->bonds[b].src == o) visit(d->bonds[b].tgt, dd, 1);
+                    if (d->bonds[b].tgt == o) visit(d->bonds[b].src, dd, -1);
+                }
+                MCG_REQUIRE((int)seen.size() <= MAXLINK, "more than 32 links per site");
+            }
+        st->rgOn = true;
+        for (int k = 0; k < 3; k++) st->rgN[k] = (L[k] + 1) / 2;
+        st->nR = st->rgN[0] * st->rgN[1] * st->rgN[2] * no;
+        const int nb = d->nbond;
+        std::vector<std::array<int, 3>> dd(nb);
+        for (int b = 0; b < nb; b++) conv(d->bonds[b].d, dd[b].data());
+        auto sym = [&](int v, int k) { int m = mod(v, L[k]); return m > L[k] / 2 ? m - L[k] : m; };
+        for (int k = 0; k < 3; k++) {   // edge zones: wide enough for every image used by either list
+            int R = 0;
+            for (int b = 0; b < nb; b++) R = std::max({R, std::abs(sym(dd[b][k], k)), std::abs(sym(2 * dd[b][k], k))});
+            st->rgZ.R[k] = R;
+            st->rgZ.nz[k] = L[k] <= 2 * R + 1 ? L[k] : 2 * R + 1;
+        }
+        // entries of every orbital in bond order: (bond, forward | backward)
+        struct HostEnt { int b, act; };
+        std::vector<std::vector<HostEnt>> ents(no);
+        st->rgEntHost.assign((size_t)no * MAXLINK, RgEntD{0, {0, 0, 0}});
+        st->rgNentHost.assign(no, 0);
+        for (int o = 0; o < no; o++) {
+            for (int b = 0; b < nb; b++) {
+                if (d->bonds[b].src == o) ents[o].push_back({b, 0});
+                if (d->bonds[b].tgt == o) ents[o].push_back({b, 1});
+            }
+            st->rgNentHost[o] = (int)ents[o].size();
+            for (size_t e = 0; e < ents[o].size(); e++) {
+                RgEntD &E = st->rgEntHost[(size_t)o * MAXLINK + e];
+                const int b = ents[o][e].b, sgn = ents[o][e].act ? -1 : 1;
+                E.o2 = ents[o][e].act ? d->bonds[b].src : d->bonds[b].tgt;
+                for (int k = 0; k < 3; k++) E.off[k] = mod(sgn * 2 * dd[b][k], L[k]);
+            }
+        }
+        // insertion order of the original and of the doubled-bond list for one representative site per zone:
+        // key = (id of the bond's source site, bond, direction)   (Lattice.py:247-271 visit sites in id order)
+        const int nsig = st->rgZ.nz[0] * st->rgZ.nz[1] * st->rgZ.nz[2] * no;
+        st->rgPermHost.assign((size_t)nsig * MAXLINK, 0);
+        auto rep = [&](int zone, int k) {
+            const int R = st->rgZ.R[k];
+            if (st->rgZ.nz[k] == L[k]) return zone;
+            return zone < R ? zone : (zone == R ? R : L[k] - R + (zone - R - 1));
+        };
+        auto sid = [&](int x, int y, int z, int o) { return (long long)((mod(x, L[0]) * L[1] + mod(y, L[1])) * L[2] + mod(z, L[2])) * no + o; };
+        for (int zx = 0; zx < st->rgZ.nz[0]; zx++) for (int zy = 0; zy < st->rgZ.nz[1]; zy++) for (int zz = 0; zz < st->rgZ.nz[2]; zz++)
+            for (int o = 0; o < no; o++) {
+                const int x = rep(zx, 0), y = rep(zy, 1), z = rep(zz, 2);
+                const int n = (int)ents[o].size();
+                std::vector<long long> kO(n), kR(n);
+                for (int e = 0; e < n; e++) {
+                    const int b = ents[o][e].b;
+                    if (!ents[o][e].act) kO[e] = kR[e] = (sid(x, y, z, o) * nb + b) * 2;
+                    else {
+                        kO[e] = (sid(x - dd[b][0], y - dd[b][1], z - dd[b][2], d->bonds[b].src) * nb + b) * 2 + 1;
+                        kR[e] = (sid(x - 2 * dd[b][0], y - 2 * dd[b][1], z - 2 * dd[b][2], d->bonds[b].src) * nb + b) * 2 + 1;
+                    }
+                }
+                int *perm = st->rgPermHost.data() + (size_t)((((zx * st->rgZ.nz[1] + zy) * st->rgZ.nz[2] + zz) * no) + o) * MAXLINK;
+                std::vector<int> slotJ(n), slotE(n);
+                for (int e = 0; e < n; e++) {
+                    int rO = 0, rR = 0;
+                    for (int f = 0; f < n; f++) { rO += kO[f] < kO[e]; rR += kR[f] < kR[e]; }
+                    slotJ[rO] = 2 * ents[o][e].b + ents[o][e].act;   // exchange of the k-th ORIGINAL link ...
+                    slotE[rR] = e;                                   // ... paired with the k-th coarse neighbour
+                }
+                for (int k = 0; k < n; k++) perm[k] = (slotJ[k] << 8) | slotE[k];
+            }
+        st->rgJHost.assign((size_t)std::max(1, nb) * 9, 0.0);
+        for (int b = 0; b < nb; b++)
+            for (int k = 0; k < 9; k++) st->rgJHost[(size_t)b * 9 + k] = d->model == 1 ? (k == 0 ? d->bonds[b].J[0] : 0.0) : d->bonds[b].J[k];
+        for (int o = 0; o < no; o++) {
+            st->rgSDHost.push_back(d->S[o]);
+            for (int k = 0; k < 3; k++) st->rgSDHost.push_back((d->D && d->model != 1) ? d->D[3 * o + k] : 0.0);
+        }
+    }
     // measurement templates
     st->pair_s = d->pair_s; st->pair_t = d->pair_t;
     conv(d->pair_d, st->pair_d);
     for (int k = 0; k < 3; k++) st->pair_d[k] = mod(st->pair_d[k], L[k]);
     st->selfPairs = st->pair_s == st->pair_t && st->pair_d[0] == 0 && st->pair_d[1] == 0 && st->pair_d[2] == 0;
     s->nLat = L[0] * L[1] * L[2];
+    if (st->rgOn) {   // pairs with a chosen i member, a chosen j member, both (heisenbergLib.c:748-790)
+        double cells = (double)st->rgN[0] * st->rgN[1] * st->rgN[2];
+        bool evenShift = !((st->pair_d[0] | st->pair_d[1] | st->pair_d[2]) & 1);
+        st->rg_ci = cells; st->rg_cj = cells; st->rg_cij = evenShift ? cells : 0.0;
+    }
     st->ncircuit = d->model == 3 ? d->ncircuit : 0;
     s->nTri = st->ncircuit * s->nLat;
     for (int i = 0; i < st->ncircuit * 3; i++) {
@@ -1039,6 +1319,16 @@ void structured_create(mcg_system *s, const mcg_lattice_desc *d) {
     st->d_gmask = (int *)up(st->gmaskHost.data(), st->gmaskHost.size() * sizeof(int));
     st->d_tverts = (int *)up(st->tvertsHost.data(), st->tvertsHost.size() * sizeof(int));
     st->d_ttris = (int *)up(st->ttrisHost.data(), st->ttrisHost.size() * sizeof(int));
+    if (st->rgOn) {
+        st->d_rgEnt = (RgEntD *)up(st->rgEntHost.data(), st->rgEntHost.size() * sizeof(RgEntD));
+        st->d_rgNent = (int *)up(st->rgNentHost.data(), st->rgNentHost.size() * sizeof(int));
+        st->d_rgPerm = (int *)up(st->rgPermHost.data(), st->rgPermHost.size() * sizeof(int));
+        st->d_rgJ = (double *)up(st->rgJHost.data(), st->rgJHost.size() * sizeof(double));
+        st->d_rgSD = (double *)up(st->rgSDHost.data(), st->rgSDHost.size() * sizeof(double));
+        st->d_ms = (double *)pool_alloc((size_t)s->R * st->nR * 3 * sizeof(double));
+        st->d_rsums = (double *)pool_alloc((size_t)s->R * NRS * sizeof(double));
+        MCG_CUDA(cudaMemset(st->d_rsums, 0, (size_t)s->R * NRS * sizeof(double)));
+    }
     size_t cs = (size_t)s->R * st->nclass * 4 * sizeof(double);
     st->d_classSums = (double *)pool_alloc(cs);
     MCG_CUDA(cudaMemset(st->d_classSums, 0, cs));
@@ -1072,7 +1362,7 @@ int structured_jit_check(const mcg_lattice_desc *d, int precision, std::string &
 
 void structured_destroy(StructuredSystem *st) {
     if (!st) return;
-    void *bufs[] = {st->d_classes, st->d_links, st->d_J, st->d_classOf, st->d_circuits, st->d_classSums, st->d_stage, st->d_tverts, st->d_ttris, st->d_gmask};
+    void *bufs[] = {st->d_classes, st->d_links, st->d_J, st->d_classOf, st->d_circuits, st->d_classSums, st->d_stage, st->d_tverts, st->d_ttris, st->d_gmask, st->d_rgEnt, st->d_rgNent, st->d_rgPerm, st->d_rgJ, st->d_rgSD, st->d_ms, st->d_rsums};
     for (void *b : bufs) pool_free(b);
     delete st;
 }
@@ -1178,6 +1468,24 @@ template <int MODE> static void launch_pass(mcg_system *s, int colour, uint64_t 
     if (prof) { MCG_CUDA(cudaEventRecord(e1, s->stream)); s->passEvents.emplace_back(e0, e1); }
 }
 
+static void launch_block_spin(mcg_system *s, const StructArgs &a) {
+    StructuredSystem *st = s->st;
+    RgS g;
+    g.nR = st->nR; g.n0 = st->rgN[0]; g.n1 = st->rgN[1]; g.n2 = st->rgN[2]; g.nLat = s->nLat;
+    g.fullJ = s->fullJ ? 1 : 0;
+    g.Z = st->rgZ; g.ent = st->d_rgEnt; g.nent = st->d_rgNent; g.perm = st->d_rgPerm; g.J = st->d_rgJ;
+    g.SD = st->d_rgSD; g.ms = st->d_ms; g.rsums = st->d_rsums; g.meas = s->measCtr;
+    g.ps = st->pair_s; g.pt = st->pair_t; g.pd0 = st->pair_d[0]; g.pd1 = st->pair_d[1]; g.pd2 = st->pair_d[2];
+    sdispatch(s, [&]<int NC, typename real, bool FJ>() {
+        k_struct_rg_majority<NC, real><<<dim3((st->nR + 255) / 256, s->R), 256, 0, s->stream>>>(a, g);
+        k_struct_rg_sums<NC, real><<<dim3(std::min((st->nR + 127) / 128, 148 * 8), s->R), 128, 0, s->stream>>>(a, g, st->rg_cij > 0 ? 1 : 0);
+    });
+    k_extra_finalize<<<(s->R + 63) / 64, 64, 0, s->stream>>>(s->model, s->R, s->nLat, st->nR, st->rg_ci, st->rg_cj, st->rg_cij, 0, s->d_sums,
+                                                              st->d_rsums, nullptr, s->d_acc, nullptr, s->d_slot);
+    s->launches += 3;
+    s->measCtr++;
+}
+
 static void fold_and_extras(mcg_system *s) {
     StructuredSystem *st = s->st;
     StructArgs a = struct_args(s);
@@ -1193,17 +1501,23 @@ static void fold_and_extras(mcg_system *s) {
     }
     if (st->ncircuit > 0 && s->NC == 3) {
         s->launches++;
-        if (st->nvert <= TOPO_MAXV) {
-            dim3 gc((s->nLat + 255) / 256, s->R);
-            if (s->prec == 64) k_struct_topo_cells<double><<<gc, 256, 0, s->stream>>>(a, st->ncircuit, st->nvert, st->d_tverts, st->d_ttris, s->d_sums);
-            else k_struct_topo_cells<float><<<gc, 256, 0, s->stream>>>(a, st->ncircuit, st->nvert, st->d_tverts, st->d_ttris, s->d_sums);
-            MCG_CUDA(cudaGetLastError());
-            return;
+        const int npar = st->p[0] * st->p[1] * st->p[2];
+        if (st->nvert <= TOPO_MAXV && st->ncircuit <= 64 && st->Xd <= 65535 && s->R <= 65535) {
+            int tz = 1;
+            while (tz < st->Zd && tz < TOPO_THREADS) tz <<= 1;
+            const int ty = TOPO_THREADS / tz;
+            const int nzc = (st->Zd + tz - 1) / tz, nyc = (st->Yd + ty - 1) / ty;
+            dim3 gc((unsigned)(nzc * nyc * npar), (unsigned)st->Xd, (unsigned)s->R), bc(tz, ty);
+            size_t sh = (size_t)3 * st->nvert * TOPO_THREADS * (s->prec == 64 ? 8 : 4);
+            if (s->prec == 64) k_struct_topo_cells<double><<<gc, bc, sh, s->stream>>>(a, st->ncircuit, st->nvert, st->d_tverts, st->d_ttris, nzc, nyc, s->d_sums);
+            else k_struct_topo_cells<float><<<gc, bc, sh, s->stream>>>(a, st->ncircuit, st->nvert, st->d_tverts, st->d_ttris, nzc, nyc, s->d_sums);
+        } else {
+            dim3 g((s->nTri + 255) / 256, s->R);
+            if (s->prec == 64) k_struct_topo<double><<<g, 256, 0, s->stream>>>(a, st->ncircuit, st->d_circuits, s->d_sums);
+            else k_struct_topo<float><<<g, 256, 0, s->stream>>>(a, st->ncircuit, st->d_circuits, s->d_sums);
         }
-        dim3 g((s->nTri + 255) / 256, s->R);
-        if (s->prec == 64) k_struct_topo<double><<<g, 256, 0, s->stream>>>(a, st->ncircuit, st->d_circuits, s->d_sums);
-        else k_struct_topo<float><<<g, 256, 0, s->stream>>>(a, st->ncircuit, st->d_circuits, s->d_sums);
     }
+    if (st->rgOn) launch_block_spin(s, a);
     MCG_CUDA(cudaGetLastError());
 }
 

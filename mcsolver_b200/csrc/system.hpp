@@ -44,6 +44,7 @@ struct mcg_system {
     // colouring
     int C = 0;
     std::vector<int> colourStart;        // [C+1] in storage positions
+    int *d_colourStart = nullptr;        // device copy (resident kernel)
     std::vector<int32_t> site_of, pos_of;  // permutation
     std::vector<double> S_host;          // [N] signed S in reference order
     // measurement tables

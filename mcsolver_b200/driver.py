@@ -48,11 +48,12 @@ def loadMC(rpath, precision=None, seed=None, rank=0, world=1, device=-1, workdir
     algo = engine.WOLFF if p.algorithm == "Wolff" else engine.METROPOLIS
     prec = engine.default_precision() if precision is None else precision
     sd = engine.default_seed() if seed is None else seed
-    use_tables = spec.nsite <= table_limit     # full tuples (block-spin, groups) when affordable
+    use_tables = spec.nsite <= table_limit     # per-site tables exactly as the reference builds them, while affordable
+    block_spin = all(l == 1 or l % 2 == 0 for l in spec.L)   # structured path: `out` columns <..>r, <Er>, <E^2_r>
     ninterval = spec.nsite if p.ninterval <= 0 else p.ninterval
     idx, rows, frames = scan.run_points(spec, model, T, H, p.nthermal, p.nsweep, ninterval=ninterval, algorithm=algo, precision=prec,
                                         seed=sd, rank=rank, world=world, device=device, spin_frames=p.spinFrame, tables=use_tables,
-                                        want_groups=True)
+                                        want_groups=True, block_spin=block_spin)
     rows, groups = rows
     obs = scan.observables(rows, Tf[idx], spec.nsite, model)
     if rank == 0:

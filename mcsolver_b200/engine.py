@@ -120,8 +120,9 @@ class System:
         return cls(h, ta.model, ta.N, nReplica, ta.nG)
 
     @staticmethod
-    def _desc(spec, model, keep):
+    def _desc(spec, model, keep, block_spin=False):
         d = _ffi.LatticeDesc()
+        d.block_spin = int(bool(block_spin))
         d.model = int(model)
         d.L = (C.c_int32 * 3)(*spec.L)
         d.norb = spec.norb
@@ -145,10 +146,12 @@ class System:
         return d
 
     @classmethod
-    def from_spec(cls, spec, model, precision=32, nReplica=1, beta=None, field=None, seed=1, replica_offset=0, device=-1):
-        """Structured path: spec is a mcsolver_b200.lattice.LatticeSpec (bond templates + supercell)."""
+    def from_spec(cls, spec, model, precision=32, nReplica=1, beta=None, field=None, seed=1, replica_offset=0, device=-1,
+                  block_spin=False):
+        """Structured path: spec is a mcsolver_b200.lattice.LatticeSpec (bond templates + supercell).
+        block_spin=True also evaluates the block-spin statistics (tuple slots 11-19; Ising 6-7) every measured sweep."""
         keep = []
-        d = cls._desc(spec, model, keep)
+        d = cls._desc(spec, model, keep, block_spin)
         cfg = _config(precision, nReplica, beta, field, seed, replica_offset, device, keep)
         h = C.c_void_p()
         check(_ffi.lib().mcg_create_lattice(C.byref(d), C.byref(cfg), C.byref(h)))

@@ -22,11 +22,12 @@ def shard(n_points, rank, world):
 
 
 def run_points(spec, model, T, H, nthermal, nsweep, ninterval=0, algorithm=engine.METROPOLIS, precision=32, seed=1,
-               rank=0, world=1, device=-1, flunc=0.0, spin_frames=0, tables=False, want_groups=False):
+               rank=0, world=1, device=-1, flunc=0.0, spin_frames=0, tables=False, want_groups=False, block_spin=False):
     """Run the points (T[i], H[i]) owned by `rank` and return (indices, results[n,27|10], frames).
 
     spec: LatticeSpec (bond templates + supercell).  ninterval<=0 means N (mcMain.py:145).
-    tables=True forces the table-driven engine (full tuples incl. block-spin/group slots); default is the structured path.
+    tables=True forces the table-driven engine (always full tuples); default is the structured path, which fills the
+    block-spin slots 11-19 (Ising 6-7) only when block_spin=True (one more read of the configuration per sweep).
     Result rows have the reference's tuple layout with E, E2 still in beta units (caller rescales
     exactly as mcMain.py:251 does)."""
     T = np.atleast_1d(np.asarray(T, dtype=float))
@@ -49,7 +50,7 @@ def run_points(spec, model, T, H, nthermal, nsweep, ninterval=0, algorithm=engin
                                          replica_offset=lo, device=device)
     else:
         sysm = engine.System.from_spec(spec, model, precision=precision, nReplica=idx.size, beta=beta, field=field,
-                                       seed=seed, replica_offset=lo, device=device)
+                                       seed=seed, replica_offset=lo, device=device, block_spin=block_spin)
     with sysm as s:
         s.init_spins(flunc)
         frames = s.run(algorithm, nthermal, nsweep, nint, spinFrame=spin_frames)

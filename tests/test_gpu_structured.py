@@ -166,3 +166,59 @@ def test_structured_groups_in_cell_zero_only():
         out, grp = s.results()
     r = o.run(2, 2, 6, t.N, flunc=0.4, order=order, seed=5)
     assert np.max(np.abs(grp - r["group"]) / np.maximum(1.0, np.abs(r["group"]))) < 1e-9
+
+
+RG_CASES = [c for c in CASES if all(l == 1 or (l % 2 == 0 and l >= 6) for l in c[1])]
+
+
+@pytest.mark.parametrize("case", RG_CASES, ids=["%s-%s-m%d" % (c[0], "x".join(map(str, c[1])), c[3]) for c in RG_CASES])
+def test_structured_block_spin_statistics_match_table_path_and_oracle(case):
+    """block_spin=True: tuple slots 11-19 (Ising 6, 7) from computed neighbours equal the table path, whose tables are the
+    reference's own rOrb / rOrbCluster / linkedOrb_rnorm (heisenbergLib.c:255-286, 748-803), on one configuration and
+    accumulated over a short run (same trajectory on both paths: same colouring order is not required for a set configuration)."""
+    eng = _eng()
+    name, L, T, model, h = case
+    spec = spec_of(name, L)
+    t = util.tables_for(dict(spec=name, L=L, T=T, model=model))
+    hT = h / T
+    o = util.oracle_system(t, hT)
+    start = _start(o, t, model, 77)
+    slots = [6, 7] if model == 1 else util.ON_RG_SLOTS
+    with eng.System.from_tables(t, precision=64, field=[hT], seed=77) as s:
+        s.set_spins(start)
+        s.measure()
+        ref, _ = s.results()
+    with eng.System.from_spec(spec, model, precision=64, beta=[1.0 / T], field=[h], seed=77, block_spin=True) as s:
+        s.set_spins(start)
+        s.measure()
+        out, _ = s.results()
+        for k in slots:
+            if np.isnan(ref[k]):
+                assert np.isnan(out[k]), (k, out[k])
+                continue
+            assert abs(out[k] - ref[k]) <= 1e-12 * max(1.0, abs(ref[k])), (k, out[k], ref[k])
+        if model != 1:
+            oo, _ = o.observe(start)
+            for k in slots:
+                if not np.isnan(oo[k]):
+                    assert abs(out[k] - oo[k]) <= 1e-11 * max(1.0, abs(oo[k])), (k, out[k], oo[k])
+        # accumulation over a whole run against the oracle's restatement of the loop
+        order = s.colour_order()
+        s.set_spins(start)
+        s.reset_measurements()
+        s.run(0, 2, 6, t.N)
+        out, _ = s.results()
+    if model != 1:
+        r = o.run(2, 2, 6, t.N, order=order, seed=77, spins=start)
+        for k in slots:
+            if not np.isnan(r["out"][k]):
+                assert abs(out[k] - r["out"][k]) <= 1e-9 * max(1.0, abs(r["out"][k])), (k, out[k], r["out"][k])
+
+
+def test_structured_block_spin_rejects_supercells_the_descriptor_cannot_express():
+    """L = 4 folds the doubled bonds +2d and -2d onto the same site (the reference merges them, Lattice.py:60-66) and odd L
+    leaves the all-even sublattice: both are table-path cases, refused loudly rather than answered differently."""
+    eng = _eng()
+    for L in [(4, 6, 8), (5, 5, 1)]:
+        with pytest.raises(eng.McgError, match="block_spin"):
+            eng.System.from_spec(spec_of("cubic" if L[2] > 1 else "square", L), 3 if L[2] > 1 else 2, precision=64, block_spin=True)
