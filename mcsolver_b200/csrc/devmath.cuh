@@ -70,6 +70,37 @@ __device__ __forceinline__ void block_reduce_to(double (&v)[NV], double *dst, do
     __syncthreads();
 }
 
+// ---- packed fp32 pairs: Blackwell's FFMA2 / FADD2 / FMUL2 do two independent IEEE fp32 operations per instruction
+// (PTX fma/add/mul.rn.f32x2, sm_100+).  The colour pass works on V = 4 consecutive sites per thread, so its per-site
+// arithmetic pairs up naturally; each lane rounds exactly like the scalar instruction.
+struct __align__(8) F2 { float x, y; };
+__device__ __forceinline__ unsigned long long f2_pack(F2 a) {
+    unsigned long long u;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(u) : "f"(a.x), "f"(a.y));
+    return u;
+}
+__device__ __forceinline__ F2 f2_unpack(unsigned long long u) {
+    F2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(u));
+    return r;
+}
+__device__ __forceinline__ F2 splat2(float v) { return F2{v, v}; }
+__device__ __forceinline__ F2 fma2(F2 a, F2 b, F2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)), "l"(f2_pack(c)));
+    return f2_unpack(d);
+}
+__device__ __forceinline__ F2 mul2(F2 a, F2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+    return f2_unpack(d);
+}
+__device__ __forceinline__ F2 add2(F2 a, F2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+    return f2_unpack(d);
+}
+
 template <typename real> __device__ __forceinline__ real r_sqrt(real x);
 template <> __device__ __forceinline__ float r_sqrt<float>(float x) {
     float y;   // one MUFU.SQRT; sqrtf() expands to a guarded Newton sequence with a slow-path call

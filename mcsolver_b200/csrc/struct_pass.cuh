@@ -191,6 +191,138 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
         const int xy = ((X * px + cls.ca()) * Ly + (Y * py + cls.cb())) * Lz;
         for (int zc = threadIdx.x; zc < Zc; zc += blockDim.x) {
             const int Z0 = zc * V;
+#ifndef MCG_NO_F32X2
+            if constexpr (NC == 3 && sizeof(real) == 4 && V == 4) {
+                // ---- Heisenberg fp32: the four sites of the item as two packed pairs (sites 0,1 and 2,3) ----
+                // Same formulas as the scalar branch below, with the plane normal taken as m = -n: the reflection
+                // s' = s - 2 (s.m) m and its energy are even in the normal, so no sign has to be applied to the
+                // sine/cosine pair and the move is bit-identical.
+                F2 s2[3][2], H2[3][2], Hl2[3][2];
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+#pragma unroll
+                    for (int p = 0; p < 2; p++) { H2[c][p] = F2{0.f, 0.f}; Hl2[c][p] = F2{0.f, 0.f}; }
+                const float *own = (const float *)sp + rowBase + Z0;
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const float4 q4 = *reinterpret_cast<const float4 *>(own + (size_t)c * N);
+                    s2[c][0] = F2{q4.x, q4.y}; s2[c][1] = F2{q4.z, q4.w};
+                }
+                cls.for_links([&](auto L) {
+                    const int nb = rowBase + L.delta() + L.mxp() * wxp + L.mxm() * wxm + L.myp() * wyp + L.mym() * wym;
+                    float t[3][4];
+#pragma unroll
+                    for (int c = 0; c < 3; c++) load_shifted<float, 4>((const float *)sp + (size_t)c * N + nb, Z0, L.cZ(), Zd, t[c]);
+                    const bool lowk = MODE == 1 && lowmode == 2 && L.low();
+                    if (!FULLJ && L.cZ() == 0) {   // aligned row, diagonal exchange: packed multiply-add straight from the float4
+#pragma unroll
+                        for (int c = 0; c < 3; c++)
+#pragma unroll
+                            for (int p = 0; p < 2; p++) {
+                                const F2 t2 = F2{t[c][2 * p], t[c][2 * p + 1]};
+                                const F2 J2 = splat2((float)L.J(c));
+                                H2[c][p] = fma2(J2, t2, H2[c][p]);
+                                if (lowk) Hl2[c][p] = fma2(J2, t2, Hl2[c][p]);
+                            }
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < 4; v++) {
+                            const float tx = t[0][v], ty = t[1][v], tz = t[2][v];
+                            float hx, hy, hz;
+                            if (FULLJ) {
+                                hx = (float)L.J(0) * tx + (float)L.J(3) * ty + (float)L.J(4) * tz;
+                                hy = (float)L.J(6) * tx + (float)L.J(1) * ty + (float)L.J(5) * tz;
+                                hz = (float)L.J(7) * tx + (float)L.J(8) * ty + (float)L.J(2) * tz;
+                            } else { hx = (float)L.J(0) * tx; hy = (float)L.J(1) * ty; hz = (float)L.J(2) * tz; }
+                            float &Hx = (v & 1) ? H2[0][v >> 1].y : H2[0][v >> 1].x;
+                            float &Hy = (v & 1) ? H2[1][v >> 1].y : H2[1][v >> 1].x;
+                            float &Hz = (v & 1) ? H2[2][v >> 1].y : H2[2][v >> 1].x;
+                            Hx += hx; Hy += hy; Hz += hz;
+                            if (lowk) {
+                                float &Lx_ = (v & 1) ? Hl2[0][v >> 1].y : Hl2[0][v >> 1].x;
+                                float &Ly_ = (v & 1) ? Hl2[1][v >> 1].y : Hl2[1][v >> 1].x;
+                                float &Lz_ = (v & 1) ? Hl2[2][v >> 1].y : Hl2[2][v >> 1].x;
+                                Lx_ += hx; Ly_ += hy; Lz_ += hz;
+                            }
+                        }
+                    }
+                });
+                const uint32_t id0 = (uint32_t)((xy + Z0 * pz + cls.cc()) * norb + cls.co());
+                const float fbeta = (float)beta, fhf = (float)hf, fS = (float)S;
+                F2 aM[3] = {F2{0.f, 0.f}, F2{0.f, 0.f}, F2{0.f, 0.f}}, aE = F2{0.f, 0.f};
+#pragma unroll
+                for (int p = 0; p < 2; p++) {
+                    uint32_t wa[4], wb[4];
+                    rng4(a.key, a.replica0 + r, STREAM_METRO, 0, sweep, id0 + (uint32_t)((2 * p) * idStrideZ), wa);
+                    rng4(a.key, a.replica0 + r, STREAM_METRO, 0, sweep, id0 + (uint32_t)((2 * p + 1) * idStrideZ), wb);
+                    const F2 sx = s2[0][p], sy = s2[1][p], sz = s2[2][p];
+                    const F2 hx = H2[0][p], hy = H2[1][p], hz = H2[2][p];
+                    // proposal plane normal m = -n of random_dir<3>: m = (r cos(phi), r sin(phi), -z), z = 2u-1, phi = 2 pi (u'-1/2)
+                    const F2 u0 = F2{u01<float>(wa[0]), u01<float>(wb[0])}, u1 = F2{u01<float>(wa[1]), u01<float>(wb[1])};
+                    const F2 m2 = fma2(u0, splat2(-2.f), splat2(1.f));
+                    const F2 zp = fma2(u0, splat2(2.f), splat2(-1.f));
+                    const F2 om = fma2(m2, zp, splat2(1.f));                     // 1 - z*z
+                    const F2 ph = mul2(add2(u1, splat2(-0.5f)), splat2(6.283185307179586f));
+                    float sa, ca, sb, cb;
+                    __sincosf(ph.x, &sa, &ca);
+                    __sincosf(ph.y, &sb, &cb);
+                    const F2 rr = F2{r_sqrt<float>(om.x), r_sqrt<float>(om.y)};
+                    const F2 m0 = mul2(rr, F2{ca, cb}), m1 = mul2(rr, F2{sa, sb});
+                    // heisenbergLib.c:451-456 with s1m = -2 (s.m): transSpin = s1m m, dE = s1m (beta m.H - hf m_z) + on-site difference
+                    const F2 sm = fma2(sz, m2, fma2(sy, m1, mul2(sx, m0)));
+                    const F2 s1m = mul2(sm, splat2(-2.f));
+                    const F2 mH = fma2(m2, hz, fma2(m1, hy, mul2(m0, hx)));
+                    F2 dE = mul2(s1m, fma2(m2, splat2(-fhf), mul2(mH, splat2(fbeta))));
+                    if (hasD) {
+                        const F2 nx = fma2(s1m, m0, sx), ny = fma2(s1m, m1, sy), nz = fma2(s1m, m2, sz);
+                        const F2 neg1 = splat2(-1.f);
+                        F2 dOn = mul2(splat2((float)D0), fma2(mul2(sx, sx), neg1, mul2(nx, nx)));
+                        dOn = fma2(splat2((float)D1), fma2(mul2(sy, sy), neg1, mul2(ny, ny)), dOn);
+                        dOn = fma2(splat2((float)D2), fma2(mul2(sz, sz), neg1, mul2(nz, nz)), dOn);
+                        dE = fma2(splat2(fbeta), dOn, dE);
+                    }
+                    // heisenbergLib.c:461 accepts if dE <= 0 or exp(-dE) > u; u < 1 <= exp(-dE) for dE <= 0, so one test decides
+                    const F2 ex = mul2(dE, splat2(-1.4426950408889634f));
+                    float ea, eb_;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea) : "f"(ex.x));
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb_) : "f"(ex.y));
+                    const bool atta = PARTIAL ? (u01<float>(wa[3]) < (float)pAtt) : true;
+                    const bool attb = PARTIAL ? (u01<float>(wb[3]) < (float)pAtt) : true;
+                    const bool acca = atta & (ea > u01<float>(wa[2])), accb = attb & (eb_ > u01<float>(wb[2]));
+                    const F2 ms = F2{acca ? s1m.x : 0.f, accb ? s1m.y : 0.f};   // rejected: s + 0*m = s exactly
+                    F2 tx = fma2(ms, m0, sx), ty = fma2(ms, m1, sy), tz = fma2(ms, m2, sz);
+                    if (renorm) {   // every site, accepted or not
+                        const F2 n2 = fma2(tz, tz, fma2(ty, ty, mul2(tx, tx)));
+                        const F2 f = mul2(F2{r_rsqrt<float>(n2.x), r_rsqrt<float>(n2.y)}, splat2(fS));
+                        tx = mul2(tx, f); ty = mul2(ty, f); tz = mul2(tz, f);
+                    }
+                    if (PARTIAL) natt += (atta ? 1 : 0) + (attb ? 1 : 0);
+                    nacc += (acca ? 1 : 0) + (accb ? 1 : 0);
+                    s2[0][p] = tx; s2[1][p] = ty; s2[2][p] = tz;
+                    if (MODE == 1) {
+                        aM[0] = add2(aM[0], tx); aM[1] = add2(aM[1], ty); aM[2] = add2(aM[2], tz);
+                        F2 e = fma2(tz, splat2(-fhf), aE);
+                        if (lowmode == 1) e = fma2(splat2(fbeta), fma2(tz, hz, fma2(ty, hy, mul2(tx, hx))), e);
+                        else if (lowmode == 2) e = fma2(splat2(fbeta), fma2(tz, Hl2[2][p], fma2(ty, Hl2[1][p], mul2(tx, Hl2[0][p]))), e);
+                        if (hasD) {
+                            const F2 on = fma2(splat2((float)D2), mul2(tz, tz), fma2(splat2((float)D1), mul2(ty, ty), mul2(splat2((float)D0), mul2(tx, tx))));
+                            e = fma2(splat2(fbeta), on, e);
+                        }
+                        aE = e;
+                    }
+                }
+                if (MODE == 1) {
+                    accM[0] += (real)(aM[0].x + aM[0].y); accM[1] += (real)(aM[1].x + aM[1].y); accM[2] += (real)(aM[2].x + aM[2].y);
+                    accE += (real)(aE.x + aE.y);
+                }
+                if (!PARTIAL) natt += V;
+                float *ownw = (float *)sp + rowBase + Z0;
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+                    *reinterpret_cast<float4 *>(ownw + (size_t)c * N) = make_float4(s2[c][0].x, s2[c][0].y, s2[c][1].x, s2[c][1].y);
+                continue;
+            }
+#endif
             real s[3][V], H[3][V], Hl[3][V];
 #pragma unroll
             for (int c = 0; c < 3; c++)
