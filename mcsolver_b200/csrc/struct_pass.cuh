@@ -108,7 +108,7 @@ template <typename real> struct PLink {
     real J[9];
 };
 template <typename real> struct PassTable {
-    int nl, nqc, pad0, pad1;
+    int nl, nqc, uniformJ, pad1;   // uniformJ: every link of every class of the pass carries the same diagonal exchange
     int ca[PT_MAXC], cb[PT_MAXC], cc[PT_MAXC], co[PT_MAXC], lowmode[PT_MAXC];
     real S[PT_MAXC], D[PT_MAXC][3];
     PLink<real> L[PT_MAXC][PT_MAXL];
@@ -137,6 +137,7 @@ template <typename real> struct RtClass {
     __device__ __forceinline__ int lowmode() const { return T.lowmode[j]; }
     __device__ __forceinline__ real S() const { return T.S[j]; }
     __device__ __forceinline__ real D(int e) const { return T.D[j][e]; }
+    __device__ __forceinline__ bool uniformJ() const { return T.uniformJ != 0; }
     template <typename F> __device__ __forceinline__ void for_links(F &&f) const {
         const int n = T.nl;
         for (int k = 0; k < n; k++) f(RtLink<real>{T.L[j][k]});
@@ -192,8 +193,8 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
         for (int zc = threadIdx.x; zc < Zc; zc += blockDim.x) {
             const int Z0 = zc * V;
 #ifndef MCG_NO_F32X2
-            if constexpr (NC == 3 && sizeof(real) == 4 && V == 4) {
-                // ---- Heisenberg fp32: the four sites of the item as two packed pairs (sites 0,1 and 2,3) ----
+            if constexpr (NC >= 2 && sizeof(real) == 4 && V == 4) {
+                // ---- XY / Heisenberg fp32: the four sites of the item as two packed pairs (sites 0,1 and 2,3) ----
                 // Same formulas as the scalar branch below, with the plane normal taken as m = -n: the reflection
                 // s' = s - 2 (s.m) m and its energy are even in the normal, so no sign has to be applied to the
                 // sine/cosine pair and the move is bit-identical.
@@ -201,10 +202,10 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
 #pragma unroll
                 for (int c = 0; c < 3; c++)
 #pragma unroll
-                    for (int p = 0; p < 2; p++) { H2[c][p] = F2{0.f, 0.f}; Hl2[c][p] = F2{0.f, 0.f}; }
+                    for (int p = 0; p < 2; p++) { s2[c][p] = F2{0.f, 0.f}; H2[c][p] = F2{0.f, 0.f}; Hl2[c][p] = F2{0.f, 0.f}; }
                 const float *own = (const float *)sp + rowBase + Z0;
 #pragma unroll
-                for (int c = 0; c < 3; c++) {
+                for (int c = 0; c < NC; c++) {
                     const float4 q4 = *reinterpret_cast<const float4 *>(own + (size_t)c * N);
                     s2[c][0] = F2{q4.x, q4.y}; s2[c][1] = F2{q4.z, q4.w};
                 }
@@ -212,11 +213,14 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                     const int nb = rowBase + L.delta() + L.mxp() * wxp + L.mxm() * wxm + L.myp() * wyp + L.mym() * wym;
                     float t[3][4];
 #pragma unroll
-                    for (int c = 0; c < 3; c++) load_shifted<float, 4>((const float *)sp + (size_t)c * N + nb, Z0, L.cZ(), Zd, t[c]);
+                    for (int c = 0; c < NC; c++) load_shifted<float, 4>((const float *)sp + (size_t)c * N + nb, Z0, L.cZ(), Zd, t[c]);
                     const bool lowk = MODE == 1 && lowmode == 2 && L.low();
-                    if (!FULLJ && L.cZ() == 0) {   // aligned row, diagonal exchange: packed multiply-add straight from the float4
+                    // aligned row, one diagonal exchange shared by every link of the class (its splat lives in one register
+                    // pair): packed multiply-add straight from the float4.  Distinct tensors per link would each need their
+                    // constant moved into a pair, where the scalar FFMA takes it as an immediate - measured slower (CrI3).
+                    if (!FULLJ && cls.uniformJ() && L.cZ() == 0) {
 #pragma unroll
-                        for (int c = 0; c < 3; c++)
+                        for (int c = 0; c < NC; c++)
 #pragma unroll
                             for (int p = 0; p < 2; p++) {
                                 const F2 t2 = F2{t[c][2 * p], t[c][2 * p + 1]};
@@ -227,22 +231,25 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                     } else {
 #pragma unroll
                         for (int v = 0; v < 4; v++) {
-                            const float tx = t[0][v], ty = t[1][v], tz = t[2][v];
-                            float hx, hy, hz;
-                            if (FULLJ) {
+                            const float tx = t[0][v], ty = t[1][v], tz = NC == 3 ? t[2][v] : 0.f;
+                            float hx, hy, hz = 0.f;
+                            if (NC == 2) {
+                                if (FULLJ) { hx = (float)L.J(0) * tx + (float)L.J(3) * ty; hy = (float)L.J(6) * tx + (float)L.J(1) * ty; }
+                                else { hx = (float)L.J(0) * tx; hy = (float)L.J(1) * ty; }
+                            } else if (FULLJ) {
                                 hx = (float)L.J(0) * tx + (float)L.J(3) * ty + (float)L.J(4) * tz;
                                 hy = (float)L.J(6) * tx + (float)L.J(1) * ty + (float)L.J(5) * tz;
                                 hz = (float)L.J(7) * tx + (float)L.J(8) * ty + (float)L.J(2) * tz;
                             } else { hx = (float)L.J(0) * tx; hy = (float)L.J(1) * ty; hz = (float)L.J(2) * tz; }
                             float &Hx = (v & 1) ? H2[0][v >> 1].y : H2[0][v >> 1].x;
                             float &Hy = (v & 1) ? H2[1][v >> 1].y : H2[1][v >> 1].x;
-                            float &Hz = (v & 1) ? H2[2][v >> 1].y : H2[2][v >> 1].x;
-                            Hx += hx; Hy += hy; Hz += hz;
+                            Hx += hx; Hy += hy;
+                            if (NC == 3) { float &Hz = (v & 1) ? H2[2][v >> 1].y : H2[2][v >> 1].x; Hz += hz; }
                             if (lowk) {
                                 float &Lx_ = (v & 1) ? Hl2[0][v >> 1].y : Hl2[0][v >> 1].x;
                                 float &Ly_ = (v & 1) ? Hl2[1][v >> 1].y : Hl2[1][v >> 1].x;
-                                float &Lz_ = (v & 1) ? Hl2[2][v >> 1].y : Hl2[2][v >> 1].x;
-                                Lx_ += hx; Ly_ += hy; Lz_ += hz;
+                                Lx_ += hx; Ly_ += hy;
+                                if (NC == 3) { float &Lz_ = (v & 1) ? Hl2[2][v >> 1].y : Hl2[2][v >> 1].x; Lz_ += hz; }
                             }
                         }
                     }
@@ -257,28 +264,36 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                     rng4(a.key, a.replica0 + r, STREAM_METRO, 0, sweep, id0 + (uint32_t)((2 * p + 1) * idStrideZ), wb);
                     const F2 sx = s2[0][p], sy = s2[1][p], sz = s2[2][p];
                     const F2 hx = H2[0][p], hy = H2[1][p], hz = H2[2][p];
-                    // proposal plane normal m = -n of random_dir<3>: m = (r cos(phi), r sin(phi), -z), z = 2u-1, phi = 2 pi (u'-1/2)
-                    const F2 u0 = F2{u01<float>(wa[0]), u01<float>(wb[0])}, u1 = F2{u01<float>(wa[1]), u01<float>(wb[1])};
-                    const F2 m2 = fma2(u0, splat2(-2.f), splat2(1.f));
-                    const F2 zp = fma2(u0, splat2(2.f), splat2(-1.f));
-                    const F2 om = fma2(m2, zp, splat2(1.f));                     // 1 - z*z
-                    const F2 ph = mul2(add2(u1, splat2(-0.5f)), splat2(6.283185307179586f));
+                    // plane normal m = -n of random_dir: O(3) m = (r cos phi, r sin phi, -z), z = 2u-1; O(2) m = (cos phi, sin phi);
+                    // phi = 2 pi (u' - 1/2) from the second (O(3)) / first (O(2)) Philox word
+                    const F2 uphi = NC == 3 ? F2{u01<float>(wa[1]), u01<float>(wb[1])} : F2{u01<float>(wa[0]), u01<float>(wb[0])};
+                    const F2 ph = mul2(add2(uphi, splat2(-0.5f)), splat2(6.283185307179586f));
                     float sa, ca, sb, cb;
                     __sincosf(ph.x, &sa, &ca);
                     __sincosf(ph.y, &sb, &cb);
-                    const F2 rr = F2{r_sqrt<float>(om.x), r_sqrt<float>(om.y)};
-                    const F2 m0 = mul2(rr, F2{ca, cb}), m1 = mul2(rr, F2{sa, sb});
-                    // heisenbergLib.c:451-456 with s1m = -2 (s.m): transSpin = s1m m, dE = s1m (beta m.H - hf m_z) + on-site difference
-                    const F2 sm = fma2(sz, m2, fma2(sy, m1, mul2(sx, m0)));
+                    F2 m0 = F2{ca, cb}, m1 = F2{sa, sb}, m2 = F2{0.f, 0.f};
+                    if (NC == 3) {
+                        const F2 u0 = F2{u01<float>(wa[0]), u01<float>(wb[0])};
+                        m2 = fma2(u0, splat2(-2.f), splat2(1.f));
+                        const F2 zp = fma2(u0, splat2(2.f), splat2(-1.f));
+                        const F2 om = fma2(m2, zp, splat2(1.f));                     // 1 - z*z
+                        const F2 rr = F2{r_sqrt<float>(om.x), r_sqrt<float>(om.y)};
+                        m0 = mul2(rr, m0); m1 = mul2(rr, m1);
+                    }
+                    // heisenbergLib.c:451-456 with s1m = -2 (s.m): transSpin = s1m m, dE = s1m (beta m.H - hf m_axis) + on-site difference
+                    F2 sm = fma2(sy, m1, mul2(sx, m0)), mH = fma2(m1, hy, mul2(m0, hx));
+                    if (NC == 3) { sm = fma2(sz, m2, sm); mH = fma2(m2, hz, mH); }
                     const F2 s1m = mul2(sm, splat2(-2.f));
-                    const F2 mH = fma2(m2, hz, fma2(m1, hy, mul2(m0, hx)));
-                    F2 dE = mul2(s1m, fma2(m2, splat2(-fhf), mul2(mH, splat2(fbeta))));
+                    F2 dE = mul2(s1m, fma2(NC == 3 ? m2 : m0, splat2(-fhf), mul2(mH, splat2(fbeta))));
                     if (hasD) {
-                        const F2 nx = fma2(s1m, m0, sx), ny = fma2(s1m, m1, sy), nz = fma2(s1m, m2, sz);
+                        const F2 nx = fma2(s1m, m0, sx), ny = fma2(s1m, m1, sy);
                         const F2 neg1 = splat2(-1.f);
                         F2 dOn = mul2(splat2((float)D0), fma2(mul2(sx, sx), neg1, mul2(nx, nx)));
                         dOn = fma2(splat2((float)D1), fma2(mul2(sy, sy), neg1, mul2(ny, ny)), dOn);
-                        dOn = fma2(splat2((float)D2), fma2(mul2(sz, sz), neg1, mul2(nz, nz)), dOn);
+                        if (NC == 3) {
+                            const F2 nz = fma2(s1m, m2, sz);
+                            dOn = fma2(splat2((float)D2), fma2(mul2(sz, sz), neg1, mul2(nz, nz)), dOn);
+                        }
                         dE = fma2(splat2(fbeta), dOn, dE);
                     }
                     // heisenbergLib.c:461 accepts if dE <= 0 or exp(-dE) > u; u < 1 <= exp(-dE) for dE <= 0, so one test decides
@@ -290,22 +305,33 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                     const bool attb = PARTIAL ? (u01<float>(wb[3]) < (float)pAtt) : true;
                     const bool acca = atta & (ea > u01<float>(wa[2])), accb = attb & (eb_ > u01<float>(wb[2]));
                     const F2 ms = F2{acca ? s1m.x : 0.f, accb ? s1m.y : 0.f};   // rejected: s + 0*m = s exactly
-                    F2 tx = fma2(ms, m0, sx), ty = fma2(ms, m1, sy), tz = fma2(ms, m2, sz);
+                    F2 tx = fma2(ms, m0, sx), ty = fma2(ms, m1, sy), tz = NC == 3 ? fma2(ms, m2, sz) : sz;
                     if (renorm) {   // every site, accepted or not
-                        const F2 n2 = fma2(tz, tz, fma2(ty, ty, mul2(tx, tx)));
+                        F2 n2 = fma2(ty, ty, mul2(tx, tx));
+                        if (NC == 3) n2 = fma2(tz, tz, n2);
                         const F2 f = mul2(F2{r_rsqrt<float>(n2.x), r_rsqrt<float>(n2.y)}, splat2(fS));
-                        tx = mul2(tx, f); ty = mul2(ty, f); tz = mul2(tz, f);
+                        tx = mul2(tx, f); ty = mul2(ty, f);
+                        if (NC == 3) tz = mul2(tz, f);
                     }
                     if (PARTIAL) natt += (atta ? 1 : 0) + (attb ? 1 : 0);
                     nacc += (acca ? 1 : 0) + (accb ? 1 : 0);
                     s2[0][p] = tx; s2[1][p] = ty; s2[2][p] = tz;
                     if (MODE == 1) {
-                        aM[0] = add2(aM[0], tx); aM[1] = add2(aM[1], ty); aM[2] = add2(aM[2], tz);
-                        F2 e = fma2(tz, splat2(-fhf), aE);
-                        if (lowmode == 1) e = fma2(splat2(fbeta), fma2(tz, hz, fma2(ty, hy, mul2(tx, hx))), e);
-                        else if (lowmode == 2) e = fma2(splat2(fbeta), fma2(tz, Hl2[2][p], fma2(ty, Hl2[1][p], mul2(tx, Hl2[0][p]))), e);
+                        aM[0] = add2(aM[0], tx); aM[1] = add2(aM[1], ty);
+                        if (NC == 3) aM[2] = add2(aM[2], tz);
+                        F2 e = fma2(NC == 3 ? tz : tx, splat2(-fhf), aE);
+                        if (lowmode == 1) {
+                            F2 eb2 = fma2(ty, hy, mul2(tx, hx));
+                            if (NC == 3) eb2 = fma2(tz, hz, eb2);
+                            e = fma2(splat2(fbeta), eb2, e);
+                        } else if (lowmode == 2) {
+                            F2 eb2 = fma2(ty, Hl2[1][p], mul2(tx, Hl2[0][p]));
+                            if (NC == 3) eb2 = fma2(tz, Hl2[2][p], eb2);
+                            e = fma2(splat2(fbeta), eb2, e);
+                        }
                         if (hasD) {
-                            const F2 on = fma2(splat2((float)D2), mul2(tz, tz), fma2(splat2((float)D1), mul2(ty, ty), mul2(splat2((float)D0), mul2(tx, tx))));
+                            F2 on = fma2(splat2((float)D1), mul2(ty, ty), mul2(splat2((float)D0), mul2(tx, tx)));
+                            if (NC == 3) on = fma2(splat2((float)D2), mul2(tz, tz), on);
                             e = fma2(splat2(fbeta), on, e);
                         }
                         aE = e;
@@ -318,7 +344,7 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                 if (!PARTIAL) natt += V;
                 float *ownw = (float *)sp + rowBase + Z0;
 #pragma unroll
-                for (int c = 0; c < 3; c++)
+                for (int c = 0; c < NC; c++)
                     *reinterpret_cast<float4 *>(ownw + (size_t)c * N) = make_float4(s2[c][0].x, s2[c][0].y, s2[c][1].x, s2[c][1].y);
                 continue;
             }
@@ -475,6 +501,13 @@ template <int JJ> struct CtClass {
     __device__ __forceinline__ constexpr int lowmode() const { return C::lowmode; }
     __device__ __forceinline__ constexpr jit_real S() const { return C::S; }
     __device__ __forceinline__ constexpr jit_real D(int e) const { return C::D(e); }
+    template <int K> static __device__ __forceinline__ constexpr bool uj_from() {
+        if constexpr (K >= C::nl) return true;
+        else
+            return CtLinkData<JJ, K>::J(0) == CtLinkData<JJ, 0>::J(0) && CtLinkData<JJ, K>::J(1) == CtLinkData<JJ, 0>::J(1) &&
+                   CtLinkData<JJ, K>::J(2) == CtLinkData<JJ, 0>::J(2) && uj_from<K + 1>();
+    }
+    __device__ __forceinline__ constexpr bool uniformJ() const { return uj_from<0>(); }
     template <typename F> __device__ __forceinline__ void for_links(F &&f) const {
         ct_for<0, C::nl>([&](auto k) { f(CtLink<JJ, decltype(k)::value>{}); });
     }

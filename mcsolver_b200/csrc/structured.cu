@@ -764,6 +764,7 @@ std::string jit_prologue(const mcg_system *s, int colour, bool partial) {
     const int JW = s->NC == 1 ? 1 : 9;
     std::ostringstream o;
     o << "#define MCG_JIT 1\ntypedef " << (f32 ? "float" : "double") << " jit_real;\n";
+    if (getenv("MCG_NO_F32X2")) o << "#define MCG_NO_F32X2 1\n";   // A/B switch: scalar fp32 arithmetic instead of packed pairs
     o << "#define JIT_NC " << s->NC << "\n#define JIT_FULLJ " << (s->fullJ ? "true" : "false") << "\n#define JIT_V " << st->V
       << "\n#define JIT_PARTIAL " << (partial ? "true" : "false") << "\n#define JIT_NQC " << nqc << "\n#define JIT_MINB " << (getenv("MCG_JIT_MINB") ? atoi(getenv("MCG_JIT_MINB")) : (f32 ? 4 : 2)) << "\n";
     o << "#define JIT_Xd " << st->Xd << "\n#define JIT_Yd " << st->Yd << "\n#define JIT_Zd " << st->Zd << "\n#define JIT_Zc "
@@ -1138,6 +1139,11 @@ static void structured_build_host(mcg_system *s, const mcg_lattice_desc *d, std:
         std::vector<char> buf(sizeof(PassTable<real>), 0);
         PassTable<real> *P = reinterpret_cast<PassTable<real> *>(buf.data());
         P->nl = nlp; P->nqc = nqc;
+        P->uniformJ = 1;
+        for (int j = 0; j < nqc; j++)
+            for (int k = 0; k < st->classes[q0 + j].nlink; k++)
+                for (int c = 0; c < 3 && JW == 9; c++)
+                    if (Jt[((size_t)(q0 + j) * MAXLINK + k) * JW + c] != Jt[(size_t)q0 * MAXLINK * JW + c]) P->uniformJ = 0;
         for (int j = 0; j < nqc; j++) {
             const SClassD &cl = st->classes[q0 + j];
             P->ca[j] = cl.a; P->cb[j] = cl.b; P->cc[j] = cl.c; P->co[j] = cl.o; P->lowmode[j] = cl.lowmode;

@@ -12,7 +12,13 @@ PEAK = 6547.5e9
 rows = []
 
 
+ONLY = os.environ.get("ONLY", "")
+
+
 def run(name, spec, model, R, T, H=None, z=None, nsw=10, meas=True):
+    if ONLY and not any(name.startswith(o) for o in ONLY.split(",")):
+        return
+    spec = spec() if callable(spec) else spec
     H = np.zeros(R) if H is None else H
     with engine.System.from_spec(spec, model, precision=32, nReplica=R, beta=1 / np.asarray(T, float), field=H, seed=1) as s:
         C = s.num_colours()
@@ -30,10 +36,11 @@ def run(name, spec, model, R, T, H=None, z=None, nsw=10, meas=True):
 
 sq = lambda L: LatticeSpec(L=(L, L, 1), S=[1.0], bonds=[(0, 0, (1, 0, 0), J), (0, 0, (0, 1, 0), J)])
 cu = lambda L: LatticeSpec(L=(L, L, L), S=[1.0], bonds=[(0, 0, (1, 0, 0), J), (0, 0, (0, 1, 0), J), (0, 0, (0, 0, 1), J)])
-run("C1 XY square 4096^2 T-scan", sq(4096), 2, 8, np.linspace(0.9, 1.2, 8), z=4)
-run("C2 Ising square 4096^2 T-scan", sq(4096), 1, 16, np.linspace(2.0, 2.6, 16), z=4)
-run("C3 CrI3 honeycomb 512^2 (1NN+2NN+3NN, D)", spec_of("cri3", (512, 512, 1)), 3, 21, np.linspace(30, 50, 21), z=12)
-run("C4 skyrmion hex 1024^2 (DMI, D, h, Q)", spec_of("skyrmion", (1024, 1024, 1)), 3, 16, np.full(16, 0.3), H=np.linspace(0, 0.7, 16), z=3)
-run("C5 Heisenberg sc 256^3 T-scan", cu(256), 3, 8, 0.8 * 1.443 * (1.3 / 0.8) ** (np.arange(8) / 7), z=6)
-run("C5 + dipole stencil r<=2 (32 links), 128^3", add_dipole_stencil(cu(128), 0.1, 2.0), 3, 8, np.linspace(1.2, 1.9, 8), z=32, nsw=4)
-json.dump(rows, open("gpurun_out/configs_r1.json", "w"), indent=1)
+run("C1 XY square 4096^2 T-scan", lambda: sq(4096), 2, 8, np.linspace(0.9, 1.2, 8), z=4)
+run("C2 Ising square 4096^2 T-scan", lambda: sq(4096), 1, 16, np.linspace(2.0, 2.6, 16), z=4)
+run("C3 CrI3 honeycomb 512^2 (1NN+2NN+3NN, D)", lambda: spec_of("cri3", (512, 512, 1)), 3, 21, np.linspace(30, 50, 21), z=12)
+run("C4 skyrmion hex 1024^2 (DMI, D, h, Q)", lambda: spec_of("skyrmion", (1024, 1024, 1)), 3, 16, np.full(16, 0.3), H=np.linspace(0, 0.7, 16), z=3)
+run("C5 Heisenberg sc 256^3 T-scan", lambda: cu(256), 3, 8, 0.8 * 1.443 * (1.3 / 0.8) ** (np.arange(8) / 7), z=6)
+run("C5 + dipole stencil r<=2 (32 links), 128^3", lambda: add_dipole_stencil(cu(128), 0.1, 2.0), 3, 8, np.linspace(1.2, 1.9, 8), z=32, nsw=4)
+if not ONLY:
+    json.dump(rows, open("gpurun_out/configs_r1.json", "w"), indent=1)
