@@ -269,10 +269,11 @@ class System:
 # ---------------------------------------------------------------------------------------------
 # legacy one-shot calls: positional tuples in, reference-layout tuples out
 # ---------------------------------------------------------------------------------------------
-def jit_check(spec, model, precision=32):
-    """Host-only: NVRTC-compile the specialised pass kernels of a lattice; returns (n_modules, report)."""
+def jit_check(spec, model, precision=32, block_spin=False):
+    """Host-only: build the class tables of a lattice (incl. the block-spin tables when asked) and NVRTC-compile its
+    specialised pass kernels; returns (n_modules, report)."""
     keep = []
-    d = System._desc(spec, model, keep)
+    d = System._desc(spec, model, keep, block_spin)
     n = C.c_int(0)
     buf = C.create_string_buffer(8192)
     check(_ffi.lib().mcg_jit_check(C.byref(d), int(precision), C.byref(n), buf, len(buf)))

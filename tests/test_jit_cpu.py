@@ -33,3 +33,19 @@ def test_wide_stencils_are_left_to_the_runtime_table_kernel(tmp_path, monkeypatc
     spec = add_dipole_stencil(spec_of("cubic", (16, 16, 16)), 0.2, 2.0)
     n, report = engine.jit_check(spec, 3, 32)
     assert n == 0 and "not eligible" in report                  # 32 links per site: unrolling would thrash the I-cache
+
+
+def test_block_spin_descriptor_is_validated_on_the_host(tmp_path, monkeypatch):
+    """The structured block-spin tables are built with the class tables (no GPU needed): supercells the descriptor cannot
+    express exactly (odd sizes; sizes where the doubled bonds +2d and -2d fold onto one site) are refused by name."""
+    monkeypatch.setenv("MCG_CACHE_DIR", str(tmp_path))
+    try:
+        n, _ = engine.jit_check(spec_of("cubic", (8, 8, 16), ), 3, 32, block_spin=True)
+    except engine.McgError as e:
+        if "cannot dlopen libnvrtc" in str(e):
+            pytest.skip("NVRTC not installed")
+        raise
+    assert n == 2
+    for L in [(5, 8, 16), (4, 8, 16)]:
+        with pytest.raises(engine.McgError, match="block_spin"):
+            engine.jit_check(spec_of("cubic", L), 3, 32, block_spin=True)
