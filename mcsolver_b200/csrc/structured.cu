@@ -23,6 +23,7 @@
 
 #include "structured.hpp"
 #include "struct_pass.cuh"
+#include "topo_pass.cuh"
 #include "jit.hpp"
 #include "kernels_wolff.cuh"
 #include "kernels_extra.cuh"
@@ -53,6 +54,7 @@ struct StructuredSystem {
     std::vector<char> fastOK;            // per colour: pass table fits the __grid_constant__ fast path
     std::vector<std::vector<char>> passTables;   // per colour: PassTable<real> bytes
     std::vector<void *> jitResolved;     // [colour*2 + partial] -> JitPass* once looked up (nullptr = not yet)
+    void *jitTopo = nullptr;             // JitPass* of the specialised topological-charge kernel, once looked up
     SClassD *d_classes = nullptr;
     SLinkD *d_links = nullptr;
     void *d_J = nullptr;
@@ -409,29 +411,6 @@ __global__ void __launch_bounds__(256) k_struct_topo(StructArgs a, int ncirc, co
 }
 
 
-// Topological charge, one thread per CELL: the ncircuit triangles of a cell share vertices (the four
-// circuits of samples/SkyrmionOnHexLattice touch 5 distinct sites), so the distinct vertices are loaded
-// once and the triangles index into them.  fp32 engines evaluate the solid angle in fp32 (sum in fp64);
-// fp64 engines keep the reference's double arithmetic (parity <= 1e-12).   calcSignedArea heisenbergLib.c:114-127
-template <typename T> __device__ __forceinline__ T tri_area(const T (&a)[3], const T (&b)[3], const T (&c)[3], T la, T lb, T lc) {
-    T ab = (a[0] * b[0] + a[1] * b[1] + a[2] * b[2]) / la / lb;
-    T bc = (b[0] * c[0] + b[1] * c[1] + b[2] * c[2]) / lb / lc;
-    T ca = (c[0] * a[0] + c[1] * a[1] + c[2] * a[2]) / lc / la;
-    T cx = b[1] * c[2] - b[2] * c[1], cy = b[2] * c[0] - b[0] * c[2], cz = b[0] * c[1] - b[1] * c[0];
-    T re = T(1) + ab + bc + ca;
-    T im = (a[0] * cx + a[1] * cy + a[2] * cz) / la / lb / lc;
-    if (fabs(re) < T(1e-6)) return im > 0 ? T(MCG_REF_PI) : T(-MCG_REF_PI);
-    return T(2) * atan(im / re);
-}
-// same quantity for vertices already normalised to unit length (fp32 engines)
-template <typename T> __device__ __forceinline__ T tri_area_unit(const T (&a)[3], const T (&b)[3], const T (&c)[3]) {
-    T cx = b[1] * c[2] - b[2] * c[1], cy = b[2] * c[0] - b[0] * c[2], cz = b[0] * c[1] - b[1] * c[0];
-    T re = T(1) + (a[0] * b[0] + a[1] * b[1] + a[2] * b[2]) + (b[0] * c[0] + b[1] * c[1] + b[2] * c[2]) + (c[0] * a[0] + c[1] * a[1] + c[2] * a[2]);
-    T im = a[0] * cx + a[1] * cy + a[2] * cz;
-    if (fabs(re) < T(1e-6)) return im > 0 ? T(MCG_REF_PI) : T(-MCG_REF_PI);
-    if constexpr (sizeof(T) == 4) return T(2) * atanf(__fdividef(im, re));
-    else return T(2) * atan(im / re);
-}
 constexpr int TOPO_MAXV = 12;
 constexpr int TOPO_THREADS = 128;
 // The vertex table is indexed by runtime triangle indices, so it lives in shared memory ([vertex][component][thread],
@@ -822,7 +801,7 @@ static std::string cache_path(const std::string &src) {
     else d = csrc_dir() + "/../build/jitcache";
     if (getenv("MCG_NO_DISK_CACHE")) return "";
     uint64_t h = fnv1a(src);
-    for (const char *f : {"/struct_pass.cuh", "/devmath.cuh", "/rng.cuh"}) h = fnv1a(read_file(csrc_dir() + f), h);
+    for (const char *f : {"/struct_pass.cuh", "/topo_pass.cuh", "/devmath.cuh", "/rng.cuh"}) h = fnv1a(read_file(csrc_dir() + f), h);
     std::string mk = "mkdir -p '" + d + "' 2>/dev/null";
     if (system(mk.c_str()) != 0) return "";
     char name[64];
@@ -842,8 +821,9 @@ std::vector<char> jit_compile_cubin(const std::string &src, std::string &log) {
     nvrtcProgram prog;
     if (api.createProgram(&prog, src.c_str(), "mcg_pass.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) { log = "nvrtcCreateProgram failed"; return {}; }
     std::string inc = "-I" + csrc_dir();
-    const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", inc.c_str(), "-default-device"};
-    nvrtcResult res = api.compileProgram(prog, 5, opts);
+    // 128: "loop is not reachable" - the scalar item code after the packed fp32 branch of pass_body, by construction
+    const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", inc.c_str(), "-default-device", "--diag-suppress=128"};
+    nvrtcResult res = api.compileProgram(prog, 6, opts);
     size_t ls = 0;
     api.getLogSize(prog, &ls);
     if (ls > 1) { log.resize(ls); api.getLog(prog, &log[0]); }
@@ -924,6 +904,72 @@ bool jit_launch_pass(mcg_system *s, int colour, int mode, const StructArgs &a, i
     void *params[] = {(void *)&a, &q0, &rowsPerBlock, &nrb, &sweep, s->prec == 32 ? (void *)&pf : (void *)&pd};
     CUresult r = api.launchKernel(jp->f[mode], grid.x, 1, 1, block.x, block.y, 1, 0, (CUstream)s->stream, params, nullptr);
     if (r != CUDA_SUCCESS) throw Error(MCG_ERR_CUDA, "cuLaunchKernel of the JIT pass kernel failed");
+    return true;
+}
+
+// ---- specialised topological-charge kernel (topo_pass.cuh) ----
+static bool jit_topo_worthwhile(const StructuredSystem *st) {
+    const int npar = st->p[0] * st->p[1] * st->p[2];
+    return st->ncircuit > 0 && st->ncircuit <= 32 && st->nvert <= 16 && npar * st->nvert <= 256;
+}
+
+std::string jit_topo_prologue(const mcg_system *s) {
+    const StructuredSystem *st = s->st;
+    const bool f32 = s->prec == 32;
+    const int px = st->p[0], py = st->p[1], pz = st->p[2], no = st->norb, npar = px * py * pz;
+    std::ostringstream o;
+    o << "#define MCG_JIT_TOPO 1\ntypedef " << (f32 ? "float" : "double") << " jit_real;\n";
+    o << "#define JT_NV " << st->nvert << "\n#define JT_NT " << st->ncircuit << "\n#define JT_NPAR " << npar << "\n#define JT_Xd " << st->Xd
+      << "\n#define JT_Yd " << st->Yd << "\n#define JT_Zd " << st->Zd << "\n#define JT_N " << s->N << "\n";
+    o << "namespace mcg {\ntemplate <int PAR, int K> struct CtVert;\ntemplate <int T> struct CtTri;\n";
+    for (int par = 0; par < npar; par++) {
+        const int cc = par % pz, cb = (par / pz) % py, ca = par / (pz * py);
+        for (int k = 0; k < st->nvert; k++) {
+            const int *e = st->tvertsHost.data() + 4 * k;   // (orbital, dx, dy, dz), offsets in [0, L)
+            const int na = ca + e[1], nb = cb + e[2], nc = cc + e[3];
+            const int q = st->classOf[(((na % px) * py + nb % py) * pz + nc % pz) * no + e[0]];
+            o << "template <> struct CtVert<" << par << "," << k << "> { static constexpr int base=" << q * st->ncellc << ", cX=" << (na / px) % st->Xd
+              << ", cY=" << (nb / py) % st->Yd << ", cZ=" << (nc / pz) % st->Zd << "; static constexpr jit_real len=" << lit(std::fabs(st->classes[q].S), f32)
+              << "; };\n";
+        }
+    }
+    for (int t = 0; t < st->ncircuit; t++)
+        o << "template <> struct CtTri<" << t << "> { static constexpr int i0=" << st->ttrisHost[3 * t] << ", i1=" << st->ttrisHost[3 * t + 1]
+          << ", i2=" << st->ttrisHost[3 * t + 2] << "; };\n";
+    o << "}\n#include \"topo_pass.cuh\"\n";
+    return o.str();
+}
+
+static bool jit_launch_topo(mcg_system *s, const StructArgs &a, int nzc, int nyc, dim3 grid, dim3 block) {
+    StructuredSystem *st = s->st;
+    if (!jit_enabled(s) || !jit_topo_worthwhile(st)) return false;
+    JitApi &api = jit_api();
+    if (!api.ok) return false;
+    JitPass *jp = static_cast<JitPass *>(st->jitTopo);
+    if (!jp) {
+        std::lock_guard<std::mutex> lock(g_jit_mutex);
+        auto key = std::make_pair(s->device, jit_topo_prologue(s));
+        auto it = g_jit_cache.find(key);
+        if (it == g_jit_cache.end()) {
+            JitPass np;
+            std::string log;
+            std::vector<char> cubin = jit_compile_cubin(key.second, log);
+            CUmodule mod = nullptr;
+            if (cubin.empty() || api.moduleLoadData(&mod, cubin.data()) != CUDA_SUCCESS ||
+                api.moduleGetFunction(&np.f[0], mod, "mcg_topo") != CUDA_SUCCESS) {
+                np.failed = true;
+                fprintf(stderr, "mcsolver_b200: JIT topological-charge kernel unavailable (%s); using the offline CUDA kernel\n", log.substr(0, 2000).c_str());
+            }
+            it = g_jit_cache.emplace(key, np).first;
+        }
+        jp = &it->second;
+        st->jitTopo = jp;
+    }
+    if (jp->failed) return false;
+    double *sums = s->d_sums;
+    void *params[] = {(void *)&a, &nzc, &nyc, &sums};
+    CUresult r = api.launchKernel(jp->f[0], grid.x, grid.y, grid.z, block.x, block.y, 1, 0, (CUstream)s->stream, params, nullptr);
+    if (r != CUDA_SUCCESS) throw Error(MCG_ERR_CUDA, "cuLaunchKernel of the JIT topological-charge kernel failed");
     return true;
 }
 
@@ -1362,6 +1408,12 @@ int structured_jit_check(const mcg_lattice_desc *d, int precision, std::string &
         if (cubin.empty()) { report = o.str(); return -1; }
         ncompiled++;
     }
+    if (jit_topo_worthwhile(tmp.st) && tmp.NC == 3) {
+        std::string log;
+        std::vector<char> cubin = jit_compile_cubin(jit_topo_prologue(&tmp), log);
+        o << "topological charge: cubin " << cubin.size() << " bytes" << (log.empty() ? "" : " log: " + log.substr(0, 1500)) << "\n";
+        if (cubin.empty()) { report = o.str(); return -1; }
+    }
     report = o.str();
     return ncompiled;
 }
@@ -1515,7 +1567,8 @@ static void fold_and_extras(mcg_system *s) {
             const int nzc = (st->Zd + tz - 1) / tz, nyc = (st->Yd + ty - 1) / ty;
             dim3 gc((unsigned)(nzc * nyc * npar), (unsigned)st->Xd, (unsigned)s->R), bc(tz, ty);
             size_t sh = (size_t)3 * st->nvert * TOPO_THREADS * (s->prec == 64 ? 8 : 4);
-            if (s->prec == 64) k_struct_topo_cells<double><<<gc, bc, sh, s->stream>>>(a, st->ncircuit, st->nvert, st->d_tverts, st->d_ttris, nzc, nyc, s->d_sums);
+            if (jit_launch_topo(s, a, nzc, nyc, gc, bc)) { /* specialised kernel launched */ }
+            else if (s->prec == 64) k_struct_topo_cells<double><<<gc, bc, sh, s->stream>>>(a, st->ncircuit, st->nvert, st->d_tverts, st->d_ttris, nzc, nyc, s->d_sums);
             else k_struct_topo_cells<float><<<gc, bc, sh, s->stream>>>(a, st->ncircuit, st->nvert, st->d_tverts, st->d_ttris, nzc, nyc, s->d_sums);
         } else {
             dim3 g((s->nTri + 255) / 256, s->R);

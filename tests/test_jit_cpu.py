@@ -25,7 +25,9 @@ def test_specialised_kernels_compile_for_sm100a(name, L, model, prec, ncol, tmp_
     assert "V=%d" % (4 if prec == 32 else 2) in report, report
     if ncol is not None:
         assert n == ncol, report
-    assert n >= 2 and len(os.listdir(tmp_path)) == n            # one cached cubin per colour
+    topo = 1 if (name == "skyrmion" and model == 3) else 0       # + the specialised topological-charge kernel
+    assert ("topological charge: cubin" in report) == bool(topo), report
+    assert n >= 2 and len(os.listdir(tmp_path)) == n + topo     # one cached cubin per colour
 
 
 def test_wide_stencils_are_left_to_the_runtime_table_kernel(tmp_path, monkeypatch):
