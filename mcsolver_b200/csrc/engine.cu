@@ -504,8 +504,28 @@ static int resident_max_sites() {
     return e ? atoi(e) : 4096;   // measured crossover with the launch-per-phase path (scripts/probe_resident.py)
 }
 
+// blocks per replica of the cooperative variant (0 = not applicable: too small to split, too many replicas to co-reside)
+static int coop_blocks_per_replica(mcg_system *s) {
+    if (getenv("MCG_NO_COOP")) return 0;
+    const char *e = getenv("MCG_COOP_MAXN");
+    if (s->N > (e ? atoi(e) : 131072)) return 0;
+    int dev = 0, sms = 0, coop = 0, perSM = 0;
+    MCG_CUDA(cudaGetDevice(&dev));
+    MCG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    MCG_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    if (!coop) return 0;
+    dispatch(s, [&]<int NC, typename real, bool FJ>() {
+        MCG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_resident_coop<NC, real, FJ>, RES_THREADS, 0));
+    });
+    const int capacity = sms * perSM;
+    const char *ps = getenv("MCG_COOP_SITES");   // sites per block aimed at (tests force many blocks on tiny lattices)
+    const int per = std::max(1, ps ? atoi(ps) : RES_THREADS * 4);
+    int B = std::min(capacity / std::max(1, s->R), (s->N + per - 1) / per);
+    return B >= 2 ? B : 0;
+}
+
 static void run_resident(mcg_system *s, int algorithm, int64_t thermalUpdates, int64_t perSweep, double pAtt, int64_t nsweep, int spinFrame,
-                         double *frames) {
+                         double *frames, int coopB) {
     if (!s->d_colourStart) {
         s->d_colourStart = dalloc<int>(s->colourStart.size());
         MCG_CUDA(cudaMemcpy(s->d_colourStart, s->colourStart.data(), s->colourStart.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -516,7 +536,14 @@ static void run_resident(mcg_system *s, int algorithm, int64_t thermalUpdates, i
         for (double h : s->field_host) anyField = anyField || h != 0.0;
         needResidual = anyField || (s->model != MCG_ISING && !s->isoNoOnsite);
     }
-    s->wolffPrimed = false;   // the resident kernel keeps its forest in shared memory; the global buffers are not prepared
+    if (coopB == 0 || algorithm != MCG_WOLFF) s->wolffPrimed = false;   // single-block kernel: forest in shared memory, global buffers not prepared
+    if (coopB > 0 && algorithm == MCG_WOLFF && !s->d_parent) {
+        const size_t RN = (size_t)s->R * s->N;
+        s->d_parent = (int32_t *)pool_alloc(2 * RN * sizeof(int32_t));
+        s->d_proj = pool_alloc(2 * RN * s->real_size());
+        s->d_wres = dalloc<double>(2 * (size_t)s->R);
+        s->wolffPrimed = false;
+    }
     const size_t fsz = (size_t)s->N * (s->NC == 1 ? 1 : 3);
     double *d_frames = nullptr;
     if (spinFrame > 0) {
@@ -547,20 +574,32 @@ static void run_resident(mcg_system *s, int algorithm, int64_t thermalUpdates, i
     if (algorithm == MCG_WOLFF) biggest = s->N;
     int nthreads = 64;
     while (nthreads < biggest && nthreads < RES_THREADS) nthreads <<= 1;
+    CoopPlan Q;
+    Q.B = coopB; Q.parentBase = s->d_parent; Q.projBase = (char *)s->d_proj; Q.sums = s->d_sums; Q.rsums = s->d_rsums; Q.primed = 0;
+    w.wres = s->d_wres;
 
     auto launch = [&](int64_t thermal, int64_t i0, int64_t n) {
         P.thermal = thermal; P.perSweep = perSweep; P.nsweep = n; P.i0 = i0;
         P.sweep0 = s->sweepCtr; P.step0 = s->wolffCtr; P.meas0 = s->measCtr;
-        const size_t shm = algorithm == MCG_WOLFF ? resident_wolff_smem(s->N, s->real_size()) : 0;
-        dispatch(s, [&]<int NC, typename real, bool FJ>() {
-            if (shm > 40 * 1024) MCG_CUDA(cudaFuncSetAttribute(k_resident<NC, real, FJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-            k_resident<NC, real, FJ><<<s->R, nthreads, shm, s->stream>>>(a, g, w, s->d_pos_of, P);
-        });
+        if (coopB > 0) {
+            Q.primed = s->wolffPrimed ? 1 : 0;
+            const int32_t *posOf = s->d_pos_of;
+            void *args[] = {(void *)&a, (void *)&g, (void *)&w, (void *)&posOf, (void *)&P, (void *)&Q};
+            dispatch(s, [&]<int NC, typename real, bool FJ>() {
+                MCG_CUDA(cudaLaunchCooperativeKernel((const void *)k_resident_coop<NC, real, FJ>, dim3((unsigned)(s->R * coopB)), dim3(RES_THREADS), args, 0, s->stream));
+            });
+        } else {
+            const size_t shm = algorithm == MCG_WOLFF ? resident_wolff_smem(s->N, s->real_size()) : 0;
+            dispatch(s, [&]<int NC, typename real, bool FJ>() {
+                if (shm > 40 * 1024) MCG_CUDA(cudaFuncSetAttribute(k_resident<NC, real, FJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+                k_resident<NC, real, FJ><<<s->R, nthreads, shm, s->stream>>>(a, g, w, s->d_pos_of, P);
+            });
+        }
         MCG_CUDA(cudaGetLastError());
         s->launches++;
         const int64_t updates = thermal + n * perSweep;
         if (algorithm == MCG_METROPOLIS) s->sweepCtr += updates;
-        else s->wolffCtr += updates;
+        else { s->wolffCtr += updates; if (coopB > 0 && updates > 0) s->wolffPrimed = true; }
         if (extras) s->measCtr += n;
     };
     const int64_t chunk = 1 << 16;   // bounds the run time of one launch
@@ -585,10 +624,10 @@ static void run(mcg_system *s, int algorithm, int64_t nthermal, int64_t nsweep, 
         else if (ninterval > 0) pAtt = (double)ninterval / (double)s->N;
         else nsub = 0;
     }
-    if (!s->structured && !s->profilePasses && s->N <= resident_max_sites()) {
+    if (!s->structured && !s->profilePasses) {
         const int64_t per = algorithm == MCG_METROPOLIS ? nsub : ninterval;
-        run_resident(s, algorithm, nthermal * per, per, pAtt, nsweep, spinFrame, frames);
-        return;
+        if (s->N <= resident_max_sites()) { run_resident(s, algorithm, nthermal * per, per, pAtt, nsweep, spinFrame, frames, 0); return; }
+        if (const int B = coop_blocks_per_replica(s)) { run_resident(s, algorithm, nthermal * per, per, pAtt, nsweep, spinFrame, frames, B); return; }
     }
     auto updates = [&](int64_t intervals) {
         if (algorithm == MCG_METROPOLIS) { if (nsub > 0) metropolis_sweeps(s, intervals * nsub, pAtt); }

@@ -14,11 +14,20 @@ CASES = [("skyrmion", (6, 6, 1), 0.3, 3, 0.2), ("cri3", (4, 4, 1), 35.0, 3, 0.0)
 IDS = ["%s-%s-m%d" % (c[0], "x".join(map(str, c[1])), c[3]) for c in CASES]
 
 
-def _run(eng, t, model, hT, algo, ninterval, prec, R, monkeypatch, resident):
-    if resident:
-        monkeypatch.delenv("MCG_NO_RESIDENT", raising=False)
-    else:
+def _mode(monkeypatch, mode):
+    """mode: 'resident' (one block per replica), 'coop' (cooperative kernel, several blocks per replica), 'phases'."""
+    for k in ("MCG_NO_RESIDENT", "MCG_NO_COOP", "MCG_RESIDENT_MAXN", "MCG_COOP_SITES"):
+        monkeypatch.delenv(k, raising=False)
+    if mode == "phases":
         monkeypatch.setenv("MCG_NO_RESIDENT", "1")
+        monkeypatch.setenv("MCG_NO_COOP", "1")
+    elif mode == "coop":
+        monkeypatch.setenv("MCG_RESIDENT_MAXN", "0")
+        monkeypatch.setenv("MCG_COOP_SITES", "24")
+
+
+def _run(eng, t, model, hT, algo, ninterval, prec, R, monkeypatch, resident):
+    _mode(monkeypatch, resident if isinstance(resident, str) else ("resident" if resident else "phases"))
     beta = np.linspace(1.0, 0.8, R)
     with eng.System.from_tables(t, precision=prec, nReplica=R, beta=beta, field=np.full(R, hT), seed=31) as s:
         s.init_spins(0.3)
@@ -34,13 +43,14 @@ def _run(eng, t, model, hT, algo, ninterval, prec, R, monkeypatch, resident):
 @pytest.mark.parametrize("case", CASES, ids=IDS)
 @pytest.mark.parametrize("algo", [0, 1], ids=["metropolis", "wolff"])
 @pytest.mark.parametrize("prec", [64, 32])
-def test_resident_kernel_equals_launch_per_phase(case, algo, prec, monkeypatch):
+@pytest.mark.parametrize("mode", ["resident", "coop"])
+def test_resident_kernel_equals_launch_per_phase(case, algo, prec, mode, monkeypatch):
     from mcsolver_b200 import engine as eng
     name, L, T, model, h = case
     t = util.tables_for(dict(spec=name, L=L, T=T, model=model))
     hT = h / T
     ninterval = t.N if algo == 0 else 2
-    a = _run(eng, t, model, hT, algo, ninterval, prec, 3, monkeypatch, resident=True)
+    a = _run(eng, t, model, hT, algo, ninterval, prec, 3, monkeypatch, resident=mode)
     b = _run(eng, t, model, hT, algo, ninterval, prec, 3, monkeypatch, resident=False)
     assert a["launches"] <= 2 < b["launches"]          # one launch for thermalisation, one for the measured sweeps
     tol = 1e-11 if prec == 64 else 2e-5
@@ -65,10 +75,7 @@ def test_resident_partial_sweeps_and_many_chunks(monkeypatch):
     t = util.tables_for(dict(spec="square", L=(8, 8, 1), T=0.9, model=2))
     out = {}
     for resident in (True, False):
-        if resident:
-            monkeypatch.delenv("MCG_NO_RESIDENT", raising=False)
-        else:
-            monkeypatch.setenv("MCG_NO_RESIDENT", "1")
+        _mode(monkeypatch, "resident" if resident else "phases")
         with eng.System.from_tables(t, precision=64, seed=8) as s:
             s.init_spins(0.2)
             s.run(0, 3, 40, 17)
@@ -76,7 +83,7 @@ def test_resident_partial_sweeps_and_many_chunks(monkeypatch):
     assert out[True][1] == out[False][1]
     assert np.max(np.abs(out[True][2] - out[False][2])) < 1e-12
     assert np.max(np.abs(out[True][0] - out[False][0]) / np.maximum(1.0, np.abs(out[False][0]))) < 1e-11
-    monkeypatch.delenv("MCG_NO_RESIDENT", raising=False)
+    _mode(monkeypatch, "resident")
     t = util.tables_for(dict(spec="square", L=(8, 8, 1), T=2.3, model=1))
     with eng.System.from_tables(t, precision=32, seed=8) as s:
         l0 = s.launch_count()
