@@ -50,7 +50,10 @@ __device__ __forceinline__ void metro_site(const GenArgs &a, real *sp, int r, in
     load_spin<NC, real>(sp, a.N, p, s);
     local_field<NC, real, FULLJ>(a, sp, p, H);
     uint32_t w[4];
-    rng4(a.key, a.replica0 + r, STREAM_METRO, 0, sweep, (uint32_t)a.site_of[p], w);
+    if (NC == 1) {   // one uniform per attempt: word id & 3 of the block shared by four site ids (rng.cuh)
+        IsingWords iw;
+        iw.get(a.key, a.replica0 + r, sweep, (uint32_t)a.site_of[p], pAtt < real(1), w[2], w[3]);
+    } else rng4(a.key, a.replica0 + r, STREAM_METRO, 0, sweep, (uint32_t)a.site_of[p], w);
     if (!(pAtt < real(1)) || u01<real>(w[3]) < pAtt) {
         attempted++;
         if (NC == 1) {

@@ -54,6 +54,30 @@ __host__ __device__ __forceinline__ void rng4(const RngKey &key, uint32_t replic
                   key, out);
 }
 
+// Ising needs ONE uniform per attempt, a Philox block holds four: four consecutive reference site ids share the block
+// whose first counter word is id >> 2 (sub-stream 0) and use word id & 3 of it; the attempt-probability uniform of
+// partial sweeps (ninterval < N) comes from sub-stream 1 in the same way.  The mapping depends on the reference site id
+// only, so it is the same on every path; a caller visiting several sites keeps the last block (the V = 4 item of the
+// structured pass needs two Philox calls instead of four).
+__host__ __device__ __forceinline__ uint32_t pick4(const uint32_t (&w)[4], uint32_t i) {
+    const uint32_t lo = (i & 1u) ? w[1] : w[0], hi = (i & 1u) ? w[3] : w[2];
+    return (i & 2u) ? hi : lo;
+}
+struct IsingWords {
+    uint32_t blk = 0xffffffffu;
+    uint32_t wa[4], wp[4];
+    __host__ __device__ __forceinline__ void get(const RngKey &key, uint32_t replica, uint64_t sweep, uint32_t id, bool partial,
+                                                 uint32_t &wAcc, uint32_t &wAtt) {
+        if ((id >> 2) != blk) {
+            blk = id >> 2;
+            rng4(key, replica, STREAM_METRO, 0, sweep, blk, wa);
+            if (partial) rng4(key, replica, STREAM_METRO, 1, sweep, blk, wp);
+        }
+        wAcc = pick4(wa, id & 3u);
+        wAtt = partial ? pick4(wp, id & 3u) : 0u;
+    }
+};
+
 // uniforms strictly inside (0,1): fp64 uses all 32 bits: (r+0.5)/2^32; fp32 the top 23 bits:
 // (k+0.5)/2^23 with k = r>>9, built without an int->float conversion: 1.mantissa - (1 - 2^-24), exact.
 template <typename real> __host__ __device__ __forceinline__ real u01(uint32_t r);

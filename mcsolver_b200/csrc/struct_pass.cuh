@@ -383,12 +383,14 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                 }
             });
             const uint32_t id0 = (uint32_t)((xy + Z0 * pz + cls.cc()) * norb + cls.co());
+            IsingWords iw;   // Ising: sites of the item that fall into the same block of four ids share one Philox call
 #pragma unroll
             for (int v = 0; v < V; v++) {
                 real sx = s[0][v], sy = s[1][v], sz = s[2][v];
                 const real hx = H[0][v], hy = H[1][v], hz = H[2][v];
                 uint32_t w[4];
-                rng4(a.key, a.replica0 + r, STREAM_METRO, 0, sweep, id0 + (uint32_t)(v * idStrideZ), w);
+                if (NC == 1) iw.get(a.key, a.replica0 + r, sweep, id0 + (uint32_t)(v * idStrideZ), PARTIAL, w[2], w[3]);
+                else rng4(a.key, a.replica0 + r, STREAM_METRO, 0, sweep, id0 + (uint32_t)(v * idStrideZ), w);
                 const bool att = PARTIAL ? (u01<real>(w[3]) < pAtt) : true;
                 bool acc;
                 if (NC == 1) {

@@ -215,13 +215,15 @@ __global__ void __launch_bounds__(256) k_struct(StructArgs a, int q0, int nqc, i
                 }
             }
             const uint32_t id0 = (uint32_t)(((x * a.Ly + y) * a.Lz + (Z0 * a.pz + sc.c)) * a.norb + sc.o);
+            IsingWords iw;
 #pragma unroll
             for (int v = 0; v < V; v++) {
                 real sv[3] = {s[0][v], s[1][v], s[2][v]};
                 const real Hv[3] = {H[0][v], H[1][v], H[2][v]};
                 if (MODE != 2) {
                     uint32_t w[4];
-                    rng4(a.key, a.replica0 + r, STREAM_METRO, 0, sweep, id0 + (uint32_t)(v * idStrideZ), w);
+                    if (NC == 1) iw.get(a.key, a.replica0 + r, sweep, id0 + (uint32_t)(v * idStrideZ), pAtt < real(1), w[2], w[3]);
+                    else rng4(a.key, a.replica0 + r, STREAM_METRO, 0, sweep, id0 + (uint32_t)(v * idStrideZ), w);
                     if (!(pAtt < real(1)) || u01<real>(w[3]) < pAtt) {
                         natt++;
                         if (NC == 1) {

@@ -656,11 +656,14 @@ static void ising_local_update_ref(const orc_sys *s, double *sp, orc_state *st) 
         sp[i] *= -1; st->tot[0] += sp[i] * 2; st->energy -= corr; st->accepted++;
     }
 }
-static void ising_attempt_philox(const orc_sys *s, double *sp, int i, const uint32_t r[4], int f32, double pAtt, orc_state *st) {
-    if (pAtt < 1.0 && !((f32 ? u01f(r[3]) : u01(r[3])) < pAtt)) return;
+/* Ising stream convention of the engine (csrc/rng.cuh): four consecutive site ids share the Philox block whose first
+ * counter word is id >> 2 and use word id & 3 of it - sub-stream 0 for the acceptance uniform, sub-stream 1 for the
+ * attempt-probability uniform of partial sweeps. */
+static void ising_attempt_philox(const orc_sys *s, double *sp, int i, uint32_t wAcc, uint32_t wAtt, int f32, double pAtt, orc_state *st) {
+    if (pAtt < 1.0 && !((f32 ? u01f(wAtt) : u01(wAtt)) < pAtt)) return;
     double corr = orc_ising_flip_corr(s, sp, i);
     st->attempts++;
-    if (corr >= 0 || exp(corr) > (f32 ? u01f(r[2]) : u01(r[2]))) { sp[i] *= -1; st->accepted++; }
+    if (corr >= 0 || exp(corr) > (f32 ? u01f(wAcc) : u01(wAcc))) { sp[i] *= -1; st->accepted++; }
 }
 static void ising_block_update(const orc_sys *s, double *sp, orc_state *st, int mode, uint64_t seed, uint32_t replica,
                                uint64_t step, int f32, int *scr) { /* isingLib.c:165-236 */
@@ -740,9 +743,10 @@ int orc_run_ising(const orc_sys *s, int update_mode, long nthermal, long nsweep,
     for (long long q_ = 0; q_ < (count); q_++) {                                                             \
         for (int p_ = 0; p_ < N; p_++) {                                                                     \
             int i_ = order[p_];                                                                              \
-            uint32_t r_[4];                                                                                  \
-            rng4(seed, replica, STREAM_METRO, 0, sweepCtr, (uint32_t)i_, r_);                                \
-            ising_attempt_philox(s, sp, i_, r_, f32, pAtt, &st);                                             \
+            uint32_t ra_[4], rp_[4] = {0, 0, 0, 0};                                                          \
+            rng4(seed, replica, STREAM_METRO, 0, sweepCtr, (uint32_t)i_ >> 2, ra_);                          \
+            if (pAtt < 1.0) rng4(seed, replica, STREAM_METRO, 1, sweepCtr, (uint32_t)i_ >> 2, rp_);          \
+            ising_attempt_philox(s, sp, i_, ra_[i_ & 3], rp_[i_ & 3], f32, pAtt, &st);                       \
         }                                                                                                    \
         sweepCtr++;                                                                                          \
     }
