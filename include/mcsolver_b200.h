@@ -129,6 +129,10 @@ MCG_API int mcg_destroy(mcg_system *sys);
 MCG_API int mcg_jit_check(const mcg_lattice_desc *d, int precision, int *ncompiled, char *report, int report_len);
 MCG_API int mcg_num_colours(const mcg_system *sys, int *ncolours);
 MCG_API int mcg_colour_order(const mcg_system *sys, int32_t *order /*[N] site ids, colour-major*/);
+/* Philox stream layout of the Metropolis sweeps (csrc/rng.cuh), for checkers that restate the trajectory:
+ * stride = 0: one block per site (table-built systems, scalar structured pass); stride = S, group = V: the V sites
+ * id = base + m*S of one vector item share their blocks. */
+MCG_API int mcg_rng_layout(const mcg_system *sys, int32_t *stride, int32_t *group);
 MCG_API int mcg_set_params(mcg_system *sys, const double *beta, const double *field); /* per replica */
 
 /* ---- state ---- */

@@ -53,6 +53,7 @@ SIGNATURES = {
     "mcg_jit_check": (_i, [C.POINTER(LatticeDesc), _i, _vp, _vp, _i]),
     "mcg_num_colours": (_i, [_vp, _vp]),
     "mcg_colour_order": (_i, [_vp, _vp]),
+    "mcg_rng_layout": (_i, [_vp, _vp, _vp]),
     "mcg_set_params": (_i, [_vp, _vp, _vp]),
     "mcg_init_spins": (_i, [_vp, _d]),
     "mcg_set_spins": (_i, [_vp, _i, _vp]),

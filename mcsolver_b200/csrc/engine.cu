@@ -779,6 +779,13 @@ MCG_API int mcg_num_colours(const mcg_system *sys, int *ncolours) {
     return guarded([&] { MCG_REQUIRE(sys && ncolours, "NULL argument"); *ncolours = sys->C; });
 }
 
+MCG_API int mcg_rng_layout(const mcg_system *sys, int32_t *stride, int32_t *group) {
+    return guarded([&] {
+        MCG_REQUIRE(sys && stride && group, "NULL argument");
+        *stride = 0; *group = 0;
+        if (sys->structured) structured_rng_layout(sys, stride, group);
+    });
+}
 MCG_API int mcg_colour_order(const mcg_system *sys, int32_t *order) {
     return guarded([&] {
         MCG_REQUIRE(sys && order, "NULL argument");

@@ -78,6 +78,45 @@ struct IsingWords {
     }
 };
 
+// ---- grouped streams of the vectorised structured pass ----
+// One thread of that pass updates an ITEM of V sites whose reference ids are id0 + v*S (S = id stride along the vector
+// axis).  Per-site Philox blocks waste words (an O(3) attempt uses 3 of 4, O(2) 2, Ising 1), so the item draws its words
+// from shared blocks instead: group index G = (id / (V*S))*S + id % S is the first counter word, member m = (id / S) % V,
+// the t-th word of member m is word k = W*m + t of the group (W = words per attempt = number of spin components), i.e.
+// word k & 3 of the block drawn with sub-stream k >> 2.  V = 4: 3 Philox calls per item instead of 4 (O(3)), 2 (O(2)),
+// 1 (Ising).  The attempt-probability uniform of partial sweeps is word m of the block with sub-stream 7.
+// Still a pure function of (site id, S, V) - the oracle restates it (oracle.c: grouped_words).
+template <int W, int V> struct ItemWords {
+    static constexpr int NCALL = (W * V + 3) / 4;
+    uint32_t c[NCALL][4];
+    uint32_t p[4];
+    uint32_t G;
+    int have;   // blocks drawn so far (a compile-time constant after unrolling)
+    __host__ __device__ __forceinline__ void begin(const RngKey &key, uint32_t replica, uint64_t sweep, uint32_t id0, uint32_t S, bool partial) {
+        G = (id0 / (V * S)) * S + id0 % S;
+        have = 0;
+        if (partial) rng4(key, replica, STREAM_METRO, 7u, sweep, G, p);
+    }
+    // draw the blocks that hold the words of members [0, mEnd): called right before those members are processed, so that
+    // at most the words of the members in flight are live (drawing all blocks up front spills the 64-register pass kernel)
+    __host__ __device__ __forceinline__ void need(const RngKey &key, uint32_t replica, uint64_t sweep, int mEnd) {
+        const int last = (W * mEnd - 1) >> 2;
+#pragma unroll
+        for (int i = 0; i < NCALL; i++)
+            if (i >= have && i <= last) rng4(key, replica, STREAM_METRO, (uint32_t)i, sweep, G, c[i]);
+        if (last + 1 > have) have = last + 1;
+    }
+    // m and t are compile-time constants in the unrolled callers: static register indices
+    __host__ __device__ __forceinline__ uint32_t word(int m, int t) const { return c[(W * m + t) >> 2][(W * m + t) & 3]; }
+    // the words of member m in the slots the per-site code uses: [0],[1] direction, [2] acceptance, [3] attempt probability
+    __host__ __device__ __forceinline__ void lane(int m, bool partial, uint32_t (&w)[4]) const {
+        if (W == 3) { w[0] = word(m, 0); w[1] = word(m, 1); w[2] = word(m, 2); }
+        else if (W == 2) { w[0] = word(m, 0); w[1] = 0u; w[2] = word(m, 1); }
+        else { w[0] = 0u; w[1] = 0u; w[2] = word(m, 0); }
+        w[3] = partial ? p[m] : 0u;
+    }
+};
+
 // uniforms strictly inside (0,1): fp64 uses all 32 bits: (r+0.5)/2^32; fp32 the top 23 bits:
 // (k+0.5)/2^23 with k = r>>9, built without an int->float conversion: 1.mantissa - (1 - 2^-24), exact.
 template <typename real> __host__ __device__ __forceinline__ real u01(uint32_t r);

@@ -257,11 +257,14 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                 const uint32_t id0 = (uint32_t)((xy + Z0 * pz + cls.cc()) * norb + cls.co());
                 const float fbeta = (float)beta, fhf = (float)hf, fS = (float)S;
                 F2 aM[3] = {F2{0.f, 0.f}, F2{0.f, 0.f}, F2{0.f, 0.f}}, aE = F2{0.f, 0.f};
+                ItemWords<NC, 4> iw;   // the item's four sites share NC Philox blocks (rng.cuh)
+                iw.begin(a.key, a.replica0 + r, sweep, id0, (uint32_t)idStrideZ, PARTIAL);
 #pragma unroll
                 for (int p = 0; p < 2; p++) {
                     uint32_t wa[4], wb[4];
-                    rng4(a.key, a.replica0 + r, STREAM_METRO, 0, sweep, id0 + (uint32_t)((2 * p) * idStrideZ), wa);
-                    rng4(a.key, a.replica0 + r, STREAM_METRO, 0, sweep, id0 + (uint32_t)((2 * p + 1) * idStrideZ), wb);
+                    iw.need(a.key, a.replica0 + r, sweep, 2 * p + 2);
+                    iw.lane(2 * p, PARTIAL, wa);
+                    iw.lane(2 * p + 1, PARTIAL, wb);
                     const F2 sx = s2[0][p], sy = s2[1][p], sz = s2[2][p];
                     const F2 hx = H2[0][p], hy = H2[1][p], hz = H2[2][p];
                     // plane normal m = -n of random_dir: O(3) m = (r cos phi, r sin phi, -z), z = 2u-1; O(2) m = (cos phi, sin phi);
@@ -383,14 +386,16 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                 }
             });
             const uint32_t id0 = (uint32_t)((xy + Z0 * pz + cls.cc()) * norb + cls.co());
-            IsingWords iw;   // Ising: sites of the item that fall into the same block of four ids share one Philox call
+            ItemWords<NC, V> iw;   // V > 1: the item's sites share their Philox blocks (rng.cuh); V == 1: per-site streams
+            if (V > 1) iw.begin(a.key, a.replica0 + r, sweep, id0, (uint32_t)idStrideZ, PARTIAL);
 #pragma unroll
             for (int v = 0; v < V; v++) {
                 real sx = s[0][v], sy = s[1][v], sz = s[2][v];
                 const real hx = H[0][v], hy = H[1][v], hz = H[2][v];
                 uint32_t w[4];
-                if (NC == 1) iw.get(a.key, a.replica0 + r, sweep, id0 + (uint32_t)(v * idStrideZ), PARTIAL, w[2], w[3]);
-                else rng4(a.key, a.replica0 + r, STREAM_METRO, 0, sweep, id0 + (uint32_t)(v * idStrideZ), w);
+                if (V > 1) { iw.need(a.key, a.replica0 + r, sweep, v + 1); iw.lane(v, PARTIAL, w); }
+                else if (NC == 1) { IsingWords one; one.get(a.key, a.replica0 + r, sweep, id0, PARTIAL, w[2], w[3]); }
+                else rng4(a.key, a.replica0 + r, STREAM_METRO, 0, sweep, id0, w);
                 const bool att = PARTIAL ? (u01<real>(w[3]) < pAtt) : true;
                 bool acc;
                 if (NC == 1) {

@@ -215,15 +215,17 @@ __global__ void __launch_bounds__(256) k_struct(StructArgs a, int q0, int nqc, i
                 }
             }
             const uint32_t id0 = (uint32_t)(((x * a.Ly + y) * a.Lz + (Z0 * a.pz + sc.c)) * a.norb + sc.o);
-            IsingWords iw;
+            ItemWords<NC, V> iw;   // same stream convention as pass_body
+            if (MODE != 2 && V > 1) iw.begin(a.key, a.replica0 + r, sweep, id0, (uint32_t)idStrideZ, pAtt < real(1));
 #pragma unroll
             for (int v = 0; v < V; v++) {
                 real sv[3] = {s[0][v], s[1][v], s[2][v]};
                 const real Hv[3] = {H[0][v], H[1][v], H[2][v]};
                 if (MODE != 2) {
                     uint32_t w[4];
-                    if (NC == 1) iw.get(a.key, a.replica0 + r, sweep, id0 + (uint32_t)(v * idStrideZ), pAtt < real(1), w[2], w[3]);
-                    else rng4(a.key, a.replica0 + r, STREAM_METRO, 0, sweep, id0 + (uint32_t)(v * idStrideZ), w);
+                    if (V > 1) { iw.need(a.key, a.replica0 + r, sweep, v + 1); iw.lane(v, pAtt < real(1), w); }
+                    else if (NC == 1) { IsingWords one; one.get(a.key, a.replica0 + r, sweep, id0, pAtt < real(1), w[2], w[3]); }
+                    else rng4(a.key, a.replica0 + r, STREAM_METRO, 0, sweep, id0, w);
                     if (!(pAtt < real(1)) || u01<real>(w[3]) < pAtt) {
                         natt++;
                         if (NC == 1) {
@@ -1474,6 +1476,12 @@ void structured_get_spins(mcg_system *s, int r, double *spins) {
     MCG_CUDA(cudaGetLastError());
     MCG_CUDA(cudaMemcpyAsync(spins, buf, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     MCG_CUDA(cudaStreamSynchronize(s->stream));
+}
+
+void structured_rng_layout(const mcg_system *s, int32_t *stride, int32_t *group) {
+    const StructuredSystem *st = s->st;
+    if (st->V > 1) { *stride = st->p[2] * st->norb; *group = st->V; }   // ItemWords (rng.cuh): ids id0 + v * pz * norb, v < V
+    else { *stride = 0; *group = 0; }
 }
 
 void structured_colour_order(const mcg_system *s, int32_t *order) {

@@ -188,6 +188,12 @@ class System:
         check(_ffi.lib().mcg_colour_order(self._h, ptr(o)))
         return o
 
+    def rng_layout(self):
+        """(stride, group) of the Philox streams of the Metropolis sweeps (csrc/rng.cuh); (0, 0) = one block per site."""
+        a, b = C.c_int32(0), C.c_int32(0)
+        check(_ffi.lib().mcg_rng_layout(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def set_params(self, beta=None, field=None):
         b = f64(beta) if beta is not None else None
         h = f64(field) if field is not None else None

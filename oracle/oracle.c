@@ -52,6 +52,8 @@ typedef struct {
     int ignoreOffDiag;    /* p_diagonalDot = diagonalDot_simple (heisenbergLib.c:592-593) */
     int isingStrideBug;   /* reproduce isingLib.c:30 (linkStrength+i instead of +i*maxNLinking) */
     int wolffHalfMove;    /* reproduce heisenbergLib.c:418 / xyLib.c:362 (residual uses half move) */
+    int rngStride;        /* Philox colour sweeps: 0 = one Philox block per site (table path); S >= 1 = grouped streams of the */
+    int rngGroup;         /*   vectorised structured pass: rngGroup sites with ids base + m*S share their blocks (csrc/rng.cuh) */
 } orc_sys;
 
 /* ------------------------------------------------------------------------------------------ */
@@ -81,6 +83,37 @@ static void rng4(uint64_t seed, uint32_t replica, uint32_t stream, uint32_t sub,
     uint32_t ctr[4] = {site, (uint32_t)sweep, (uint32_t)((sweep >> 32) & 0xFFFFu) | (sub << 16) | (stream << 24), replica};
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     orc_philox4x32(ctr, key, out);
+}
+/* Words of site id for one colour sweep, in the slots the attempt code reads: r[0], r[1] direction, r[2] acceptance,
+ * r[3] attempt probability (partial sweeps).  W = words per attempt = number of spin components.
+ *   stride 0 : per-site blocks (counter word 0 = id); Ising: four consecutive ids share the block id >> 2, word id & 3,
+ *              sub-stream 1 for the attempt-probability uniform.
+ *   stride S : grouped streams - group G = (id/(V*S))*S + id%S, member m = (id/S)%V, word k = W*m + t is word k&3 of the
+ *              block drawn with sub-stream k>>2; attempt probability: word m of sub-stream 7.       (csrc/rng.cuh) */
+static void site_words(const orc_sys *s, uint64_t seed, uint32_t replica, uint64_t sweep, uint32_t id, int partial, uint32_t r[4]) {
+    const int W = s->model;
+    uint32_t b[4];
+    r[0] = r[1] = r[2] = r[3] = 0;
+    if (s->rngStride <= 0) {
+        if (W == 1) {
+            rng4(seed, replica, STREAM_METRO, 0, sweep, id >> 2, b);
+            r[2] = b[id & 3];
+            if (partial) { rng4(seed, replica, STREAM_METRO, 1, sweep, id >> 2, b); r[3] = b[id & 3]; }
+        } else rng4(seed, replica, STREAM_METRO, 0, sweep, id, r);
+        return;
+    }
+    const uint32_t S = (uint32_t)s->rngStride, V = (uint32_t)s->rngGroup;
+    const uint32_t G = (id / (V * S)) * S + id % S, m = (id / S) % V;
+    uint32_t w[3] = {0, 0, 0};
+    for (int t = 0; t < W; t++) {
+        uint32_t k = (uint32_t)W * m + (uint32_t)t;
+        rng4(seed, replica, STREAM_METRO, k >> 2, sweep, G, b);
+        w[t] = b[k & 3];
+    }
+    if (W == 3) { r[0] = w[0]; r[1] = w[1]; r[2] = w[2]; }
+    else if (W == 2) { r[0] = w[0]; r[2] = w[1]; }
+    else r[2] = w[0];
+    if (partial) { rng4(seed, replica, STREAM_METRO, 7, sweep, G, b); r[3] = b[m]; }
 }
 static double u01(uint32_t r) { return ((double)r + 0.5) * (1.0 / 4294967296.0); }
 /* fp32 engine convention: 23 random bits, (k+0.5)/2^23, evaluated exactly in double here */
@@ -567,7 +600,7 @@ int orc_run(const orc_sys *s, int update_mode, long nthermal, long nsweep, long 
         for (int p_ = 0; p_ < N; p_++) {                                                                    \
             int i_ = order[p_];                                                                             \
             uint32_t r_[4];                                                                                 \
-            rng4(seed, replica, STREAM_METRO, 0, sweepCtr, (uint32_t)i_, r_);                               \
+            site_words(s, seed, replica, sweepCtr, (uint32_t)i_, pAtt < 1.0, r_);                           \
             on_attempt_philox(s, sp, i_, r_, f32, pAtt, &st);                                               \
         }                                                                                                   \
         sweepCtr++;                                                                                         \
@@ -656,9 +689,6 @@ static void ising_local_update_ref(const orc_sys *s, double *sp, orc_state *st) 
         sp[i] *= -1; st->tot[0] += sp[i] * 2; st->energy -= corr; st->accepted++;
     }
 }
-/* Ising stream convention of the engine (csrc/rng.cuh): four consecutive site ids share the Philox block whose first
- * counter word is id >> 2 and use word id & 3 of it - sub-stream 0 for the acceptance uniform, sub-stream 1 for the
- * attempt-probability uniform of partial sweeps. */
 static void ising_attempt_philox(const orc_sys *s, double *sp, int i, uint32_t wAcc, uint32_t wAtt, int f32, double pAtt, orc_state *st) {
     if (pAtt < 1.0 && !((f32 ? u01f(wAtt) : u01(wAtt)) < pAtt)) return;
     double corr = orc_ising_flip_corr(s, sp, i);
@@ -743,10 +773,9 @@ int orc_run_ising(const orc_sys *s, int update_mode, long nthermal, long nsweep,
     for (long long q_ = 0; q_ < (count); q_++) {                                                             \
         for (int p_ = 0; p_ < N; p_++) {                                                                     \
             int i_ = order[p_];                                                                              \
-            uint32_t ra_[4], rp_[4] = {0, 0, 0, 0};                                                          \
-            rng4(seed, replica, STREAM_METRO, 0, sweepCtr, (uint32_t)i_ >> 2, ra_);                          \
-            if (pAtt < 1.0) rng4(seed, replica, STREAM_METRO, 1, sweepCtr, (uint32_t)i_ >> 2, rp_);          \
-            ising_attempt_philox(s, sp, i_, ra_[i_ & 3], rp_[i_ & 3], f32, pAtt, &st);                       \
+            uint32_t r_[4];                                                                                  \
+            site_words(s, seed, replica, sweepCtr, (uint32_t)i_, pAtt < 1.0, r_);                            \
+            ising_attempt_philox(s, sp, i_, r_[2], r_[3], f32, pAtt, &st);                                   \
         }                                                                                                    \
         sweepCtr++;                                                                                          \
     }

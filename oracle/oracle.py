@@ -28,7 +28,7 @@ class _Sys(C.Structure):
                 ("pairs", C.c_void_p), ("nG", C.c_int), ("maxG", C.c_int), ("groups", C.c_void_p),
                 ("nR", C.c_int), ("nC", C.c_int), ("rOrb", C.c_void_p), ("rCl", C.c_void_p),
                 ("rNbr", C.c_void_p), ("h", C.c_double), ("ignoreOffDiag", C.c_int),
-                ("isingStrideBug", C.c_int), ("wolffHalfMove", C.c_int)]
+                ("isingStrideBug", C.c_int), ("wolffHalfMove", C.c_int), ("rngStride", C.c_int), ("rngGroup", C.c_int)]
 
 
 def lib():
@@ -100,6 +100,7 @@ class System:
         self.ignoreOffDiag = int(ignoreOffDiag)
         self.isingStrideBug = int(isingStrideBug)
         self.wolffHalfMove = int(wolffHalfMove)
+        self.rng_layout = (0, 0)   # (stride, group) of the Philox colour sweeps: engine.System.rng_layout() of the path under test
 
     @classmethod
     def from_tables(cls, t, h_over_T=0.0, **kw):
@@ -137,6 +138,7 @@ class System:
         s.nR, s.nC, s.rOrb, s.rCl, s.rNbr = self.nR, self.nC, _p(self.rOrb), _p(self.rCl), _p(self.rNbr)
         s.h, s.ignoreOffDiag = self.h, self.ignoreOffDiag
         s.isingStrideBug, s.wolffHalfMove = self.isingStrideBug, self.wolffHalfMove
+        s.rngStride, s.rngGroup = int(self.rng_layout[0]), int(self.rng_layout[1])
         return s
 
     # -- configuration-level functions ------------------------------------------------------

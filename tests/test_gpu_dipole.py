@@ -35,6 +35,7 @@ def test_all_pairs_dipole_on_the_table_path_matches_oracle(model):
         s.set_spins(start)
         assert abs(s.energy() - o.total_energy(start)) <= 1e-12 * max(1.0, abs(o.total_energy(start)))
         order = s.colour_order()
+        o.rng_layout = s.rng_layout()
         r = o.run(2, 7, 1, t.N, order=order, seed=5, spins=start)
         s.metropolis_sweeps(8)
         got = s.get_spins()
@@ -54,6 +55,7 @@ def test_dipole_stencil_on_the_structured_path_matches_oracle(model, L):
     with eng.System.from_spec(spec, model, precision=64, beta=[1 / T], seed=9) as s:
         assert s.num_colours() >= 8                # sites within distance 2 must all differ in colour
         order = s.colour_order()
+        o.rng_layout = s.rng_layout()
         if model == 1:
             start = np.random.RandomState(3).choice([-1.0, 1.0], size=t.N)
         else:

@@ -39,6 +39,7 @@ def test_degenerate_supercells_match_oracle_on_both_paths(L, model):
             s.set_spins(start)
             assert abs(s.energy() - Eo) <= 1e-12 * max(1.0, abs(Eo)), path
             order = s.colour_order()
+            o.rng_layout = s.rng_layout()
             r = o.run(2, 5, 1, t.N, order=order, seed=3, spins=start)
             s.metropolis_sweeps(6)
             got = s.get_spins()

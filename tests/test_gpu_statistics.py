@@ -1,7 +1,7 @@
 """Parity level 2 (north_star): equilibrium observables of the CUDA engine agree with the reference's
-own CPU runs within 3 sigma.  tests/golden/stats.json holds K=8 independently seeded runs of the
+own CPU runs within 3 sigma.  tests/golden/stats.json holds K=48 independently seeded runs of the
 reference's compiled C engines per (model, T, H) point (mean, sigma over seeds); here the engine
-runs K=8 replicas (independent Philox streams) of the same point with the same sweep counts through
+runs K=48 replicas (independent Philox streams) of the same point with the same sweep counts through
 the C ABI and the two sample means are compared with the combined standard error:
     |mean_gpu - mean_ref| <= 3 * sqrt(sigma_gpu^2/K + sigma_ref^2/K) + tol_abs
 autoCorr (slot 7) depends on the update dynamics (random site vs colour sweeps) and is not compared;

@@ -39,6 +39,7 @@ def test_structured_energy_observables_and_trajectory_fp64(case):
     # structured systems take UNSCALED couplings and beta = 1/T per replica
     with eng.System.from_spec(spec, model, precision=64, beta=[1.0 / T], field=[h], seed=4321) as s:
         order = s.colour_order()
+        o.rng_layout = s.rng_layout()
         assert sorted(order.tolist()) == list(range(t.N))
         start = _start(o, t, model, 4321)
         if model != 1:
@@ -75,6 +76,7 @@ def test_structured_whole_run_fused_measurement_matches_oracle(case):
     o = util.oracle_system(t, hT)
     with eng.System.from_spec(spec, model, precision=64, beta=[1.0 / T], field=[h], seed=17) as s:
         order = s.colour_order()
+        o.rng_layout = s.rng_layout()
         s.init_spins(0.3)
         fr = s.run(0, 4, 15, 2 * t.N, spinFrame=3)
         out, grp = s.results()
@@ -161,6 +163,7 @@ def test_structured_groups_in_cell_zero_only():
     o = util.oracle_system(t, 0.3 / 0.7)
     with eng.System.from_spec(spec, 3, precision=64, beta=[1 / 0.7], field=[0.3], seed=5) as s:
         order = s.colour_order()
+        o.rng_layout = s.rng_layout()
         s.init_spins(0.4)
         s.run(0, 2, 6, t.N)
         out, grp = s.results()
@@ -204,6 +207,7 @@ def test_structured_block_spin_statistics_match_table_path_and_oracle(case):
                     assert abs(out[k] - oo[k]) <= 1e-11 * max(1.0, abs(oo[k])), (k, out[k], oo[k])
         # accumulation over a whole run against the oracle's restatement of the loop
         order = s.colour_order()
+        o.rng_layout = s.rng_layout()
         s.set_spins(start)
         s.reset_measurements()
         s.run(0, 2, 6, t.N)
