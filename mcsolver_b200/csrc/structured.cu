@@ -745,11 +745,17 @@ std::string jit_prologue(const mcg_system *s, int colour, bool partial) {
     const bool f32 = s->prec == 32;
     const int q0 = st->colourClassStart[colour], nqc = st->colourClassStart[colour + 1] - q0;
     const int JW = s->NC == 1 ? 1 : 9;
+    // resident blocks per SM the kernel is compiled for (register budget 65536 / (256 * minb)): four for the short link lists
+    // (sc: 64 registers, measured best of 2..5), two once a class has more than 8 links - the unrolled field sums then need the
+    // registers more than the occupancy (CrI3, 12 links: +7 % over four)
+    int maxLinks = 0;
+    for (int j = 0; j < nqc; j++) maxLinks = std::max(maxLinks, st->classes[q0 + j].nlink);
+    const int minb = getenv("MCG_JIT_MINB") ? atoi(getenv("MCG_JIT_MINB")) : (f32 && maxLinks <= 8 ? 4 : 2);
     std::ostringstream o;
     o << "#define MCG_JIT 1\ntypedef " << (f32 ? "float" : "double") << " jit_real;\n";
     if (getenv("MCG_NO_F32X2")) o << "#define MCG_NO_F32X2 1\n";   // A/B switch: scalar fp32 arithmetic instead of packed pairs
     o << "#define JIT_NC " << s->NC << "\n#define JIT_FULLJ " << (s->fullJ ? "true" : "false") << "\n#define JIT_V " << st->V
-      << "\n#define JIT_PARTIAL " << (partial ? "true" : "false") << "\n#define JIT_NQC " << nqc << "\n#define JIT_MINB " << (getenv("MCG_JIT_MINB") ? atoi(getenv("MCG_JIT_MINB")) : (f32 ? 4 : 2)) << "\n";
+      << "\n#define JIT_PARTIAL " << (partial ? "true" : "false") << "\n#define JIT_NQC " << nqc << "\n#define JIT_MINB " << minb << "\n";
     o << "#define JIT_Xd " << st->Xd << "\n#define JIT_Yd " << st->Yd << "\n#define JIT_Zd " << st->Zd << "\n#define JIT_Zc "
       << st->Zd / st->V << "\n#define JIT_N " << s->N << "\n#define JIT_px " << st->p[0] << "\n#define JIT_py " << st->p[1]
       << "\n#define JIT_pz " << st->p[2] << "\n#define JIT_norb " << st->norb << "\n#define JIT_Ly " << st->L[1]
