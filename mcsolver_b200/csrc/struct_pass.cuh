@@ -381,8 +381,21 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                             hz = L.J(7) * tx + L.J(8) * ty + L.J(2) * tz;
                         } else { hx = L.J(0) * tx; hy = L.J(1) * ty; hz = L.J(2) * tz; }
                     }
-                    H[0][v] += hx; H[1][v] += hy; H[2][v] += hz;
-                    if (lowk) { Hl[0][v] += hx; Hl[1][v] += hy; Hl[2][v] += hz; }
+                    if (FULLJ && !lowk) {
+                        // full tensor, link not needed separately for the fused energy: accumulate inside the multiply-add chain
+                        // (three FFMA per component instead of FMUL + two FFMA + FADD)
+                        if (NC == 2) {
+                            H[0][v] = L.J(0) * tx + (L.J(3) * ty + H[0][v]);
+                            H[1][v] = L.J(6) * tx + (L.J(1) * ty + H[1][v]);
+                        } else {
+                            H[0][v] = L.J(0) * tx + (L.J(3) * ty + (L.J(4) * tz + H[0][v]));
+                            H[1][v] = L.J(6) * tx + (L.J(1) * ty + (L.J(5) * tz + H[1][v]));
+                            H[2][v] = L.J(7) * tx + (L.J(8) * ty + (L.J(2) * tz + H[2][v]));
+                        }
+                    } else {
+                        H[0][v] += hx; H[1][v] += hy; H[2][v] += hz;
+                        if (lowk) { Hl[0][v] += hx; Hl[1][v] += hy; Hl[2][v] += hz; }
+                    }
                 }
             });
             const uint32_t id0 = (uint32_t)((xy + Z0 * pz + cls.cc()) * norb + cls.co());
