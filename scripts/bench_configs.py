@@ -13,6 +13,7 @@ rows = []
 
 
 ONLY = os.environ.get("ONLY", "")
+PREC = int(os.environ.get("PREC", "32"))   # 64: fp64 state (w doubles)
 
 
 def run(name, spec, model, R, T, H=None, z=None, nsw=10, meas=True):
@@ -20,13 +21,13 @@ def run(name, spec, model, R, T, H=None, z=None, nsw=10, meas=True):
         return
     spec = spec() if callable(spec) else spec
     H = np.zeros(R) if H is None else H
-    with engine.System.from_spec(spec, model, precision=32, nReplica=R, beta=1 / np.asarray(T, float), field=H, seed=1) as s:
+    with engine.System.from_spec(spec, model, precision=PREC, nReplica=R, beta=1 / np.asarray(T, float), field=H, seed=1) as s:
         C = s.num_colours()
         s.init_spins(0.0)
         s.timed_sweeps(3, with_measure=meas)
         ms = s.timed_sweeps(nsw, with_measure=meas)
         att = R * spec.nsite * nsw / (ms * 1e-3)
-        w = 4 * model
+        w = (PREC // 8) * model
         balg = (2 + min(C - 1, z)) * w
         rows.append(dict(config=name, N=spec.nsite, replicas=R, colours=C, z=z, attempts_per_s=att, B_alg=balg, GBps=att * balg / 1e9,
                          roofline_frac=att * balg / PEAK, ms_per_sweep=ms / nsw))
@@ -42,5 +43,5 @@ run("C3 CrI3 honeycomb 512^2 (1NN+2NN+3NN, D)", lambda: spec_of("cri3", (512, 51
 run("C4 skyrmion hex 1024^2 (DMI, D, h, Q)", lambda: spec_of("skyrmion", (1024, 1024, 1)), 3, 16, np.full(16, 0.3), H=np.linspace(0, 0.7, 16), z=3)
 run("C5 Heisenberg sc 256^3 T-scan", lambda: cu(256), 3, 8, 0.8 * 1.443 * (1.3 / 0.8) ** (np.arange(8) / 7), z=6)
 run("C5 + dipole stencil r<=2 (32 links), 128^3", lambda: add_dipole_stencil(cu(128), 0.1, 2.0), 3, 8, np.linspace(1.2, 1.9, 8), z=32, nsw=4)
-if not ONLY:
+if not ONLY and PREC == 32:
     json.dump(rows, open("gpurun_out/configs_r1.json", "w"), indent=1)
