@@ -27,7 +27,7 @@ struct SLinkD {
     int o2, dx, dy, dz;   // neighbour orbital and cell offset reduced to [0,L): its reference id without decoding
 };
 struct SClassD {
-    int a, b, c, o, colour, nlink, lowmode, pad;
+    int a, b, c, o, colour, nlink, lowmode, pad;   // pad: number of leading links into lower colours (links are sorted low-first)
     double S, D[3];
 };
 
@@ -109,7 +109,7 @@ template <typename real> struct PLink {
 };
 template <typename real> struct PassTable {
     int nl, nqc, uniformJ, pad1;   // uniformJ: every link of every class of the pass carries the same diagonal exchange
-    int ca[PT_MAXC], cb[PT_MAXC], cc[PT_MAXC], co[PT_MAXC], lowmode[PT_MAXC];
+    int ca[PT_MAXC], cb[PT_MAXC], cc[PT_MAXC], co[PT_MAXC], lowmode[PT_MAXC], nlow[PT_MAXC];
     real S[PT_MAXC], D[PT_MAXC][3];
     PLink<real> L[PT_MAXC][PT_MAXL];
 };
@@ -117,6 +117,8 @@ template <typename real> struct PassTable {
 // runtime views (offline build)
 template <typename real> struct RtLink {
     const PLink<real> &L;
+    int k;
+    __device__ __forceinline__ int idx() const { return k; }
     __device__ __forceinline__ int delta() const { return L.delta; }
     __device__ __forceinline__ int mxp() const { return L.mxp; }
     __device__ __forceinline__ int mxm() const { return L.mxm; }
@@ -135,12 +137,13 @@ template <typename real> struct RtClass {
     __device__ __forceinline__ int cc() const { return T.cc[j]; }
     __device__ __forceinline__ int co() const { return T.co[j]; }
     __device__ __forceinline__ int lowmode() const { return T.lowmode[j]; }
+    __device__ __forceinline__ int nlow() const { return T.nlow[j]; }
     __device__ __forceinline__ real S() const { return T.S[j]; }
     __device__ __forceinline__ real D(int e) const { return T.D[j][e]; }
     __device__ __forceinline__ bool uniformJ() const { return T.uniformJ != 0; }
     template <typename F> __device__ __forceinline__ void for_links(F &&f) const {
         const int n = T.nl;
-        for (int k = 0; k < n; k++) f(RtLink<real>{T.L[j][k]});
+        for (int k = 0; k < n; k++) f(RtLink<real>{T.L[j][k], k});
     }
 };
 
@@ -170,7 +173,7 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
     const int px = MCG_DIM(a, px), py = MCG_DIM(a, py), pz = MCG_DIM(a, pz), norb = MCG_DIM(a, norb);
     const int Ly = MCG_DIM(a, Ly), Lz = MCG_DIM(a, Lz), nrows = MCG_DIM(a, nrows), nclass = MCG_DIM(a, nclass);
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    const int lowmode = cls.lowmode();
+    const int lowmode = cls.lowmode(), nlow = cls.nlow();
     const real S = cls.S();
     const real D0 = cls.D(0), D1 = cls.D(1), D2 = cls.D(2);
     const bool hasD = D0 != real(0) || D1 != real(0) || D2 != real(0);   // a literal under JIT: the D terms fold away
@@ -214,7 +217,6 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                     float t[3][4];
 #pragma unroll
                     for (int c = 0; c < NC; c++) load_shifted<float, 4>((const float *)sp + (size_t)c * N + nb, Z0, L.cZ(), Zd, t[c]);
-                    const bool lowk = MODE == 1 && lowmode == 2 && L.low();
                     // aligned row, one diagonal exchange shared by every link of the class (its splat lives in one register
                     // pair): packed multiply-add straight from the float4.  Distinct tensors per link would each need their
                     // constant moved into a pair, where the scalar FFMA takes it as an immediate - measured slower (CrI3).
@@ -226,7 +228,6 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                                 const F2 t2 = F2{t[c][2 * p], t[c][2 * p + 1]};
                                 const F2 J2 = splat2((float)L.J(c));
                                 H2[c][p] = fma2(J2, t2, H2[c][p]);
-                                if (lowk) Hl2[c][p] = fma2(J2, t2, Hl2[c][p]);
                             }
                     } else {
 #pragma unroll
@@ -245,13 +246,13 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                             float &Hy = (v & 1) ? H2[1][v >> 1].y : H2[1][v >> 1].x;
                             Hx += hx; Hy += hy;
                             if (NC == 3) { float &Hz = (v & 1) ? H2[2][v >> 1].y : H2[2][v >> 1].x; Hz += hz; }
-                            if (lowk) {
-                                float &Lx_ = (v & 1) ? Hl2[0][v >> 1].y : Hl2[0][v >> 1].x;
-                                float &Ly_ = (v & 1) ? Hl2[1][v >> 1].y : Hl2[1][v >> 1].x;
-                                Lx_ += hx; Ly_ += hy;
-                                if (NC == 3) { float &Lz_ = (v & 1) ? Hl2[2][v >> 1].y : Hl2[2][v >> 1].x; Lz_ += hz; }
-                            }
                         }
+                    }
+                    // links are sorted with the lower-colour neighbours first: after the last of them the running sum IS the
+                    // field of the final neighbours that the fused bond energy needs
+                    if (MODE == 1 && lowmode == 2 && L.idx() == nlow - 1) {
+#pragma unroll
+                        for (int c = 0; c < 3; c++) { Hl2[c][0] = H2[c][0]; Hl2[c][1] = H2[c][1]; }
                     }
                 });
                 const uint32_t id0 = (uint32_t)((xy + Z0 * pz + cls.cc()) * norb + cls.co());
@@ -365,7 +366,6 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                 real t[3][V];
 #pragma unroll
                 for (int c = 0; c < NC; c++) load_shifted<real, V>(sp + (size_t)c * N + nb, Z0, L.cZ(), Zd, t[c]);
-                const bool lowk = MODE == 1 && lowmode == 2 && L.low();
 #pragma unroll
                 for (int v = 0; v < V; v++) {
                     const real tx = t[0][v], ty = NC >= 2 ? t[1][v] : real(0), tz = NC == 3 ? t[2][v] : real(0);
@@ -381,9 +381,9 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                             hz = L.J(7) * tx + L.J(8) * ty + L.J(2) * tz;
                         } else { hx = L.J(0) * tx; hy = L.J(1) * ty; hz = L.J(2) * tz; }
                     }
-                    if (FULLJ && !lowk) {
-                        // full tensor, link not needed separately for the fused energy: accumulate inside the multiply-add chain
-                        // (three FFMA per component instead of FMUL + two FFMA + FADD)
+                    if (FULLJ) {
+                        // full tensor: accumulate inside the multiply-add chain (three FFMA per component instead of FMUL + two
+                        // FFMA + FADD)
                         if (NC == 2) {
                             H[0][v] = L.J(0) * tx + (L.J(3) * ty + H[0][v]);
                             H[1][v] = L.J(6) * tx + (L.J(1) * ty + H[1][v]);
@@ -392,10 +392,14 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                             H[1][v] = L.J(6) * tx + (L.J(1) * ty + (L.J(5) * tz + H[1][v]));
                             H[2][v] = L.J(7) * tx + (L.J(8) * ty + (L.J(2) * tz + H[2][v]));
                         }
-                    } else {
-                        H[0][v] += hx; H[1][v] += hy; H[2][v] += hz;
-                        if (lowk) { Hl[0][v] += hx; Hl[1][v] += hy; Hl[2][v] += hz; }
-                    }
+                    } else { H[0][v] += hx; H[1][v] += hy; H[2][v] += hz; }
+                }
+                // lower-colour neighbours come first in the link list: snapshot their field for the fused bond energy
+                if (MODE == 1 && lowmode == 2 && L.idx() == nlow - 1) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++)
+#pragma unroll
+                        for (int v = 0; v < V; v++) Hl[c][v] = H[c][v];
                 }
             });
             const uint32_t id0 = (uint32_t)((xy + Z0 * pz + cls.cc()) * norb + cls.co());
@@ -509,6 +513,7 @@ template <int JJ, int K> struct CtLink {
     __device__ __forceinline__ constexpr int mym() const { return D::mym; }
     __device__ __forceinline__ constexpr int cZ() const { return D::cZ; }
     __device__ __forceinline__ constexpr int low() const { return D::low; }
+    __device__ __forceinline__ constexpr int idx() const { return K; }
     __device__ __forceinline__ constexpr jit_real J(int e) const { return D::J(e); }
 };
 template <int JJ> struct CtClass {
@@ -519,6 +524,7 @@ template <int JJ> struct CtClass {
     __device__ __forceinline__ constexpr int cc() const { return C::cc; }
     __device__ __forceinline__ constexpr int co() const { return C::co; }
     __device__ __forceinline__ constexpr int lowmode() const { return C::lowmode; }
+    __device__ __forceinline__ constexpr int nlow() const { return C::nlow; }
     __device__ __forceinline__ constexpr jit_real S() const { return C::S; }
     __device__ __forceinline__ constexpr jit_real D(int e) const { return C::D(e); }
     template <int K> static __device__ __forceinline__ constexpr bool uj_from() {

@@ -764,7 +764,7 @@ std::string jit_prologue(const mcg_system *s, int colour, bool partial) {
     for (int j = 0; j < nqc; j++) {
         const SClassD &cl = st->classes[q0 + j];
         o << "template <> struct CtClassData<" << j << "> { static constexpr int nl=" << cl.nlink << ", ca=" << cl.a << ", cb=" << cl.b
-          << ", cc=" << cl.c << ", co=" << cl.o << ", lowmode=" << cl.lowmode << "; static constexpr jit_real S=" << lit(std::fabs(cl.S), f32)
+          << ", cc=" << cl.c << ", co=" << cl.o << ", lowmode=" << cl.lowmode << ", nlow=" << cl.pad << "; static constexpr jit_real S=" << lit(std::fabs(cl.S), f32)
           << "; static __device__ constexpr jit_real D(int e) { constexpr jit_real v[3] = {" << lit(cl.D[0], f32) << "," << lit(cl.D[1], f32)
           << "," << lit(cl.D[2], f32) << "}; return v[e]; } };\n";
         for (int k = 0; k < cl.nlink; k++) {
@@ -1176,6 +1176,27 @@ static void structured_build_host(mcg_system *s, const mcg_lattice_desc *d, std:
             for (int e = 0; e < JW; e++) Jt[((size_t)q * MAXLINK + k) * JW + e] = t.J[e];
         }
         cl.lowmode = nlow == 0 ? 0 : (nlow == nreal ? 1 : 2);
+        // links to lower colours first: the field of the already final neighbours (the bond-energy part of the fused
+        // measurement) is then simply the running field sum after the first nlow links - no second accumulator per link
+        {
+            std::vector<int> perm(cl.nlink);
+            for (int k = 0; k < cl.nlink; k++) perm[k] = k;
+            std::stable_sort(perm.begin(), perm.end(), [&](int x, int y) { return links[(size_t)q * MAXLINK + x].low > links[(size_t)q * MAXLINK + y].low; });
+            std::vector<SLinkD> l2(cl.nlink);
+            std::vector<int> cx2(cl.nlink), cy2(cl.nlink);
+            std::vector<double> j2((size_t)cl.nlink * JW);
+            for (int k = 0; k < cl.nlink; k++) {
+                const size_t src = (size_t)q * MAXLINK + perm[k];
+                l2[k] = links[src]; cx2[k] = st->cXs[src]; cy2[k] = st->cYs[src];
+                for (int e = 0; e < JW; e++) j2[(size_t)k * JW + e] = Jt[src * JW + e];
+            }
+            for (int k = 0; k < cl.nlink; k++) {
+                const size_t dst = (size_t)q * MAXLINK + k;
+                links[dst] = l2[k]; st->cXs[dst] = cx2[k]; st->cYs[dst] = cy2[k];
+                for (int e = 0; e < JW; e++) Jt[dst * JW + e] = j2[(size_t)k * JW + e];
+            }
+        }
+        cl.pad = nlow;   // number of leading links into lower colours
     }
     st->linksHost = links;
     st->JHost = Jt;
@@ -1202,7 +1223,7 @@ static void structured_build_host(mcg_system *s, const mcg_lattice_desc *d, std:
                     if (Jt[((size_t)(q0 + j) * MAXLINK + k) * JW + c] != Jt[(size_t)q0 * MAXLINK * JW + c]) P->uniformJ = 0;
         for (int j = 0; j < nqc; j++) {
             const SClassD &cl = st->classes[q0 + j];
-            P->ca[j] = cl.a; P->cb[j] = cl.b; P->cc[j] = cl.c; P->co[j] = cl.o; P->lowmode[j] = cl.lowmode;
+            P->ca[j] = cl.a; P->cb[j] = cl.b; P->cc[j] = cl.c; P->co[j] = cl.o; P->lowmode[j] = cl.lowmode; P->nlow[j] = cl.pad;
             P->S[j] = (real)std::fabs(cl.S);
             for (int e = 0; e < 3; e++) P->D[j][e] = (real)cl.D[e];
             for (int k = 0; k < nlp; k++) {
