@@ -99,6 +99,48 @@ __device__ __forceinline__ void load_shifted(const real *__restrict__ row, int Z
     }
 }
 
+// the NC component rows of one neighbour at once: ONE decision on the shift for all components (with a runtime link
+// table the per-component version re-branched three times and kept three copies of the address arithmetic alive)
+template <typename real, int V, int NC>
+__device__ __forceinline__ void load_shifted_nc(const real *__restrict__ base, size_t N, int Z0, int cZ, int Zd, real (&o)[3][V]) {
+    if (cZ == 0) {
+#pragma unroll
+        for (int c = 0; c < NC; c++) vload<real, V>(base + (size_t)c * N + Z0, o[c]);
+    } else if (V > 1 && cZ == -1) {
+        const int zl = Z0 == 0 ? Zd - 1 : Z0 - 1;
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            real t[V];
+            vload<real, V>(base + (size_t)c * N + Z0, t);
+            o[c][0] = base[(size_t)c * N + zl];
+#pragma unroll
+            for (int i = 1; i < V; i++) o[c][i] = t[i - 1];
+        }
+    } else if (V > 1 && cZ == 1) {
+        const int zr = Z0 + V >= Zd ? 0 : Z0 + V;
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            real t[V];
+            vload<real, V>(base + (size_t)c * N + Z0, t);
+#pragma unroll
+            for (int i = 0; i < V - 1; i++) o[c][i] = t[i + 1];
+            o[c][V - 1] = base[(size_t)c * N + zr];
+        }
+    } else {
+        int z[V];
+#pragma unroll
+        for (int i = 0; i < V; i++) {
+            z[i] = Z0 + i + cZ;
+            if (z[i] < 0) z[i] += Zd;
+            if (z[i] >= Zd) z[i] -= Zd;
+        }
+#pragma unroll
+        for (int c = 0; c < NC; c++)
+#pragma unroll
+            for (int i = 0; i < V; i++) o[c][i] = base[(size_t)c * N + z[i]];
+    }
+}
+
 // ---- link / class tables of one colour pass ----
 constexpr int PT_MAXC = 8, PT_MAXL = 32;
 template <typename real> struct PLink {
@@ -110,12 +152,16 @@ template <typename real> struct PLink {
 template <typename real> struct PassTable {
     int nl, nqc, uniformJ, pad1;   // uniformJ: every link of every class of the pass carries the same diagonal exchange
     int ca[PT_MAXC], cb[PT_MAXC], cc[PT_MAXC], co[PT_MAXC], lowmode[PT_MAXC], nlow[PT_MAXC];
+    // links are sorted (lower colours first; within each half by Z-shift kind 0, -1, +1, other): gend[j][4*half + kind] is
+    // the end index of that run, so every run is a loop whose shift is a compile-time constant
+    int gend[PT_MAXC][8];
     real S[PT_MAXC], D[PT_MAXC][3];
     PLink<real> L[PT_MAXC][PT_MAXL];
 };
 
 // runtime views (offline build)
-template <typename real> struct RtLink {
+// CZ: the link's Z shift when the run it belongs to fixes it (0, -1, +1), 2 = read it from the table
+template <typename real, int CZ = 2> struct RtLink {
     const PLink<real> &L;
     int k;
     __device__ __forceinline__ int idx() const { return k; }
@@ -124,7 +170,7 @@ template <typename real> struct RtLink {
     __device__ __forceinline__ int mxm() const { return L.mxm; }
     __device__ __forceinline__ int myp() const { return L.myp; }
     __device__ __forceinline__ int mym() const { return L.mym; }
-    __device__ __forceinline__ int cZ() const { return L.cZ; }
+    __device__ __forceinline__ int cZ() const { return CZ == 2 ? L.cZ : CZ; }
     __device__ __forceinline__ int low() const { return L.low; }
     __device__ __forceinline__ real J(int e) const { return L.J[e]; }
 };
@@ -141,9 +187,24 @@ template <typename real> struct RtClass {
     __device__ __forceinline__ real S() const { return T.S[j]; }
     __device__ __forceinline__ real D(int e) const { return T.D[j][e]; }
     __device__ __forceinline__ bool uniformJ() const { return T.uniformJ != 0; }
-    template <typename F> __device__ __forceinline__ void for_links(F &&f) const {
-        const int n = T.nl;
-        for (int k = 0; k < n; k++) f(RtLink<real>{T.L[j][k], k});
+    // f on every link; snap once after the leading nlow links (the lower-colour neighbours).  Two loops instead of a
+    // test inside one: the snapshot is a dozen register moves that were predicated into every iteration
+    template <int CZ, typename F> __device__ __forceinline__ void run(int &k, int kend, F &&f) const {
+        // two links per trip: the second link's loads are issued before the first one's multiply-adds retire
+#pragma unroll 2
+        for (; k < kend; k++) f(RtLink<real, CZ>{T.L[j][k], k});
+    }
+    template <typename F, typename G> __device__ __forceinline__ void for_links(F &&f, G &&snap) const {
+        int k = 0;
+#pragma unroll 1
+        for (int part = 0; part < 2; part++) {
+            const int *ge = T.gend[j] + 4 * part;
+            run<0>(k, ge[0], f);
+            run<-1>(k, ge[1], f);
+            run<1>(k, ge[2], f);
+            run<2>(k, ge[3], f);
+            if (part == 0) snap();
+        }
     }
 };
 
@@ -168,12 +229,19 @@ template <int I, int N, typename F> __device__ __forceinline__ void ct_for(F &&f
 // full sweep drops the fourth uniform, its compare and the attempt counter from the per-site code.
 template <int NC, typename real, bool FULLJ, int MODE, int V, bool PARTIAL, typename CLS>
 __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, int q, int r, int rb, int rowsPerBlock, uint64_t sweep,
-                                          real pAtt, double *red) {
+                                          real pAtt, double *red, float4 *hls = nullptr) {
+    // hls (offline full-tensor kernel only): per-thread shared-memory parking for the lower-colour field snapshot, so its
+    // 12 registers are free while the remaining links stream in
+#ifndef MCG_JIT
+    constexpr bool PARK = FULLJ && NC == 3 && MODE == 1 && V == 4 && sizeof(real) == 4;
+#else
+    constexpr bool PARK = false;
+#endif
     const int Xd = MCG_DIM(a, Xd), Yd = MCG_DIM(a, Yd), Zd = MCG_DIM(a, Zd), Zc = MCG_DIM(a, Zc), N = MCG_DIM(a, N);
     const int px = MCG_DIM(a, px), py = MCG_DIM(a, py), pz = MCG_DIM(a, pz), norb = MCG_DIM(a, norb);
     const int Ly = MCG_DIM(a, Ly), Lz = MCG_DIM(a, Lz), nrows = MCG_DIM(a, nrows), nclass = MCG_DIM(a, nclass);
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    const int lowmode = cls.lowmode(), nlow = cls.nlow();
+    const int lowmode = cls.lowmode();
     const real S = cls.S();
     const real D0 = cls.D(0), D1 = cls.D(1), D2 = cls.D(2);
     const bool hasD = D0 != real(0) || D1 != real(0) || D2 != real(0);   // a literal under JIT: the D terms fold away
@@ -215,8 +283,7 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                 cls.for_links([&](auto L) {
                     const int nb = rowBase + L.delta() + L.mxp() * wxp + L.mxm() * wxm + L.myp() * wyp + L.mym() * wym;
                     float t[3][4];
-#pragma unroll
-                    for (int c = 0; c < NC; c++) load_shifted<float, 4>((const float *)sp + (size_t)c * N + nb, Z0, L.cZ(), Zd, t[c]);
+                    load_shifted_nc<float, 4, NC>((const float *)sp + nb, (size_t)N, Z0, L.cZ(), Zd, t);
                     // aligned row, one diagonal exchange shared by every link of the class (its splat lives in one register
                     // pair): packed multiply-add straight from the float4.  Distinct tensors per link would each need their
                     // constant moved into a pair, where the scalar FFMA takes it as an immediate - measured slower (CrI3).
@@ -248,9 +315,10 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                             if (NC == 3) { float &Hz = (v & 1) ? H2[2][v >> 1].y : H2[2][v >> 1].x; Hz += hz; }
                         }
                     }
+                }, [&]() {
                     // links are sorted with the lower-colour neighbours first: after the last of them the running sum IS the
                     // field of the final neighbours that the fused bond energy needs
-                    if (MODE == 1 && lowmode == 2 && L.idx() == nlow - 1) {
+                    if (MODE == 1 && lowmode == 2) {
 #pragma unroll
                         for (int c = 0; c < 3; c++) { Hl2[c][0] = H2[c][0]; Hl2[c][1] = H2[c][1]; }
                     }
@@ -364,8 +432,7 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
             cls.for_links([&](auto L) {
                 const int nb = rowBase + L.delta() + L.mxp() * wxp + L.mxm() * wxm + L.myp() * wyp + L.mym() * wym;
                 real t[3][V];
-#pragma unroll
-                for (int c = 0; c < NC; c++) load_shifted<real, V>(sp + (size_t)c * N + nb, Z0, L.cZ(), Zd, t[c]);
+                load_shifted_nc<real, V, NC>(sp + nb, (size_t)N, Z0, L.cZ(), Zd, t);
 #pragma unroll
                 for (int v = 0; v < V; v++) {
                     const real tx = t[0][v], ty = NC >= 2 ? t[1][v] : real(0), tz = NC == 3 ? t[2][v] : real(0);
@@ -394,14 +461,29 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                         }
                     } else { H[0][v] += hx; H[1][v] += hy; H[2][v] += hz; }
                 }
+            }, [&]() {
                 // lower-colour neighbours come first in the link list: snapshot their field for the fused bond energy
-                if (MODE == 1 && lowmode == 2 && L.idx() == nlow - 1) {
+                if (MODE == 1 && lowmode == 2) {
+                    if constexpr (PARK) {
 #pragma unroll
-                    for (int c = 0; c < 3; c++)
+                        for (int c = 0; c < 3; c++) hls[c * 256 + tid] = make_float4((float)H[c][0], (float)H[c][1], (float)H[c][2], (float)H[c][3]);
+                    } else {
 #pragma unroll
-                        for (int v = 0; v < V; v++) Hl[c][v] = H[c][v];
+                        for (int c = 0; c < 3; c++)
+#pragma unroll
+                            for (int v = 0; v < V; v++) Hl[c][v] = H[c][v];
+                    }
                 }
             });
+            if constexpr (PARK) {
+                if (lowmode == 2) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const float4 h4 = hls[c * 256 + tid];
+                        Hl[c][0] = (real)h4.x; Hl[c][1] = (real)h4.y; Hl[c][2] = (real)h4.z; Hl[c][3] = (real)h4.w;
+                    }
+                }
+            }
             const uint32_t id0 = (uint32_t)((xy + Z0 * pz + cls.cc()) * norb + cls.co());
             ItemWords<NC, V> iw;   // V > 1: the item's sites share their Philox blocks (rng.cuh); V == 1: per-site streams
             if (V > 1) iw.begin(a.key, a.replica0 + r, sweep, id0, (uint32_t)idStrideZ, PARTIAL);
@@ -491,15 +573,19 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
 
 #ifndef MCG_JIT
 // offline entry: tables as a __grid_constant__ parameter
+// full 3x3 tensors on three components (DMI, dipole stencils: up to 32 links) need more than 64 registers to keep the
+// four sites' field sums, the fused-energy snapshot and a neighbour's 12 values live: 3 resident blocks instead of 4
 template <int NC, typename real, bool FULLJ, int MODE, int V, bool PARTIAL>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, (FULLJ && NC == 3 && sizeof(real) == 4) ? 3 : 4)
 k_struct_fast(const __grid_constant__ StructArgs a, const __grid_constant__ PassTable<real> T, int q0, int rowsPerBlock, int nrb,
               uint64_t sweep, real pAtt) {
     __shared__ double red[4 * 32];
+    constexpr bool PARK = FULLJ && NC == 3 && MODE == 1 && V == 4 && sizeof(real) == 4;
+    __shared__ float4 hls[PARK ? 3 * 256 : 1];
     const int nqc = T.nqc;
     const int bid = blockIdx.x;
     const int j = bid % nqc, tq = bid / nqc, rb = tq % nrb, r = tq / nrb;
-    pass_body<NC, real, FULLJ, MODE, V, PARTIAL>(a, RtClass<real>{T, j}, q0 + j, r, rb, rowsPerBlock, sweep, pAtt, red);
+    pass_body<NC, real, FULLJ, MODE, V, PARTIAL>(a, RtClass<real>{T, j}, q0 + j, r, rb, rowsPerBlock, sweep, pAtt, red, hls);
 }
 #else
 // ---- JIT entry points: JIT_NC, jit_real, JIT_FULLJ, JIT_V, JIT_NQC, JIT_PARTIAL, JIT_MINB, CtLinkData<J,K>, CtClassData<J>
@@ -534,8 +620,12 @@ template <int JJ> struct CtClass {
                    CtLinkData<JJ, K>::J(2) == CtLinkData<JJ, 0>::J(2) && uj_from<K + 1>();
     }
     __device__ __forceinline__ constexpr bool uniformJ() const { return uj_from<0>(); }
-    template <typename F> __device__ __forceinline__ void for_links(F &&f) const {
-        ct_for<0, C::nl>([&](auto k) { f(CtLink<JJ, decltype(k)::value>{}); });
+    template <typename F, typename G> __device__ __forceinline__ void for_links(F &&f, G &&snap) const {
+        if constexpr (C::nlow == 0) snap();
+        ct_for<0, C::nl>([&](auto k) {
+            f(CtLink<JJ, decltype(k)::value>{});
+            if constexpr (decltype(k)::value == C::nlow - 1) snap();
+        });
     }
 };
 

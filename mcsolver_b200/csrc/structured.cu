@@ -305,25 +305,36 @@ __global__ void __launch_bounds__(256) k_struct(StructArgs a, int q0, int nqc, i
 
 
 // classSums -> the raw per-sweep sums the common finalize kernel consumes; clears classSums
-__global__ void k_struct_fold(StructArgs a, int R, int NC, int prec, int pair_s, int pair_t, int selfPairs, double nLat, double *sums, int nG,
+__global__ void __launch_bounds__(32) k_struct_fold(StructArgs a, int R, int NC, int prec, int pair_s, int pair_t, int selfPairs, double nLat, double *sums, int nG,
                               const int *__restrict__ gmask, int groupInSC, double *gacc, const int32_t *slot) {
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per replica, lanes over the classes (a dipole stencil has 64 of them; one thread walking them through
+    // read-modify-writes of global memory took 85 us per sweep)
+    const int r = blockIdx.x, lane = threadIdx.x;
     if (r >= R) return;
-    double *s = sums + (size_t)r * NSUM;
-    for (int q = 0; q < a.nclass; q++) {
+    double v[11];   // tot[3], si[3], sj[3], E, sij
+#pragma unroll
+    for (int i = 0; i < 11; i++) v[i] = 0.0;
+    for (int q = lane; q < a.nclass; q += 32) {
         const double *c = a.classSums + ((size_t)r * a.nclass + q) * 4;
         const SClassD &cl = a.classes[q];
-        for (int k = 0; k < 3; k++) {
-            s[SUM_TOT + k] += c[k];
-            if (cl.o == pair_s) s[SUM_SI + k] += c[k];
-            if (cl.o == pair_t) s[SUM_SJ + k] += c[k];
-        }
-        s[SUM_E] += c[3];
-        if (selfPairs && cl.o == pair_s) s[SUM_SIJ] += cl.S * cl.S * (nLat / (a.nclass / a.norb));
+        const double c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3];
+        v[0] += c0; v[1] += c1; v[2] += c2;
+        if (cl.o == pair_s) { v[3] += c0; v[4] += c1; v[5] += c2; }
+        if (cl.o == pair_t) { v[6] += c0; v[7] += c1; v[8] += c2; }
+        v[9] += c3;
+        if (selfPairs && cl.o == pair_s) v[10] += cl.S * cl.S * (nLat / (a.nclass / a.norb));
+    }
+#pragma unroll
+    for (int i = 0; i < 11; i++) v[i] = warp_sum(v[i]);
+    double *s = sums + (size_t)r * NSUM;
+    if (lane == 0) {
+        for (int k = 0; k < 3; k++) { s[SUM_TOT + k] += v[k]; s[SUM_SI + k] += v[3 + k]; s[SUM_SJ + k] += v[6 + k]; }
+        s[SUM_E] += v[9];
+        s[SUM_SIJ] += v[10];
     }
     // orbital-group statistics (heisenbergLib.c:806-830): group sums are sums of class sums ("Supergroup")
     // or the listed orbitals of cell (0,0,0); the last "group" is totSpin/nLat
-    if (nG > 0) {
+    if (nG > 0 && lane == 0) {
         const int n1 = nG + 1;
         double *G = gacc + (size_t)slot[r] * (n1 + 1) * n1;
         double g[17][3];
@@ -353,7 +364,8 @@ __global__ void k_struct_fold(StructArgs a, int R, int NC, int prec, int pair_s,
                 if (x == y) G[n1 * n1 + x] += d * d;
             }
     }
-    for (int q = 0; q < a.nclass; q++) {
+    __syncwarp();
+    for (int q = lane; q < a.nclass; q += 32) {
         double *c = a.classSums + ((size_t)r * a.nclass + q) * 4;
         c[0] = c[1] = c[2] = c[3] = 0.0;
     }
@@ -1181,7 +1193,13 @@ static void structured_build_host(mcg_system *s, const mcg_lattice_desc *d, std:
         {
             std::vector<int> perm(cl.nlink);
             for (int k = 0; k < cl.nlink; k++) perm[k] = k;
-            std::stable_sort(perm.begin(), perm.end(), [&](int x, int y) { return links[(size_t)q * MAXLINK + x].low > links[(size_t)q * MAXLINK + y].low; });
+            // within each half: aligned rows, then Z shift -1, +1, others (runs with a fixed shift, struct_pass.cuh: PassTable::gend)
+            auto zkind = [](int cz) { return cz == 0 ? 0 : cz == -1 ? 1 : cz == 1 ? 2 : 3; };
+            std::stable_sort(perm.begin(), perm.end(), [&](int x, int y) {
+                const SLinkD &lx = links[(size_t)q * MAXLINK + x], &ly = links[(size_t)q * MAXLINK + y];
+                if (lx.low != ly.low) return lx.low > ly.low;
+                return zkind(lx.cZ) < zkind(ly.cZ);
+            });
             std::vector<SLinkD> l2(cl.nlink);
             std::vector<int> cx2(cl.nlink), cy2(cl.nlink);
             std::vector<double> j2((size_t)cl.nlink * JW);
@@ -1226,6 +1244,17 @@ static void structured_build_host(mcg_system *s, const mcg_lattice_desc *d, std:
             P->ca[j] = cl.a; P->cb[j] = cl.b; P->cc[j] = cl.c; P->co[j] = cl.o; P->lowmode[j] = cl.lowmode; P->nlow[j] = cl.pad;
             P->S[j] = (real)std::fabs(cl.S);
             for (int e = 0; e < 3; e++) P->D[j][e] = (real)cl.D[e];
+            {   // run boundaries; the zero-J pads of a shorter class are not visited at all
+                auto zkind = [](int cz) { return cz == 0 ? 0 : cz == -1 ? 1 : cz == 1 ? 2 : 3; };
+                int k = 0;
+                for (int half = 0; half < 2; half++)
+                    for (int kind = 0; kind < 4; kind++) {
+                        const int hend = half == 0 ? cl.pad : cl.nlink;
+                        while (k < hend && zkind(links[(size_t)(q0 + j) * MAXLINK + k].cZ) == kind) k++;
+                        P->gend[j][4 * half + kind] = k;
+                    }
+                if (k != cl.nlink) return;   // not sorted as expected: leave this colour to the generic kernel
+            }
             for (int k = 0; k < nlp; k++) {
                 PLink<real> &L = P->L[j][k];
                 if (k >= cl.nlink) { L.delta = 0; L.mxp = L.mxm = L.myp = L.mym = 0; L.cZ = 0; L.low = 0; continue; }   // zero-J pad: own cell
@@ -1585,7 +1614,7 @@ static void fold_and_extras(mcg_system *s) {
     StructuredSystem *st = s->st;
     StructArgs a = struct_args(s);
     s->launches++;
-    k_struct_fold<<<(s->R + 63) / 64, 64, 0, s->stream>>>(a, s->R, s->NC, s->prec, st->pair_s, st->pair_t, st->selfPairs ? 1 : 0, (double)s->nLat, s->d_sums,
+    k_struct_fold<<<s->R, 32, 0, s->stream>>>(a, s->R, s->NC, s->prec, st->pair_s, st->pair_t, st->selfPairs ? 1 : 0, (double)s->nLat, s->d_sums,
                                                           s->nG, st->d_gmask, st->groupInSC ? 1 : 0, s->d_gacc, s->d_slot);
     if (!st->selfPairs) {
         dim3 g((s->nLat + 255) / 256, s->R);
