@@ -55,6 +55,13 @@ def _ref_worker(job):
     return t.N * (nthermal + nsweep), dt, out[8] * T
 
 
+def _quiet_stdout():
+    # the reference's PyInit_* printf("Initializing ...") goes to fd 1 of the worker: bench.py's stdout is ONE JSON line
+    fd = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(fd, 1)
+    os.close(fd)
+
+
 def reference_step(nproc, L, nthermal, nsweep):
     """One bounded sample: nproc independent temperature points, one process each (the reference's
     own parallel axis, win.py:90-91).  Returns (attempts, wall seconds of the engine calls)."""
@@ -63,7 +70,7 @@ def reference_step(nproc, L, nthermal, nsweep):
     jobs = [(L, float(Ts[i]), nthermal, nsweep, i + 1) for i in range(nproc)]
     ctx = mp.get_context("fork")
     t0 = time.time()
-    with ctx.Pool(processes=nproc) as pool:
+    with ctx.Pool(processes=nproc, initializer=_quiet_stdout) as pool:
         res = pool.map(_ref_worker, jobs)
     wall = time.time() - t0
     attempts = sum(r[0] for r in res)
