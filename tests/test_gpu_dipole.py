@@ -84,3 +84,30 @@ def test_dipole_stencil_fp32_jit_path_runs_and_lowers_symmetry():
         sp = s.get_spins(0)
         assert np.allclose(np.linalg.norm(sp, axis=1), 1.0, atol=2e-5)
         assert s.results(0)[0][8] * 1.0 < s.results(1)[0][8] * 2.0      # energy (in K) rises with temperature
+
+
+@pytest.mark.parametrize("L", [(16, 16, 16), (8, 12, 32)])
+def test_dipole_stencil_fp32_fused_energy_equals_recomputed_energy(L):
+    """The fp32 vector pass with 32 full-tensor links accumulates the bond energy from the field of the lower-colour
+    neighbours (snapshot taken between the two halves of the sorted link list).  After one measured sweep that sum
+    must equal the energy of the final configuration recomputed by the measurement-only kernel, and the fp64 engine
+    started from the same configuration must agree on it."""
+    eng = _eng()
+    spec = add_dipole_stencil(spec_of("cubic", L), 0.3, 2.0)
+    N = spec.nsite
+    T = np.array([0.7, 1.4, 3.0])
+    with eng.System.from_spec(spec, 3, precision=32, nReplica=3, beta=1 / T, seed=11) as s:
+        assert s.num_colours() >= 8
+        s.init_spins(0.4)
+        s.metropolis_sweeps(3)
+        s.reset_measurements()
+        s.run(0, 0, 1, N)
+        for r in range(3):
+            E_fused = s.results(r)[0][8] * N
+            E = s.energy(r)
+            assert abs(E_fused - E) <= 3e-6 * abs(E) + 1e-3
+            sp = s.get_spins(r)
+            assert np.abs(np.linalg.norm(sp, axis=1) - 1.0).max() < 2e-5
+            with eng.System.from_spec(spec, 3, precision=64, beta=[1 / T[r]], seed=11) as d:
+                d.set_spins(sp)
+                assert abs(d.energy() - E) <= 3e-6 * abs(E) + 1e-3

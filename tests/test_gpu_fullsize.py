@@ -46,6 +46,38 @@ def test_c5_heisenberg_cubic_256_full_size():
         assert abs(nrm.mean() - 1.0) < 1e-6 and np.abs(nrm - 1.0).max() < 2e-5
 
 
+def test_c5_with_dipole_stencil_256_full_size():
+    """BASELINE config 5 as named: sc 256^3 with the dipole term (cut-off stencil r <= 2, 32 full-tensor links, 16
+    colours).  Polarised state (S,0,0): every site has the same exactly known energy (lattice sum of the stencil); after a
+    measured sweep the fused energy equals the recomputed one and |s| is conserved."""
+    eng = _eng()
+    from mcsolver_b200.lattice import add_dipole_stencil, dipole_tensor
+    alpha = 0.1
+    spec = add_dipole_stencil(LatticeSpec(L=(256, 256, 256), S=[1.0], bonds=[(0, 0, (1, 0, 0), J), (0, 0, (0, 1, 0), J), (0, 0, (0, 0, 1), J)]), alpha, 2.0)
+    N = spec.nsite
+    T = np.array([0.9, 2.0])
+    # energy per site of the polarised (S,0,0) state: sum over bond templates of J_xx (each unordered pair once)
+    e_site = 0.0
+    for b in spec.bonds:
+        J9 = b[3]
+        e_site += float(J9[0])
+    with eng.System.from_spec(spec, 3, precision=32, nReplica=2, beta=1 / T, seed=5) as s:
+        assert s.num_colours() == 16
+        s.init_spins(0.0)
+        for r in range(2):
+            assert abs(s.energy(r) - e_site * N / T[r]) <= 5e-6 * abs(e_site) * N / T[r]
+        s.metropolis_sweeps(2)
+        s.reset_measurements()
+        s.run(0, 0, 1, N)
+        for r in range(2):
+            E = s.energy(r)
+            assert abs(s.results(r)[0][8] * N - E) <= 3e-6 * abs(E) + 1e-3
+        a0, c0, _ = s.counters(0)
+        assert a0 == N and 0 < c0 < a0      # counters restart with the measured run
+        sp = s.get_spins(1)
+        assert np.abs(np.linalg.norm(sp, axis=1) - 1.0).max() < 2e-5
+
+
 def test_c2_ising_square_4096_bit_exact_dyadic_energy_and_determinism():
     eng = _eng()
     spec = LatticeSpec(L=(4096, 4096, 1), S=[1.0], bonds=[(0, 0, (1, 0, 0), J), (0, 0, (0, 1, 0), J)])
