@@ -173,6 +173,10 @@ template <typename real, int CZ = 2> struct RtLink {
     __device__ __forceinline__ int cZ() const { return CZ == 2 ? L.cZ : CZ; }
     __device__ __forceinline__ int low() const { return L.low; }
     __device__ __forceinline__ real J(int e) const { return L.J[e]; }
+    // the neighbour's V cells of NC components; base = first component's row of the neighbour class
+    template <typename R, int V, int NC> __device__ __forceinline__ void fetch(const R *__restrict__ base, size_t N, int Z0, int Zd, R (&t)[3][V]) const {
+        load_shifted_nc<R, V, NC>(base, N, Z0, cZ(), Zd, t);
+    }
 };
 template <typename real> struct RtClass {
     const PassTable<real> &T;
@@ -194,7 +198,7 @@ template <typename real> struct RtClass {
 #pragma unroll 2
         for (; k < kend; k++) f(RtLink<real, CZ>{T.L[j][k], k});
     }
-    template <typename F, typename G> __device__ __forceinline__ void for_links(F &&f, G &&snap) const {
+    template <typename X, typename P, typename F, typename G> __device__ __forceinline__ void for_links(const X &, P &&, F &&f, G &&snap) const {
         int k = 0;
 #pragma unroll 1
         for (int part = 0; part < 2; part++) {
@@ -207,6 +211,94 @@ template <typename real> struct RtClass {
         }
     }
 };
+
+// what a link loop needs to know about the item being updated (the row-dependent part is the `pre` callable)
+template <typename real> struct LinkCtx {
+    const real *sp;   // replica's first component plane
+    size_t N;
+    int Z0, Zd;
+};
+
+#ifndef MCG_JIT
+// ---- asynchronous link pipeline (offline full-tensor fp32 kernel: dipole stencils, 32 links of 9 coefficients) ----
+// The pass is latency-bound (ncu: long-scoreboard stalls 7.6 of 11.7 cycles per issue at 24 warps per SM): registers allow
+// one or two neighbours in flight per thread.  Here every thread keeps ASYNC_D links in flight with cp.async into ITS OWN
+// shared-memory slots - nobody else reads them, so there is no block barrier, only cp.async.wait_group - and the Z shift is
+// applied while copying (four 4-byte copies instead of one 16-byte copy), so the consumer is the same three LDS.128 for
+// every link.
+constexpr int ASYNC_D = 4;
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(unsigned dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(__cvta_generic_to_global(src)) : "memory");
+}
+__device__ __forceinline__ void cp_async4(unsigned dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(__cvta_generic_to_global(src)) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NPEND> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory"); }
+
+struct AsLink {
+    const PLink<float> &L;
+    int k;
+    const float4 *slot;   // this thread's slot of the stage that holds link k: component c at slot[c * 256]
+    __device__ __forceinline__ int idx() const { return k; }
+    __device__ __forceinline__ int delta() const { return L.delta; }
+    __device__ __forceinline__ int mxp() const { return L.mxp; }
+    __device__ __forceinline__ int mxm() const { return L.mxm; }
+    __device__ __forceinline__ int myp() const { return L.myp; }
+    __device__ __forceinline__ int mym() const { return L.mym; }
+    __device__ __forceinline__ int cZ() const { return L.cZ; }
+    __device__ __forceinline__ int low() const { return L.low; }
+    __device__ __forceinline__ float J(int e) const { return L.J[e]; }
+    template <typename R, int V, int NC> __device__ __forceinline__ void fetch(const R *__restrict__, size_t, int, int, R (&t)[3][V]) const {
+        static_assert(V == 4 && sizeof(R) == 4, "async pipeline: fp32 items of four sites");
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            const float4 v = slot[c * 256];
+            t[c][0] = v.x; t[c][1] = v.y; t[c][2] = v.z; t[c][3] = v.w;
+        }
+    }
+};
+struct AsClass : RtClass<float> {
+    float4 *stages;   // [ASYNC_D][3][256 threads]
+    template <typename P, typename F, typename G> __device__ __forceinline__ void for_links(const LinkCtx<float> &x, P &&pre, F &&f, G &&snap) const {
+        const int n = T.gend[j][7], nlo = T.nlow[j];
+        const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+        auto issue = [&](int k) {
+            if (k < n) {
+                const PLink<float> &L = T.L[j][k];
+                const float *base = x.sp + pre(RtLink<float>{L, k});
+                float4 *dst = stages + (size_t)(k & (ASYNC_D - 1)) * 3 * 256 + tid;
+                const int cz = L.cZ;
+                if (cz == 0) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) cp_async16(smem_u32(dst + c * 256), base + (size_t)c * x.N + x.Z0);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        int z = x.Z0 + i + cz;
+                        if (z < 0) z += x.Zd;
+                        if (z >= x.Zd) z -= x.Zd;
+#pragma unroll
+                        for (int c = 0; c < 3; c++) cp_async4(smem_u32(dst + c * 256) + 4 * i, base + (size_t)c * x.N + z);
+                    }
+                }
+            }
+            cp_async_commit();
+        };
+#pragma unroll
+        for (int k = 0; k < ASYNC_D - 1; k++) issue(k);
+        if (nlo == 0) snap();
+#pragma unroll 1
+        for (int k = 0; k < n; k++) {
+            issue(k + ASYNC_D - 1);
+            cp_async_wait<ASYNC_D - 1>();
+            f(AsLink{T.L[j][k], k, stages + (size_t)(k & (ASYNC_D - 1)) * 3 * 256 + tid});
+            if (k == nlo - 1) snap();
+        }
+    }
+};
+#endif
 
 // dims: runtime fields offline, literals under JIT (the generated prologue defines JIT_Xd ...)
 #ifdef MCG_JIT
@@ -280,10 +372,10 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                     const float4 q4 = *reinterpret_cast<const float4 *>(own + (size_t)c * N);
                     s2[c][0] = F2{q4.x, q4.y}; s2[c][1] = F2{q4.z, q4.w};
                 }
-                cls.for_links([&](auto L) {
-                    const int nb = rowBase + L.delta() + L.mxp() * wxp + L.mxm() * wxm + L.myp() * wyp + L.mym() * wym;
+                auto nbOf = [&](auto L) { return rowBase + L.delta() + L.mxp() * wxp + L.mxm() * wxm + L.myp() * wyp + L.mym() * wym; };
+                cls.for_links(LinkCtx<float>{(const float *)sp, (size_t)N, Z0, Zd}, nbOf, [&](auto L) {
                     float t[3][4];
-                    load_shifted_nc<float, 4, NC>((const float *)sp + nb, (size_t)N, Z0, L.cZ(), Zd, t);
+                    L.template fetch<float, 4, NC>((const float *)sp + nbOf(L), (size_t)N, Z0, Zd, t);
                     // aligned row, one diagonal exchange shared by every link of the class (its splat lives in one register
                     // pair): packed multiply-add straight from the float4.  Distinct tensors per link would each need their
                     // constant moved into a pair, where the scalar FFMA takes it as an immediate - measured slower (CrI3).
@@ -429,10 +521,10 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
             const real *own = sp + rowBase + Z0;
 #pragma unroll
             for (int c = 0; c < NC; c++) vload<real, V>(own + (size_t)c * N, s[c]);
-            cls.for_links([&](auto L) {
-                const int nb = rowBase + L.delta() + L.mxp() * wxp + L.mxm() * wxm + L.myp() * wyp + L.mym() * wym;
+            auto nbOf = [&](auto L) { return rowBase + L.delta() + L.mxp() * wxp + L.mxm() * wxm + L.myp() * wyp + L.mym() * wym; };
+            cls.for_links(LinkCtx<real>{sp, (size_t)N, Z0, Zd}, nbOf, [&](auto L) {
                 real t[3][V];
-                load_shifted_nc<real, V, NC>(sp + nb, (size_t)N, Z0, L.cZ(), Zd, t);
+                L.template fetch<real, V, NC>(sp + nbOf(L), (size_t)N, Z0, Zd, t);
 #pragma unroll
                 for (int v = 0; v < V; v++) {
                     const real tx = t[0][v], ty = NC >= 2 ? t[1][v] : real(0), tz = NC == 3 ? t[2][v] : real(0);
@@ -587,6 +679,20 @@ k_struct_fast(const __grid_constant__ StructArgs a, const __grid_constant__ Pass
     const int j = bid % nqc, tq = bid / nqc, rb = tq % nrb, r = tq / nrb;
     pass_body<NC, real, FULLJ, MODE, V, PARTIAL>(a, RtClass<real>{T, j}, q0 + j, r, rb, rowsPerBlock, sweep, pAtt, red, hls);
 }
+// full-tensor fp32 pass with the asynchronous link pipeline (AsClass); dynamic shared memory = ASYNC_D stages
+template <int MODE, bool PARTIAL>
+__global__ void __launch_bounds__(256, 3)
+k_struct_async(const __grid_constant__ StructArgs a, const __grid_constant__ PassTable<float> T, int q0, int rowsPerBlock, int nrb,
+               uint64_t sweep, float pAtt) {
+    __shared__ double red[4 * 32];
+    __shared__ float4 hls[MODE == 1 ? 3 * 256 : 1];
+    extern __shared__ float4 async_stages[];
+    const int nqc = T.nqc;
+    const int bid = blockIdx.x;
+    const int j = bid % nqc, tq = bid / nqc, rb = tq % nrb, r = tq / nrb;
+    AsClass cls{{T, j}, async_stages};
+    pass_body<3, float, true, MODE, 4, PARTIAL>(a, cls, q0 + j, r, rb, rowsPerBlock, sweep, pAtt, red, hls);
+}
 #else
 // ---- JIT entry points: JIT_NC, jit_real, JIT_FULLJ, JIT_V, JIT_NQC, JIT_PARTIAL, JIT_MINB, CtLinkData<J,K>, CtClassData<J>
 // come from the generated prologue ----
@@ -601,6 +707,9 @@ template <int JJ, int K> struct CtLink {
     __device__ __forceinline__ constexpr int low() const { return D::low; }
     __device__ __forceinline__ constexpr int idx() const { return K; }
     __device__ __forceinline__ constexpr jit_real J(int e) const { return D::J(e); }
+    template <typename R, int V, int NC> __device__ __forceinline__ void fetch(const R *__restrict__ base, size_t N, int Z0, int Zd, R (&t)[3][V]) const {
+        load_shifted_nc<R, V, NC>(base, N, Z0, D::cZ, Zd, t);
+    }
 };
 template <int JJ> struct CtClass {
     typedef CtClassData<JJ> C;
@@ -620,7 +729,7 @@ template <int JJ> struct CtClass {
                    CtLinkData<JJ, K>::J(2) == CtLinkData<JJ, 0>::J(2) && uj_from<K + 1>();
     }
     __device__ __forceinline__ constexpr bool uniformJ() const { return uj_from<0>(); }
-    template <typename F, typename G> __device__ __forceinline__ void for_links(F &&f, G &&snap) const {
+    template <typename X, typename P, typename F, typename G> __device__ __forceinline__ void for_links(const X &, P &&, F &&f, G &&snap) const {
         if constexpr (C::nlow == 0) snap();
         ct_for<0, C::nl>([&](auto k) {
             f(CtLink<JJ, decltype(k)::value>{});

@@ -1574,6 +1574,25 @@ template <int MODE> static void launch_pass(mcg_system *s, int colour, uint64_t 
     if (G) {
         bool launched = false;
         if constexpr (MODE != 2) launched = jit_launch_pass(s, colour, MODE, a, q0, rowsPerBlock, nrb, sweep, pAtt, grid, block);
+        // full 3x3 tensors on fp32 Heisenberg items that the specialiser did not take (dipole stencils): asynchronous link pipeline
+        if constexpr (MODE != 2) {
+            static const bool noAsync = getenv("MCG_NO_ASYNC") != nullptr;
+            if (!launched && !noAsync && s->NC == 3 && s->prec == 32 && s->fullJ && st->V == 4 && block.x * block.y == 256) {
+                constexpr size_t dyn = (size_t)ASYNC_D * 3 * 256 * sizeof(float4);
+                static bool attrSet[2][2] = {{false, false}, {false, false}};
+                const PassTable<float> &P = *reinterpret_cast<const PassTable<float> *>(st->passTables[colour].data());
+                auto go = [&]<bool PARTIAL>() {
+                    auto kern = k_struct_async<MODE, PARTIAL>;
+                    if (!attrSet[MODE][PARTIAL]) {
+                        MCG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+                        attrSet[MODE][PARTIAL] = true;
+                    }
+                    kern<<<grid, block, dyn, s->stream>>>(a, P, q0, rowsPerBlock, nrb, sweep, (float)pAtt);
+                };
+                if (pAtt < 1.0) go.template operator()<true>(); else go.template operator()<false>();
+                launched = true;
+            }
+        }
         if (!launched)
             sdispatch(s, [&]<int NC, typename real, bool FJ>() {
                 if constexpr (MODE != 2) {
