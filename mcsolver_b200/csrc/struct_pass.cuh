@@ -193,6 +193,12 @@ template <typename real> struct RtClass {
     __device__ __forceinline__ bool uniformJ() const { return T.uniformJ != 0; }
     // f on every link; snap once after the leading nlow links (the lower-colour neighbours).  Two loops instead of a
     // test inside one: the snapshot is a dozen register moves that were predicated into every iteration
+    // the item's own spins: read up front (the asynchronous pipeline fetches them behind the last link instead)
+    template <typename R, int V, int NC> __device__ __forceinline__ void own_early(const R *__restrict__ own, size_t N, R (&sv)[3][V]) const {
+#pragma unroll
+        for (int c = 0; c < NC; c++) vload<R, V>(own + (size_t)c * N, sv[c]);
+    }
+    template <typename R, int V, int NC> __device__ __forceinline__ void own_late(R (&)[3][V]) const {}
     template <int CZ, typename F> __device__ __forceinline__ void run(int &k, int kend, F &&f) const {
         // two links per trip: the second link's loads are issued before the first one's multiply-adds retire
 #pragma unroll 2
@@ -211,6 +217,9 @@ template <typename real> struct RtClass {
         }
     }
 };
+
+// links whose coefficients arrive as splat pairs: the field sums of a full tensor run as packed FFMA2
+template <typename LK> struct LinkPacked { static constexpr bool value = false; };
 
 // what a link loop needs to know about the item being updated (the row-dependent part is the `pre` callable)
 template <typename real> struct LinkCtx {
@@ -234,53 +243,110 @@ __device__ __forceinline__ void cp_async16(unsigned dst, const void *src) {
 __device__ __forceinline__ void cp_async4(unsigned dst, const void *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(__cvta_generic_to_global(src)) : "memory");
 }
+__device__ __forceinline__ void cp_async16q(unsigned dst, unsigned long long src) {   // src: a global address
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+// keeps a loop invariant in its register: without it the compiler re-derives thread ids, the shared window base and the
+// replica's 64-bit plane offset for every link (ptxas prefers rematerialising to holding them under the 80-register cap)
+__device__ __forceinline__ void pin(unsigned &v) { asm volatile("" : "+r"(v)); }
+__device__ __forceinline__ void pin(unsigned long long &v) { asm volatile("" : "+l"(v)); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int NPEND> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory"); }
 
+// the class's link table as the pipeline reads it from shared memory: four 16-byte loads per link instead of 15 scalar ones
+struct AsTab {
+    float4 j[5];   // the nine coefficients as splat pairs (J0,J0,J1,J1)(J2,J2,J3,J3)...(J8,J8,0,0): operands of FFMA2 as loaded
+    int4 a;        // delta, cX sign, cY sign, cZ
+};
+struct AsAddr {    // just enough of a link for nb_of
+    int4 a;
+    __device__ __forceinline__ int delta() const { return a.x; }
+    __device__ __forceinline__ int mxp() const { return a.y > 0; }
+    __device__ __forceinline__ int mxm() const { return a.y < 0; }
+    __device__ __forceinline__ int myp() const { return a.z > 0; }
+    __device__ __forceinline__ int mym() const { return a.z < 0; }
+};
 struct AsLink {
-    const PLink<float> &L;
+    float4 j0, j1, j2, j3, j4;
     int k;
-    const float4 *slot;   // this thread's slot of the stage that holds link k: component c at slot[c * 256]
+    unsigned slot;        // shared-memory address of this thread's slot in the stage that holds link k; components ASYNC_D * 4096 B apart
     __device__ __forceinline__ int idx() const { return k; }
-    __device__ __forceinline__ int delta() const { return L.delta; }
-    __device__ __forceinline__ int mxp() const { return L.mxp; }
-    __device__ __forceinline__ int mxm() const { return L.mxm; }
-    __device__ __forceinline__ int myp() const { return L.myp; }
-    __device__ __forceinline__ int mym() const { return L.mym; }
-    __device__ __forceinline__ int cZ() const { return L.cZ; }
-    __device__ __forceinline__ int low() const { return L.low; }
-    __device__ __forceinline__ float J(int e) const { return L.J[e]; }
+    // the consumer never needs the neighbour's position (fetch reads the stage): nb_of on this type folds to a dead value
+    __device__ __forceinline__ int delta() const { return 0; }
+    __device__ __forceinline__ int mxp() const { return 0; }
+    __device__ __forceinline__ int mxm() const { return 0; }
+    __device__ __forceinline__ int myp() const { return 0; }
+    __device__ __forceinline__ int mym() const { return 0; }
+    __device__ __forceinline__ float J(int e) const {
+        return e == 0 ? j0.x : e == 1 ? j0.z : e == 2 ? j1.x : e == 3 ? j1.z : e == 4 ? j2.x : e == 5 ? j2.z : e == 6 ? j3.x : e == 7 ? j3.z : j4.x;
+    }
+    __device__ __forceinline__ F2 J2(int e) const {
+        return e == 0 ? F2{j0.x, j0.y} : e == 1 ? F2{j0.z, j0.w} : e == 2 ? F2{j1.x, j1.y} : e == 3 ? F2{j1.z, j1.w} : e == 4 ? F2{j2.x, j2.y}
+             : e == 5 ? F2{j2.z, j2.w} : e == 6 ? F2{j3.x, j3.y} : e == 7 ? F2{j3.z, j3.w} : F2{j4.x, j4.y};
+    }
     template <typename R, int V, int NC> __device__ __forceinline__ void fetch(const R *__restrict__, size_t, int, int, R (&t)[3][V]) const {
         static_assert(V == 4 && sizeof(R) == 4, "async pipeline: fp32 items of four sites");
 #pragma unroll
         for (int c = 0; c < NC; c++) {
-            const float4 v = slot[c * 256];
+            const float4 v = lds128(slot + c * (ASYNC_D * 4096));
             t[c][0] = v.x; t[c][1] = v.y; t[c][2] = v.z; t[c][3] = v.w;
         }
     }
 };
+template <> struct LinkPacked<AsLink> { static constexpr bool value = true; };
 struct AsClass : RtClass<float> {
-    float4 *stages;   // [ASYNC_D][3][256 threads]
+    float4 *stages;      // [3 components][ASYNC_D][256 threads]
+    const AsTab *tab;    // [nlinks + 1] in shared memory; the last entry is the item itself (offset 0, no shift)
+    static constexpr unsigned STAGE_B = 256 * 16, COMP_B = ASYNC_D * STAGE_B;
+    // called by every thread of the block before the pass: src = this class's records in global memory (built on the host)
+    __device__ __forceinline__ void stage_table(AsTab *dst, const AsTab *__restrict__ src) const {
+        const int n16 = (T.gend[j][7] + 1) * (int)(sizeof(AsTab) / 16);
+        for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < n16; i += blockDim.x * blockDim.y)
+            reinterpret_cast<float4 *>(dst)[i] = reinterpret_cast<const float4 *>(src)[i];
+        __syncthreads();
+    }
+    __device__ __forceinline__ unsigned slot0() const { return smem_u32(stages) + (threadIdx.y * blockDim.x + threadIdx.x) * 16; }
+    template <typename R, int V, int NC> __device__ __forceinline__ void own_early(const R *__restrict__, size_t, R (&)[3][V]) const {}
+    template <typename R, int V, int NC> __device__ __forceinline__ void own_late(R (&sv)[3][V]) const {
+        cp_async_wait<0>();
+        const int n = T.gend[j][7];
+        const unsigned p = slot0() + (unsigned)(n & (ASYNC_D - 1)) * STAGE_B;
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            const float4 v = lds128(p + c * COMP_B);
+            sv[c][0] = v.x; sv[c][1] = v.y; sv[c][2] = v.z; sv[c][3] = v.w;
+        }
+    }
     template <typename P, typename F, typename G> __device__ __forceinline__ void for_links(const LinkCtx<float> &x, P &&pre, F &&f, G &&snap) const {
         const int n = T.gend[j][7], nlo = T.nlow[j];
-        const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+        unsigned st0 = slot0();
+        unsigned long long ib = (unsigned long long)__cvta_generic_to_global(x.sp + x.Z0);
+        pin(st0);
+        pin(ib);
+        const unsigned long long planeB = (unsigned long long)x.N * 4;
         auto issue = [&](int k) {
-            if (k < n) {
-                const PLink<float> &L = T.L[j][k];
-                const float *base = x.sp + pre(RtLink<float>{L, k});
-                float4 *dst = stages + (size_t)(k & (ASYNC_D - 1)) * 3 * 256 + tid;
-                const int cz = L.cZ;
+            if (k <= n) {
+                const int4 a = tab[k].a;
+                const unsigned long long base = ib + (long long)pre(AsAddr{a}) * 4;
+                const unsigned dst = st0 + (unsigned)(k & (ASYNC_D - 1)) * STAGE_B;
+                const int cz = a.w;
                 if (cz == 0) {
-#pragma unroll
-                    for (int c = 0; c < 3; c++) cp_async16(smem_u32(dst + c * 256), base + (size_t)c * x.N + x.Z0);
+                    cp_async16q(dst, base);
+                    cp_async16q(dst + COMP_B, base + planeB);
+                    cp_async16q(dst + 2 * COMP_B, base + 2 * planeB);
                 } else {
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
-                        int z = x.Z0 + i + cz;
-                        if (z < 0) z += x.Zd;
-                        if (z >= x.Zd) z -= x.Zd;
+                        int dz = i + cz;
+                        if (x.Z0 + dz < 0) dz += x.Zd;
+                        if (x.Z0 + dz >= x.Zd) dz -= x.Zd;
 #pragma unroll
-                        for (int c = 0; c < 3; c++) cp_async4(smem_u32(dst + c * 256) + 4 * i, base + (size_t)c * x.N + z);
+                        for (int c = 0; c < 3; c++) cp_async4(dst + c * COMP_B + 4 * i, reinterpret_cast<const float *>(base + c * planeB) + dz);
                     }
                 }
             }
@@ -293,7 +359,7 @@ struct AsClass : RtClass<float> {
         for (int k = 0; k < n; k++) {
             issue(k + ASYNC_D - 1);
             cp_async_wait<ASYNC_D - 1>();
-            f(AsLink{T.L[j][k], k, stages + (size_t)(k & (ASYNC_D - 1)) * 3 * 256 + tid});
+            f(AsLink{tab[k].j[0], tab[k].j[1], tab[k].j[2], tab[k].j[3], tab[k].j[4], k, st0 + (unsigned)(k & (ASYNC_D - 1)) * STAGE_B});
             if (k == nlo - 1) snap();
         }
     }
@@ -313,6 +379,19 @@ template <int I, int N, typename F> __device__ __forceinline__ void ct_for(F &&f
         f(IC<I>{});
         ct_for<I + 1, N>(f);
     }
+}
+
+// position of the neighbour's row.  Runtime tables: the four wrap corrections vanish on all but the boundary rows, so
+// they sit behind a test (4 multiply-adds and 4 table loads per link otherwise); literals (JIT) fold either way.
+template <typename LK>
+__device__ __forceinline__ int nb_of(const LK &L, int rowBase, bool edgeRow, int wxp, int wxm, int wyp, int wym) {
+#ifdef MCG_JIT
+    return rowBase + L.delta() + L.mxp() * wxp + L.mxm() * wxm + L.myp() * wyp + L.mym() * wym;
+#else
+    int nb = rowBase + L.delta();
+    if (edgeRow) nb += L.mxp() * wxp + L.mxm() * wxm + L.myp() * wyp + L.mym() * wym;
+    return nb;
+#endif
 }
 
 // One colour pass over the rows [rb*rowsPerBlock, ...) of class q = q0 + j for replica r.
@@ -352,6 +431,7 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
         const int rowBase = ((q * Xd + X) * Yd + Y) * Zd;
         const int wxp = X == Xd - 1 ? -planeX : 0, wxm = X == 0 ? planeX : 0;
         const int wyp = Y == Yd - 1 ? -planeY : 0, wym = Y == 0 ? planeY : 0;
+        const bool edgeRow = (wxp | wxm | wyp | wym) != 0;
         const int xy = ((X * px + cls.ca()) * Ly + (Y * py + cls.cb())) * Lz;
         for (int zc = threadIdx.x; zc < Zc; zc += blockDim.x) {
             const int Z0 = zc * V;
@@ -372,7 +452,7 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                     const float4 q4 = *reinterpret_cast<const float4 *>(own + (size_t)c * N);
                     s2[c][0] = F2{q4.x, q4.y}; s2[c][1] = F2{q4.z, q4.w};
                 }
-                auto nbOf = [&](auto L) { return rowBase + L.delta() + L.mxp() * wxp + L.mxm() * wxm + L.myp() * wyp + L.mym() * wym; };
+                auto nbOf = [&](auto L) { return nb_of(L, rowBase, edgeRow, wxp, wxm, wyp, wym); };
                 cls.for_links(LinkCtx<float>{(const float *)sp, (size_t)N, Z0, Zd}, nbOf, [&](auto L) {
                     float t[3][4];
                     L.template fetch<float, 4, NC>((const float *)sp + nbOf(L), (size_t)N, Z0, Zd, t);
@@ -519,12 +599,26 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
 #pragma unroll
                 for (int v = 0; v < V; v++) { s[c][v] = 0; H[c][v] = 0; Hl[c][v] = 0; }
             const real *own = sp + rowBase + Z0;
-#pragma unroll
-            for (int c = 0; c < NC; c++) vload<real, V>(own + (size_t)c * N, s[c]);
-            auto nbOf = [&](auto L) { return rowBase + L.delta() + L.mxp() * wxp + L.mxm() * wxm + L.myp() * wyp + L.mym() * wym; };
+            cls.template own_early<real, V, NC>(own, (size_t)N, s);
+            auto nbOf = [&](auto L) { return nb_of(L, rowBase, edgeRow, wxp, wxm, wyp, wym); };
             cls.for_links(LinkCtx<real>{sp, (size_t)N, Z0, Zd}, nbOf, [&](auto L) {
                 real t[3][V];
                 L.template fetch<real, V, NC>(sp + nbOf(L), (size_t)N, Z0, Zd, t);
+                if constexpr (LinkPacked<decltype(L)>::value) {
+                    // same multiply-add chain as the scalar full-tensor branch below, two sites per instruction: the LDS.128
+                    // quads are aligned pairs already and the coefficients come from shared memory as (J, J)
+#pragma unroll
+                    for (int p = 0; p < 2; p++) {
+                        const F2 tx{(float)t[0][2 * p], (float)t[0][2 * p + 1]}, ty{(float)t[1][2 * p], (float)t[1][2 * p + 1]}, tz{(float)t[2][2 * p], (float)t[2][2 * p + 1]};
+                        F2 h0{(float)H[0][2 * p], (float)H[0][2 * p + 1]}, h1{(float)H[1][2 * p], (float)H[1][2 * p + 1]}, h2{(float)H[2][2 * p], (float)H[2][2 * p + 1]};
+                        h0 = fma2(L.J2(0), tx, fma2(L.J2(3), ty, fma2(L.J2(4), tz, h0)));
+                        h1 = fma2(L.J2(6), tx, fma2(L.J2(1), ty, fma2(L.J2(5), tz, h1)));
+                        h2 = fma2(L.J2(7), tx, fma2(L.J2(8), ty, fma2(L.J2(2), tz, h2)));
+                        H[0][2 * p] = h0.x; H[0][2 * p + 1] = h0.y;
+                        H[1][2 * p] = h1.x; H[1][2 * p + 1] = h1.y;
+                        H[2][2 * p] = h2.x; H[2][2 * p + 1] = h2.y;
+                    }
+                } else {
 #pragma unroll
                 for (int v = 0; v < V; v++) {
                     const real tx = t[0][v], ty = NC >= 2 ? t[1][v] : real(0), tz = NC == 3 ? t[2][v] : real(0);
@@ -553,6 +647,7 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                         }
                     } else { H[0][v] += hx; H[1][v] += hy; H[2][v] += hz; }
                 }
+                }
             }, [&]() {
                 // lower-colour neighbours come first in the link list: snapshot their field for the fused bond energy
                 if (MODE == 1 && lowmode == 2) {
@@ -567,6 +662,7 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                     }
                 }
             });
+            cls.template own_late<real, V, NC>(s);
             if constexpr (PARK) {
                 if (lowmode == 2) {
 #pragma unroll
@@ -682,15 +778,17 @@ k_struct_fast(const __grid_constant__ StructArgs a, const __grid_constant__ Pass
 // full-tensor fp32 pass with the asynchronous link pipeline (AsClass); dynamic shared memory = ASYNC_D stages
 template <int MODE, bool PARTIAL>
 __global__ void __launch_bounds__(256, 3)
-k_struct_async(const __grid_constant__ StructArgs a, const __grid_constant__ PassTable<float> T, int q0, int rowsPerBlock, int nrb,
-               uint64_t sweep, float pAtt) {
+k_struct_async(const __grid_constant__ StructArgs a, const __grid_constant__ PassTable<float> T, const AsTab *__restrict__ gtab, int q0,
+               int rowsPerBlock, int nrb, uint64_t sweep, float pAtt) {
     __shared__ double red[4 * 32];
     __shared__ float4 hls[MODE == 1 ? 3 * 256 : 1];
     extern __shared__ float4 async_stages[];
     const int nqc = T.nqc;
     const int bid = blockIdx.x;
     const int j = bid % nqc, tq = bid / nqc, rb = tq % nrb, r = tq / nrb;
-    AsClass cls{{T, j}, async_stages};
+    __shared__ AsTab tab[PT_MAXL + 1];
+    AsClass cls{{T, j}, async_stages, tab};
+    cls.stage_table(tab, gtab + (size_t)(q0 + j) * (PT_MAXL + 1));
     pass_body<3, float, true, MODE, 4, PARTIAL>(a, cls, q0 + j, r, rb, rowsPerBlock, sweep, pAtt, red, hls);
 }
 #else
@@ -722,6 +820,12 @@ template <int JJ> struct CtClass {
     __device__ __forceinline__ constexpr int nlow() const { return C::nlow; }
     __device__ __forceinline__ constexpr jit_real S() const { return C::S; }
     __device__ __forceinline__ constexpr jit_real D(int e) const { return C::D(e); }
+    // the item's own spins: read up front (the asynchronous pipeline fetches them behind the last link instead)
+    template <typename R, int V, int NC> __device__ __forceinline__ void own_early(const R *__restrict__ own, size_t N, R (&sv)[3][V]) const {
+#pragma unroll
+        for (int c = 0; c < NC; c++) vload<R, V>(own + (size_t)c * N, sv[c]);
+    }
+    template <typename R, int V, int NC> __device__ __forceinline__ void own_late(R (&)[3][V]) const {}
     template <int K> static __device__ __forceinline__ constexpr bool uj_from() {
         if constexpr (K >= C::nl) return true;
         else

@@ -59,6 +59,7 @@ struct StructuredSystem {
     SLinkD *d_links = nullptr;
     void *d_J = nullptr;
     int *d_classOf = nullptr, *d_circuits = nullptr, *d_tverts = nullptr, *d_ttris = nullptr, *d_gmask = nullptr;
+    AsTab *d_asTab = nullptr;                     // [nclass][PT_MAXL + 1] link tables of the asynchronous pipeline (fp32 full-tensor passes)
     std::vector<int> gmaskHost;
     bool groupInSC = true;
     int nvert = 0;
@@ -1441,6 +1442,26 @@ void structured_create(mcg_system *s, const mcg_lattice_desc *d) {
         st->d_rsums = (double *)pool_alloc((size_t)s->R * NRS * sizeof(double));
         MCG_CUDA(cudaMemset(st->d_rsums, 0, (size_t)s->R * NRS * sizeof(double)));
     }
+    if (s->prec == 32 && s->NC == 3 && s->fullJ) {
+        // the asynchronous pipeline's view of the pass tables: per class the links in pass order (16-byte records the kernel
+        // copies into shared memory), then one record for the item itself
+        std::vector<AsTab> at((size_t)st->nclass * (PT_MAXL + 1));
+        memset(at.data(), 0, at.size() * sizeof(AsTab));
+        for (size_t c = 0; c < st->passTables.size(); c++) {
+            if (st->passTables[c].empty()) continue;
+            const PassTable<float> &P = *reinterpret_cast<const PassTable<float> *>(st->passTables[c].data());
+            const int q0 = st->colourClassStart[c];
+            for (int j = 0; j < P.nqc; j++)
+                for (int k = 0; k < P.gend[j][7]; k++) {
+                    const PLink<float> &L = P.L[j][k];
+                    AsTab &t = at[(size_t)(q0 + j) * (PT_MAXL + 1) + k];
+                    for (int e = 0; e < 4; e++) t.j[e] = make_float4(L.J[2 * e], L.J[2 * e], L.J[2 * e + 1], L.J[2 * e + 1]);
+                    t.j[4] = make_float4(L.J[8], L.J[8], 0.f, 0.f);
+                    t.a = make_int4(L.delta, L.mxp - L.mxm, L.myp - L.mym, L.cZ);
+                }
+        }
+        st->d_asTab = (AsTab *)up(at.data(), at.size() * sizeof(AsTab));
+    }
     size_t cs = (size_t)s->R * st->nclass * 4 * sizeof(double);
     st->d_classSums = (double *)pool_alloc(cs);
     MCG_CUDA(cudaMemset(st->d_classSums, 0, cs));
@@ -1480,7 +1501,7 @@ int structured_jit_check(const mcg_lattice_desc *d, int precision, std::string &
 
 void structured_destroy(StructuredSystem *st) {
     if (!st) return;
-    void *bufs[] = {st->d_classes, st->d_links, st->d_J, st->d_classOf, st->d_circuits, st->d_classSums, st->d_stage, st->d_tverts, st->d_ttris, st->d_gmask, st->d_rgEnt, st->d_rgNent, st->d_rgPerm, st->d_rgJ, st->d_rgSD, st->d_ms, st->d_rsums};
+    void *bufs[] = {st->d_classes, st->d_links, st->d_J, st->d_classOf, st->d_circuits, st->d_classSums, st->d_stage, st->d_tverts, st->d_ttris, st->d_gmask, st->d_rgEnt, st->d_rgNent, st->d_rgPerm, st->d_rgJ, st->d_rgSD, st->d_ms, st->d_rsums, st->d_asTab};
     for (void *b : bufs) pool_free(b);
     delete st;
 }
@@ -1577,7 +1598,7 @@ template <int MODE> static void launch_pass(mcg_system *s, int colour, uint64_t 
         // full 3x3 tensors on fp32 Heisenberg items that the specialiser did not take (dipole stencils): asynchronous link pipeline
         if constexpr (MODE != 2) {
             static const bool noAsync = getenv("MCG_NO_ASYNC") != nullptr;
-            if (!launched && !noAsync && s->NC == 3 && s->prec == 32 && s->fullJ && st->V == 4 && block.x * block.y == 256) {
+            if (!launched && !noAsync && st->d_asTab && st->V == 4 && block.x * block.y == 256) {
                 constexpr size_t dyn = (size_t)ASYNC_D * 3 * 256 * sizeof(float4);
                 static bool attrSet[2][2] = {{false, false}, {false, false}};
                 const PassTable<float> &P = *reinterpret_cast<const PassTable<float> *>(st->passTables[colour].data());
@@ -1587,7 +1608,7 @@ template <int MODE> static void launch_pass(mcg_system *s, int colour, uint64_t 
                         MCG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
                         attrSet[MODE][PARTIAL] = true;
                     }
-                    kern<<<grid, block, dyn, s->stream>>>(a, P, q0, rowsPerBlock, nrb, sweep, (float)pAtt);
+                    kern<<<grid, block, dyn, s->stream>>>(a, P, st->d_asTab, q0, rowsPerBlock, nrb, sweep, (float)pAtt);
                 };
                 if (pAtt < 1.0) go.template operator()<true>(); else go.template operator()<false>();
                 launched = true;

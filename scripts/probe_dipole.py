@@ -10,6 +10,7 @@ R = 8
 cases = [("0", "4"), ("1", "4"), ("1", "2"), ("1", "1")] if os.environ.get("DIP_ALL") else [("0", "4")]
 LL = int(os.environ.get("DIP_L", "128"))
 MEAS = bool(int(os.environ.get("DIP_MEAS", "1")))
+NSW = int(os.environ.get("DIP_SWEEPS", "8"))
 spec = add_dipole_stencil(cu(LL), 0.1, 2.0)
 for jit, minb in cases:
     os.environ["MCG_JIT"] = jit
@@ -17,5 +18,5 @@ for jit, minb in cases:
     with engine.System.from_spec(spec, 3, precision=32, nReplica=R, beta=1 / np.linspace(1.2, 1.9, R), seed=1) as s:
         s.init_spins(0.0)
         s.timed_sweeps(2, with_measure=MEAS)
-        ms = s.timed_sweeps(8, with_measure=MEAS) / 2
-        print("dipole r<=2 %d^3 meas=%d jit" % (LL, MEAS) + "=%s minb=%s colours=%d: %.3f ms/sweep %.3e attempts/s" % (jit, minb, s.num_colours(), ms / 4, R * spec.nsite * 4 / ms * 1e3), flush=True)
+        ms = s.timed_sweeps(NSW, with_measure=MEAS) * 4 / NSW
+        print("dipole r<=2 %d^3 meas=%d jit" % (LL, MEAS) + " sweeps=%d" % NSW + "=%s minb=%s colours=%d: %.3f ms/sweep %.3e attempts/s" % (jit, minb, s.num_colours(), ms / 4, R * spec.nsite * 4 / ms * 1e3), flush=True)
