@@ -102,17 +102,19 @@ __device__ __forceinline__ void load_shifted(const real *__restrict__ row, int Z
 // the NC component rows of one neighbour at once: ONE decision on the shift for all components (with a runtime link
 // table the per-component version re-branched three times and kept three copies of the address arithmetic alive)
 template <typename real, int V, int NC>
-__device__ __forceinline__ void load_shifted_nc(const real *__restrict__ base, size_t N, int Z0, int cZ, int Zd, real (&o)[3][V]) {
+__device__ __forceinline__ void load_shifted_nc(const real *__restrict__ sp, size_t N, int nb, int Z0, int cZ, int Zd, real (&o)[3][V]) {
+    // rows are addressed as (sp + c*N) + nb: the component planes are loop invariants, the link adds a 32-bit offset
     if (cZ == 0) {
 #pragma unroll
-        for (int c = 0; c < NC; c++) vload<real, V>(base + (size_t)c * N + Z0, o[c]);
+        for (int c = 0; c < NC; c++) vload<real, V>(sp + (size_t)c * N + nb + Z0, o[c]);
     } else if (V > 1 && cZ == -1) {
         const int zl = Z0 == 0 ? Zd - 1 : Z0 - 1;
 #pragma unroll
         for (int c = 0; c < NC; c++) {
+            const real *row = sp + (size_t)c * N + nb;
             real t[V];
-            vload<real, V>(base + (size_t)c * N + Z0, t);
-            o[c][0] = base[(size_t)c * N + zl];
+            vload<real, V>(row + Z0, t);
+            o[c][0] = row[zl];
 #pragma unroll
             for (int i = 1; i < V; i++) o[c][i] = t[i - 1];
         }
@@ -120,11 +122,12 @@ __device__ __forceinline__ void load_shifted_nc(const real *__restrict__ base, s
         const int zr = Z0 + V >= Zd ? 0 : Z0 + V;
 #pragma unroll
         for (int c = 0; c < NC; c++) {
+            const real *row = sp + (size_t)c * N + nb;
             real t[V];
-            vload<real, V>(base + (size_t)c * N + Z0, t);
+            vload<real, V>(row + Z0, t);
 #pragma unroll
             for (int i = 0; i < V - 1; i++) o[c][i] = t[i + 1];
-            o[c][V - 1] = base[(size_t)c * N + zr];
+            o[c][V - 1] = row[zr];
         }
     } else {
         int z[V];
@@ -135,9 +138,11 @@ __device__ __forceinline__ void load_shifted_nc(const real *__restrict__ base, s
             if (z[i] >= Zd) z[i] -= Zd;
         }
 #pragma unroll
-        for (int c = 0; c < NC; c++)
+        for (int c = 0; c < NC; c++) {
+            const real *row = sp + (size_t)c * N + nb;
 #pragma unroll
-            for (int i = 0; i < V; i++) o[c][i] = base[(size_t)c * N + z[i]];
+            for (int i = 0; i < V; i++) o[c][i] = row[z[i]];
+        }
     }
 }
 
@@ -174,8 +179,8 @@ template <typename real, int CZ = 2> struct RtLink {
     __device__ __forceinline__ int low() const { return L.low; }
     __device__ __forceinline__ real J(int e) const { return L.J[e]; }
     // the neighbour's V cells of NC components; base = first component's row of the neighbour class
-    template <typename R, int V, int NC> __device__ __forceinline__ void fetch(const R *__restrict__ base, size_t N, int Z0, int Zd, R (&t)[3][V]) const {
-        load_shifted_nc<R, V, NC>(base, N, Z0, cZ(), Zd, t);
+    template <typename R, int V, int NC> __device__ __forceinline__ void fetch(const R *__restrict__ sp, int nb, size_t N, int Z0, int Zd, R (&t)[3][V]) const {
+        load_shifted_nc<R, V, NC>(sp, N, nb, Z0, cZ(), Zd, t);
     }
 };
 template <typename real> struct RtClass {
@@ -289,7 +294,7 @@ struct AsLink {
         return e == 0 ? F2{j0.x, j0.y} : e == 1 ? F2{j0.z, j0.w} : e == 2 ? F2{j1.x, j1.y} : e == 3 ? F2{j1.z, j1.w} : e == 4 ? F2{j2.x, j2.y}
              : e == 5 ? F2{j2.z, j2.w} : e == 6 ? F2{j3.x, j3.y} : e == 7 ? F2{j3.z, j3.w} : F2{j4.x, j4.y};
     }
-    template <typename R, int V, int NC> __device__ __forceinline__ void fetch(const R *__restrict__, size_t, int, int, R (&t)[3][V]) const {
+    template <typename R, int V, int NC> __device__ __forceinline__ void fetch(const R *__restrict__, int, size_t, int, int, R (&t)[3][V]) const {
         static_assert(V == 4 && sizeof(R) == 4, "async pipeline: fp32 items of four sites");
 #pragma unroll
         for (int c = 0; c < NC; c++) {
@@ -455,7 +460,7 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                 auto nbOf = [&](auto L) { return nb_of(L, rowBase, edgeRow, wxp, wxm, wyp, wym); };
                 cls.for_links(LinkCtx<float>{(const float *)sp, (size_t)N, Z0, Zd}, nbOf, [&](auto L) {
                     float t[3][4];
-                    L.template fetch<float, 4, NC>((const float *)sp + nbOf(L), (size_t)N, Z0, Zd, t);
+                    L.template fetch<float, 4, NC>((const float *)sp, nbOf(L), (size_t)N, Z0, Zd, t);
                     // aligned row, one diagonal exchange shared by every link of the class (its splat lives in one register
                     // pair): packed multiply-add straight from the float4.  Distinct tensors per link would each need their
                     // constant moved into a pair, where the scalar FFMA takes it as an immediate - measured slower (CrI3).
@@ -603,7 +608,7 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
             auto nbOf = [&](auto L) { return nb_of(L, rowBase, edgeRow, wxp, wxm, wyp, wym); };
             cls.for_links(LinkCtx<real>{sp, (size_t)N, Z0, Zd}, nbOf, [&](auto L) {
                 real t[3][V];
-                L.template fetch<real, V, NC>(sp + nbOf(L), (size_t)N, Z0, Zd, t);
+                L.template fetch<real, V, NC>(sp, nbOf(L), (size_t)N, Z0, Zd, t);
                 if constexpr (LinkPacked<decltype(L)>::value) {
                     // same multiply-add chain as the scalar full-tensor branch below, two sites per instruction: the LDS.128
                     // quads are aligned pairs already and the coefficients come from shared memory as (J, J)
@@ -805,8 +810,8 @@ template <int JJ, int K> struct CtLink {
     __device__ __forceinline__ constexpr int low() const { return D::low; }
     __device__ __forceinline__ constexpr int idx() const { return K; }
     __device__ __forceinline__ constexpr jit_real J(int e) const { return D::J(e); }
-    template <typename R, int V, int NC> __device__ __forceinline__ void fetch(const R *__restrict__ base, size_t N, int Z0, int Zd, R (&t)[3][V]) const {
-        load_shifted_nc<R, V, NC>(base, N, Z0, D::cZ, Zd, t);
+    template <typename R, int V, int NC> __device__ __forceinline__ void fetch(const R *__restrict__ sp, int nb, size_t N, int Z0, int Zd, R (&t)[3][V]) const {
+        load_shifted_nc<R, V, NC>(sp, N, nb, Z0, D::cZ, Zd, t);
     }
 };
 template <int JJ> struct CtClass {

@@ -43,5 +43,6 @@ run("C3 CrI3 honeycomb 512^2 (1NN+2NN+3NN, D)", lambda: spec_of("cri3", (512, 51
 run("C4 skyrmion hex 1024^2 (DMI, D, h, Q)", lambda: spec_of("skyrmion", (1024, 1024, 1)), 3, 16, np.full(16, 0.3), H=np.linspace(0, 0.7, 16), z=3)
 run("C5 Heisenberg sc 256^3 T-scan", lambda: cu(256), 3, 8, 0.8 * 1.443 * (1.3 / 0.8) ** (np.arange(8) / 7), z=6)
 run("C5 + dipole stencil r<=2 (32 links), 128^3", lambda: add_dipole_stencil(cu(128), 0.1, 2.0), 3, 8, np.linspace(1.2, 1.9, 8), z=32, nsw=4)
+run("C5 + dipole stencil r<=2 (32 links), 256^3", lambda: add_dipole_stencil(cu(256), 0.1, 2.0), 3, 8, 0.8 * 1.443 * (1.3 / 0.8) ** (np.arange(8) / 7), z=32, nsw=8)
 if not ONLY and PREC == 32:
     json.dump(rows, open("gpurun_out/configs_r1.json", "w"), indent=1)
