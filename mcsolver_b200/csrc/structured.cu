@@ -1597,7 +1597,7 @@ template <int MODE> static void launch_pass(mcg_system *s, int colour, uint64_t 
         if constexpr (MODE != 2) launched = jit_launch_pass(s, colour, MODE, a, q0, rowsPerBlock, nrb, sweep, pAtt, grid, block);
         // full 3x3 tensors on fp32 Heisenberg items that the specialiser did not take (dipole stencils): asynchronous link pipeline
         if constexpr (MODE != 2) {
-            static const bool noAsync = getenv("MCG_NO_ASYNC") != nullptr;
+            const bool noAsync = getenv("MCG_NO_ASYNC") != nullptr;   // read per launch: tests switch it inside one process
             if (!launched && !noAsync && st->d_asTab && st->V == 4 && block.x * block.y == 256) {
                 constexpr size_t dyn = (size_t)ASYNC_D * 3 * 256 * sizeof(float4);
                 static bool attrSet[2][2] = {{false, false}, {false, false}};
