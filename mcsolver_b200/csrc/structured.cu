@@ -991,7 +991,7 @@ static bool jit_launch_topo(mcg_system *s, const StructArgs &a, int nzc, int nyc
     if (jp->failed) return false;
     double *sums = s->d_sums;
     void *params[] = {(void *)&a, &nzc, &nyc, &sums};
-    CUresult r = api.launchKernel(jp->f[0], grid.x, grid.y, grid.z, block.x, block.y, 1, 0, (CUstream)s->stream, params, nullptr);
+    CUresult r = api.launchKernel(jp->f[0], grid.x, (grid.y + TOPO_XPT - 1) / TOPO_XPT, grid.z, block.x, block.y, 1, 0, (CUstream)s->stream, params, nullptr);
     if (r != CUDA_SUCCESS) throw Error(MCG_ERR_CUDA, "cuLaunchKernel of the JIT topological-charge kernel failed");
     return true;
 }
