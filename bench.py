@@ -199,6 +199,22 @@ def wolff_metric(device, L=4096, steps=100):
             "algorithm": "bond activation + atomicCAS union-find over the whole lattice, seed's cluster reflected"}
 
 
+def fp64_state_metric(device, spec, Ts, sweeps, peak):
+    """The same workload with fp64 spin state (the shims' default precision; 24 B/spin, 72 B per attempt): device-timed
+    sweeps with every sweep measured, outside the timed region of the headline number.  Informational."""
+    from mcsolver_b200 import engine
+    try:
+        with engine.System.from_spec(spec, 3, precision=64, nReplica=len(Ts), beta=1 / np.asarray(Ts), seed=1, device=device) as s:
+            s.init_spins(0.0)
+            s.timed_sweeps(3, with_measure=True)
+            ms = s.timed_sweeps(sweeps, with_measure=True)
+        att = len(Ts) * spec.nsite * sweeps / (ms * 1e-3)
+        return {"value": att, "unit": "attempts/s", "dtype": "f64", "bytes_per_attempt": 72, "sweeps": sweeps,
+                "roofline_frac": att * 72 / (peak * 1e9)}
+    except Exception as e:      # never let the informational leg break the contract line
+        return {"error": str(e)[:200]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -316,12 +332,16 @@ def main():
     if rank == 0 and world == 1 and not a.no_wolff:
         wolff = wolff_metric(local)
 
+    f64 = None
+    if rank == 0 and world == 1 and not a.no_wolff:
+        f64 = fp64_state_metric(local, spec, Ts, 20, measured_peak()[0])
+
     if rank == 0:
         line = {"metric": "attempted Metropolis spin updates per second", "value": value, "unit": "attempts/s", "n_gpus": world,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_max / a.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(a, world), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roof, "cpu_baseline": cpu, "wolff": wolff, "host_wall_s": wall,
+                "roofline": roof, "cpu_baseline": cpu, "wolff": wolff, "fp64_state": f64, "host_wall_s": wall,
                 "check": {"replica0_T": float(Ts[0]), "e_per_site_over_kT": float(out0[8]), "U4": float(out0[10])}}
         print(json.dumps(line), flush=True)
     if dist is not None:
