@@ -168,8 +168,11 @@ MCG_API int mcg_counters(mcg_system *sys, int replica, int64_t *attempts, int64_
 /* ---- instrumentation (bench.py) ----
  * mcg_launch_count: kernels this system has launched so far.
  * mcg_profile_passes(on): bracket every Metropolis colour-pass launch with CUDA events on the launch stream;
- * mcg_profile_read: total device time (ms) and number of the bracketed launches since the last read. */
+ * mcg_profile_read: total device time (ms) and number of the bracketed launches since the last read.
+ * mcg_jit_launch_count: how many of the launches were NVRTC-specialised kernels (mcg_pass_m0/m1, mcg_topo) - lets a
+ * test prove which build of the colour pass it exercised. */
 MCG_API int mcg_launch_count(mcg_system *sys, int64_t *launches);
+MCG_API int mcg_jit_launch_count(mcg_system *sys, int64_t *launches);
 MCG_API int mcg_profile_passes(mcg_system *sys, int on);
 MCG_API int mcg_profile_read(mcg_system *sys, double *total_ms, int64_t *nlaunches);
 
@@ -203,6 +206,24 @@ MCG_API int mcg_pt_decide(int n, const double *beta, const double *field, const 
  * and its inverse; n_acc = row length. */
 MCG_API int mcg_acc_get(mcg_system *sys, int label, double *row, int *n_acc);
 MCG_API int mcg_acc_set(mcg_system *sys, int label, const double *row);
+
+
+/* ---- parallel tempering driven by the library: one process per GPU, NCCL allgather per swap step ----
+ * SURVEY 8e / north_star: "only per-replica energies cross NVLink through an NCCL allgather at each swap step".
+ * mcg_comm_unique_id (rank 0) produces the MCG_COMM_ID_BYTES-byte communicator id that the host layer hands to every
+ * rank (any channel: a socket, a file, MPI); mcg_pt_setup joins the communicator and installs the ladder;
+ * mcg_pt_run enqueues the whole loop - measured sweeps, pack kernel, ncclAllGather of 3 doubles per replica, decide-and-
+ * relabel kernel - on the system's stream without host synchronisation; mcg_pt_reduce (collective) sums the per-label
+ * accumulators over ranks with ncclAllReduce; mcg_pt_results reads a label's result tuple from those sums.
+ * libnccl.so.2 is dlopen'ed on first use (MCG_NCCL_LIB overrides the path); without it every call that needs a
+ * communicator fails with MCG_ERR_NCCL.  world = 1 needs no NCCL. */
+#define MCG_COMM_ID_BYTES 128
+MCG_API int mcg_comm_unique_id(char *id, int len);
+MCG_API int mcg_pt_setup(mcg_system *sys, int rank, int world, const char *id, int nLabels, const double *beta, const double *field);
+MCG_API int mcg_pt_run(mcg_system *sys, int64_t nthermal, int64_t nsweep, int sweeps_per_swap, double *elapsed_ms);
+MCG_API int mcg_pt_stats(mcg_system *sys, int64_t *attempts, int64_t *accepts, int32_t *holder);
+MCG_API int mcg_pt_reduce(mcg_system *sys);
+MCG_API int mcg_pt_results(mcg_system *sys, int label, double *out, double *groupOut);
 
 #ifdef __cplusplus
 }

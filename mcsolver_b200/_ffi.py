@@ -67,6 +67,7 @@ SIGNATURES = {
     "mcg_results": (_i, [_vp, _i, _vp, _vp]),
     "mcg_counters": (_i, [_vp, _i, _vp, _vp, _vp]),
     "mcg_launch_count": (_i, [_vp, _vp]),
+    "mcg_jit_launch_count": (_i, [_vp, _vp]),
     "mcg_profile_passes": (_i, [_vp, _i]),
     "mcg_profile_read": (_i, [_vp, _vp, _vp]),
     "mcg_run": (_i, [_vp, _i, _i64, _i64, _i64, _i, _vp]),
@@ -76,6 +77,12 @@ SIGNATURES = {
     "mcg_pt_state": (_i, [_vp, _vp]),
     "mcg_pt_set_labels": (_i, [_vp, _vp, _vp, _vp]),
     "mcg_pt_decide": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _u64, _u64, _vp]),
+    "mcg_comm_unique_id": (_i, [_vp, _i]),
+    "mcg_pt_setup": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp]),
+    "mcg_pt_run": (_i, [_vp, _i64, _i64, _i, _vp]),
+    "mcg_pt_stats": (_i, [_vp, _vp, _vp, _vp]),
+    "mcg_pt_reduce": (_i, [_vp]),
+    "mcg_pt_results": (_i, [_vp, _i, _vp, _vp]),
     "mcg_acc_get": (_i, [_vp, _i, _vp, _vp]),
     "mcg_acc_set": (_i, [_vp, _i, _vp]),
 }

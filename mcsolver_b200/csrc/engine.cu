@@ -84,7 +84,7 @@ static void select_device(const mcg_config *cfg, mcg_system *s) {
 
 static GenArgs gen_args(const mcg_system *s) {
     GenArgs a;
-    a.N = s->N; a.maxL = s->maxL; a.R = s->R; a.nJ = s->nJ; a.ncls = s->ncls;
+    a.N = s->N; a.maxL = s->maxL; a.R = s->R; a.nJ = s->nJ; a.ncls = s->ncls; a.dupLinks = s->dupLinks ? 1 : 0;
     a.nbrp = s->d_nbrp; a.jtype = s->d_jtype; a.Jtab = s->d_Jtab; a.cls = s->d_cls; a.clsS = s->d_clsS; a.clsD = s->d_clsD;
     a.site_of = s->d_site_of; a.spin = s->d_spin; a.beta = s->d_beta; a.field = s->d_field; a.cnt = s->d_cnt;
     a.key = make_rng_key(s->seed);
@@ -246,6 +246,14 @@ static mcg_system *create_from_tables(const mcg_tables *t, const mcg_config *cfg
         cls[p] = (uint16_t)ic->second;
     }
     s->nJ = (int)jmap.size(); s->ncls = (int)cmap.size();
+    {   // several link slots between one pair of sites?  (the Wolff bond uniforms then need the occurrence index)
+        std::vector<int32_t> seen;
+        for (int i = 0; i < N && !s->dupLinks; i++) {
+            seen.assign(t->nbr + (size_t)i * maxL, t->nbr + (size_t)i * maxL + t->nlink[i]);
+            std::sort(seen.begin(), seen.end());
+            s->dupLinks = std::adjacent_find(seen.begin(), seen.end()) != seen.end();
+        }
+    }
     s->isoNoOnsite = true;
     for (double dv : clsD) if (dv != 0.0) s->isoNoOnsite = false;
     for (size_t j = 0; j + JW <= Jtab.size() && t->model != 1; j += JW) {
@@ -328,6 +336,9 @@ static mcg_system *create_from_tables(const mcg_tables *t, const mcg_config *cfg
         MCG_CUDA(cudaMemset(s->d_gacc, 0, sizeof(double) * s->R * (n1 + 1) * n1));
     }
     MCG_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    // table uploads and accumulator clears above went through the legacy default stream, which a non-blocking stream is
+    // not ordered with: drain it once before the first kernel can touch them
+    MCG_CUDA(cudaDeviceSynchronize());
     return sys.release();
 }
 
@@ -656,11 +667,12 @@ static void run(mcg_system *s, int algorithm, int64_t nthermal, int64_t nsweep, 
     MCG_CUDA(cudaStreamSynchronize(s->stream));
 }
 
-static void results(mcg_system *s, int r, double *out, double *groupOut) {
+// accBase / gaccBase: the accumulator rows to read (the system's own, or the cross-rank sums of a tempering run)
+void results_from(mcg_system *s, const double *accBase, const double *gaccBase, int r, double *out, double *groupOut) {
     MCG_REQUIRE(r >= 0 && r < s->nLabel && out, "bad replica/label index or NULL out");
     double A[NACC];
     MCG_CUDA(cudaStreamSynchronize(s->stream));
-    MCG_CUDA(cudaMemcpy(A, s->d_acc + (size_t)r * NACC, sizeof(A), cudaMemcpyDeviceToHost));
+    MCG_CUDA(cudaMemcpy(A, accBase + (size_t)r * NACC, sizeof(A), cudaMemcpyDeviceToHost));
     double ns = A[ACC_NMEAS];
     if (!(ns > 0)) throw Error(MCG_ERR_STATE, "no measurement has been accumulated yet");
     double U4 = (A[ACC_M2] / ns) * (A[ACC_M2] / ns) / (A[ACC_M4] / ns);                     // heisenbergLib.c:833
@@ -680,12 +692,35 @@ static void results(mcg_system *s, int r, double *out, double *groupOut) {
     out[26] = A[ACC_Q] / ns;
     if (groupOut) {
         int n = (s->nG + 2) * (s->nG + 1);
-        if (s->d_gacc && r < s->nLabel) {
-            MCG_CUDA(cudaMemcpy(groupOut, s->d_gacc + (size_t)r * n, sizeof(double) * n, cudaMemcpyDeviceToHost));
+        if (gaccBase && r < s->nLabel) {
+            MCG_CUDA(cudaMemcpy(groupOut, gaccBase + (size_t)r * n, sizeof(double) * n, cudaMemcpyDeviceToHost));
             for (int i = 0; i < n; i++) groupOut[i] /= ns;
         } else
             for (int i = 0; i < n; i++) groupOut[i] = 0.0;
     }
+}
+
+static void results(mcg_system *s, int r, double *out, double *groupOut) { results_from(s, s->d_acc, s->d_gacc, r, out, groupOut); }
+
+// one Metropolis sweep followed by the per-sweep measurement (fused into the colour passes on structured systems)
+void measured_sweep(mcg_system *s, double pAtt) {
+    if (s->structured) {
+        s->wolffPrimed = false;
+        structured_sweeps(s, 1, pAtt, true);
+        s->launches++;
+        k_finalize_sweep<<<(s->R + 63) / 64, 64, 0, s->stream>>>(s->model, s->R, s->N, s->nLat, s->d_sums, s->d_acc, s->d_slot, s->d_last);
+    } else {
+        metropolis_sweeps(s, 1, pAtt);
+        measure(s);
+    }
+}
+
+void reset_measurements_async(mcg_system *sys) {
+    MCG_CUDA(cudaMemsetAsync(sys->d_acc, 0, sizeof(double) * sys->nLabel * NACC, sys->stream));
+    MCG_CUDA(cudaMemsetAsync(sys->d_sums, 0, sizeof(double) * sys->R * NSUM, sys->stream));
+    MCG_CUDA(cudaMemsetAsync(sys->d_cnt, 0, sizeof(unsigned long long) * sys->R * NCNT, sys->stream));
+    if (sys->d_gacc) MCG_CUDA(cudaMemsetAsync(sys->d_gacc, 0, sizeof(double) * sys->nLabel * (sys->nG + 2) * (sys->nG + 1), sys->stream));
+    sys->measCtr = 0;
 }
 
 }  // namespace mcg
@@ -702,6 +737,7 @@ mcg_system::~mcg_system() {
                     d_gsum, d_gacc, d_colourStart};
     for (void *b : bufs) mcg::pool_free(b);
     if (st) mcg::structured_destroy(st);
+    if (pt) mcg::pt_destroy(pt);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -749,6 +785,7 @@ MCG_API int mcg_create_lattice(const mcg_lattice_desc *d, const mcg_config *cfg,
             MCG_CUDA(cudaMemset(sys->d_gacc, 0, sizeof(double) * sys->R * n));
         }
         MCG_CUDA(cudaStreamCreateWithFlags(&sys->stream, cudaStreamNonBlocking));
+        MCG_CUDA(cudaDeviceSynchronize());   // uploads / clears on the legacy stream are complete before s->stream is used
         *out = sys.release();
     });
 }
@@ -822,17 +859,7 @@ MCG_API int mcg_timed_sweeps(mcg_system *sys, int64_t nsweeps, double pAttempt, 
         MCG_CUDA(cudaEventRecord(e0, sys->stream));
         if (!with_measure) metropolis_sweeps(sys, nsweeps, pAttempt);
         else
-            for (int64_t i = 0; i < nsweeps; i++) {
-                if (sys->structured) {
-                    sys->wolffPrimed = false;
-                    structured_sweeps(sys, 1, pAttempt, true);
-                    sys->launches++;
-                    k_finalize_sweep<<<(sys->R + 63) / 64, 64, 0, sys->stream>>>(sys->model, sys->R, sys->N, sys->nLat, sys->d_sums, sys->d_acc, sys->d_slot, sys->d_last);
-                } else {
-                    metropolis_sweeps(sys, 1, pAttempt);
-                    measure(sys);
-                }
-            }
+            for (int64_t i = 0; i < nsweeps; i++) measured_sweep(sys, pAttempt);
         MCG_CUDA(cudaEventRecord(e1, sys->stream));
         MCG_CUDA(cudaEventSynchronize(e1));
         float ms = 0;
@@ -851,11 +878,7 @@ MCG_API int mcg_measure(mcg_system *sys) {
 }
 MCG_API int mcg_reset_measurements(mcg_system *sys) {
     SYS_GUARD({
-        MCG_CUDA(cudaMemsetAsync(sys->d_acc, 0, sizeof(double) * sys->nLabel * NACC, sys->stream));
-        MCG_CUDA(cudaMemsetAsync(sys->d_sums, 0, sizeof(double) * sys->R * NSUM, sys->stream));
-        MCG_CUDA(cudaMemsetAsync(sys->d_cnt, 0, sizeof(unsigned long long) * sys->R * NCNT, sys->stream));
-        if (sys->d_gacc) MCG_CUDA(cudaMemsetAsync(sys->d_gacc, 0, sizeof(double) * sys->nLabel * (sys->nG + 2) * (sys->nG + 1), sys->stream));
-        sys->measCtr = 0;
+        reset_measurements_async(sys);
         MCG_CUDA(cudaStreamSynchronize(sys->stream));
     });
 }
@@ -890,6 +913,9 @@ MCG_API int mcg_counters(mcg_system *sys, int replica, int64_t *attempts, int64_
 
 MCG_API int mcg_launch_count(mcg_system *sys, int64_t *launches) {
     return guarded([&] { MCG_REQUIRE(sys && launches, "NULL argument"); *launches = (int64_t)sys->launches; });
+}
+MCG_API int mcg_jit_launch_count(mcg_system *sys, int64_t *launches) {
+    return guarded([&] { MCG_REQUIRE(sys && launches, "NULL argument"); *launches = (int64_t)sys->jitLaunches; });
 }
 MCG_API int mcg_profile_passes(mcg_system *sys, int on) {
     return guarded([&] { MCG_REQUIRE(sys, "system is NULL"); sys->profilePasses = on != 0; });

@@ -12,8 +12,11 @@
 // with the FULL move (the reference reads the half move; oracle flag wolffHalfMove=0).
 //
 // The uniform of a bond is one Philox word keyed by (lower reference site id, higher reference site
-// id, step, replica): independent of the link-slot order, the storage layout and the path, so the
-// table path, the structured path and the oracle's FIFO restatement select the same clusters.
+// id, occurrence, step, replica): independent of the storage layout and the path, so the table path,
+// the structured path and the oracle's FIFO restatement select the same clusters.  "occurrence"
+// separates several links between the same two sites (tables built with forceAdd: a dipole link next
+// to an exchange bond, Lattice.py:298): each is an independent bond, so the pair activates with
+// 1-(1-p1)(1-p2) as in the reference's sequential test (heisenbergLib.c:355-366), not with max(p1,p2).
 //
 // The kernels are written over a topology policy: TableTopo (neighbour tables of the legacy payload)
 // or StructTopo (structured.cu: neighbours computed from the class decomposition).
@@ -37,10 +40,13 @@ struct WolffArgs {
     uint32_t replica0;
 };
 
-__host__ __device__ __forceinline__ void rng_bond(const RngKey &key, uint32_t replica, uint64_t step, uint32_t lo, uint32_t hi,
-                                                  uint32_t (&out)[4]) {
-    philox4x32_10(lo, hi, (STREAM_WBOND << 24) | (uint32_t)((step >> 16) & 0xFFFFFFu), (replica & 0xFFFFu) | ((uint32_t)(step & 0xFFFFu) << 16),
-                  key, out);
+// occ: occurrence index of the bond among the links of its site pair (0 unless a pair is linked more than once: every
+// duplicate is an independent bond with its own uniform, word occ & 3 of the block with sub-stream occ >> 2)
+__host__ __device__ __forceinline__ uint32_t rng_bond(const RngKey &key, uint32_t replica, uint64_t step, uint32_t lo, uint32_t hi, uint32_t occ = 0) {
+    uint32_t out[4];
+    philox4x32_10(lo, hi, (STREAM_WBOND << 24) | ((occ >> 2) << 16) | (uint32_t)((step >> 16) & 0xFFFFu),
+                  (replica & 0xFFFFu) | ((uint32_t)(step & 0xFFFFu) << 16), key, out);
+    return pick4(out, occ);
 }
 
 template <int NC, typename real>
@@ -108,6 +114,14 @@ template <int NC, typename real> struct TableTopo {
         iq = a.site_of[q];
         return iq >= ip;
     }
+    // how many earlier link slots of this site lead to the same neighbour (link lists are symmetric: the k-th link of a pair
+    // has the same rank in both endpoints' lists, Lattice.py:260-262)
+    __device__ __forceinline__ uint32_t occurrence(const Ctx &c, int k, int q) const {
+        uint32_t n = 0;
+        if (a.dupLinks)
+            for (int j = 0; j < k; j++) n += a.nbrp[(size_t)j * a.N + c.p] == q;
+        return n;
+    }
     __device__ __forceinline__ real S(const Ctx &c) const { return ((const real *)a.clsS)[a.cls[c.p]]; }
     __device__ __forceinline__ void D(const Ctx &c, real (&d)[3]) const {
         const real *D = (const real *)a.clsD + 3 * a.cls[c.p];
@@ -145,9 +159,8 @@ __device__ __forceinline__ void wolff_bonds_site(const TOPO &topo, const WolffAr
         if (NC == 1) corr = real(2) * beta * J[0] * ap * sp[q];                       // isingLib.c:183-185
         else corr = real(2) * ap * proj[q] * beta * quad_form<NC, real, FULLJ>(J, n, n);   // heisenbergLib.c:355
         if (corr < real(0)) {
-            uint32_t wd[4];
-            rng_bond(w.key, w.replica0 + r, w.step, (uint32_t)min(ip, iq), (uint32_t)max(ip, iq), wd);
-            if ((real(1) - r_exp<real>(corr)) > u01<real>(wd[0])) uf_unite(parent, p, q);
+            const uint32_t wd = rng_bond(w.key, w.replica0 + r, w.step, (uint32_t)min(ip, iq), (uint32_t)max(ip, iq), topo.occurrence(c, k, q));
+            if ((real(1) - r_exp<real>(corr)) > u01<real>(wd)) uf_unite(parent, p, q);
         }
     }
 }

@@ -59,6 +59,7 @@ struct StructuredSystem {
     SLinkD *d_links = nullptr;
     void *d_J = nullptr;
     int *d_classOf = nullptr, *d_circuits = nullptr, *d_tverts = nullptr, *d_ttris = nullptr, *d_gmask = nullptr;
+    bool asyncAttrSet[2][2] = {{false, false}, {false, false}};   // k_struct_async<MODE, PARTIAL>: dynamic shared memory opt-in done on this system's device
     AsTab *d_asTab = nullptr;                     // [nclass][PT_MAXL + 1] link tables of the asynchronous pipeline (fp32 full-tensor passes)
     std::vector<int> gmaskHost;
     bool groupInSC = true;
@@ -132,6 +133,8 @@ template <int NC, typename real> struct StructTopo {
         iq = ((xn * a.Ly + yn) * a.Lz + zn) * a.norb + L.o2;
         return true;
     }
+    // bond templates with the same (orbital, offset) are merged when the class tables are built: a pair is linked once
+    __device__ __forceinline__ uint32_t occurrence(const Ctx &, int, int) const { return 0u; }
     __device__ __forceinline__ int site_id_of(int q) const { return struct_site_id(a, q); }
     __device__ __forceinline__ int pos_of_site(int id) const {
         int o = id % a.norb, cell = id / a.norb;
@@ -927,6 +930,7 @@ bool jit_launch_pass(mcg_system *s, int colour, int mode, const StructArgs &a, i
     void *params[] = {(void *)&a, &q0, &rowsPerBlock, &nrb, &sweep, s->prec == 32 ? (void *)&pf : (void *)&pd};
     CUresult r = api.launchKernel(jp->f[mode], grid.x, 1, 1, block.x, block.y, 1, 0, (CUstream)s->stream, params, nullptr);
     if (r != CUDA_SUCCESS) throw Error(MCG_ERR_CUDA, "cuLaunchKernel of the JIT pass kernel failed");
+    s->jitLaunches++;
     return true;
 }
 
@@ -993,6 +997,7 @@ static bool jit_launch_topo(mcg_system *s, const StructArgs &a, int nzc, int nyc
     void *params[] = {(void *)&a, &nzc, &nyc, &sums};
     CUresult r = api.launchKernel(jp->f[0], grid.x, (grid.y + TOPO_XPT - 1) / TOPO_XPT, grid.z, block.x, block.y, 1, 0, (CUstream)s->stream, params, nullptr);
     if (r != CUDA_SUCCESS) throw Error(MCG_ERR_CUDA, "cuLaunchKernel of the JIT topological-charge kernel failed");
+    s->jitLaunches++;
     return true;
 }
 
@@ -1600,13 +1605,13 @@ template <int MODE> static void launch_pass(mcg_system *s, int colour, uint64_t 
             const bool noAsync = getenv("MCG_NO_ASYNC") != nullptr;   // read per launch: tests switch it inside one process
             if (!launched && !noAsync && st->d_asTab && st->V == 4 && block.x * block.y == 256) {
                 constexpr size_t dyn = (size_t)ASYNC_D * 3 * 256 * sizeof(float4);
-                static bool attrSet[2][2] = {{false, false}, {false, false}};
                 const PassTable<float> &P = *reinterpret_cast<const PassTable<float> *>(st->passTables[colour].data());
                 auto go = [&]<bool PARTIAL>() {
                     auto kern = k_struct_async<MODE, PARTIAL>;
-                    if (!attrSet[MODE][PARTIAL]) {
+                    // function attributes are per device: set once per system (a process may hold systems on several GPUs)
+                    if (!st->asyncAttrSet[MODE][PARTIAL]) {
                         MCG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-                        attrSet[MODE][PARTIAL] = true;
+                        st->asyncAttrSet[MODE][PARTIAL] = true;
                     }
                     kern<<<grid, block, dyn, s->stream>>>(a, P, st->d_asTab, q0, rowsPerBlock, nrb, sweep, (float)pAtt);
                 };

@@ -12,6 +12,7 @@ namespace mcg {
 struct GenArgs {
     int N, maxL, R;
     int nJ, ncls;
+    int dupLinks;               // some site pair is linked through more than one slot (forceAdd'ed tables)
     const int32_t *nbrp;        // [maxL][N] neighbour storage positions (pad: self)
     const uint16_t *jtype;      // [maxL][N] index into Jtab (0 = zero tensor)
     const void *Jtab;           // [nJ][9] (Ising [nJ][1]) real
@@ -28,7 +29,16 @@ struct GenArgs {
 };
 
 struct StructuredSystem;  // structured.cu
+struct PtState;           // pt.cu: ladder, label holders and the NCCL communicator of an in-library tempering run
+void pt_destroy(PtState *p);
 
+}  // namespace mcg
+
+namespace mcg {
+// engine.cu internals used by pt.cu
+void measured_sweep(mcg_system *s, double pAtt);
+void reset_measurements_async(mcg_system *s);
+void results_from(mcg_system *s, const double *accBase, const double *gaccBase, int r, double *out, double *groupOut);
 }  // namespace mcg
 
 struct mcg_system {
@@ -50,6 +60,7 @@ struct mcg_system {
     // measurement tables
     int nLat = 0, nTri = 0, nG = 0, maxG = 0, nR = 0, nC = 0;
     bool selfPairs = false;
+    bool dupLinks = false;
     // device buffers (generic path)
     int32_t *d_nbrp = nullptr, *d_site_of = nullptr, *d_pos_of = nullptr, *d_pairs = nullptr, *d_tri = nullptr;
     int32_t *d_mi = nullptr, *d_mj = nullptr;
@@ -82,9 +93,11 @@ struct mcg_system {
     cudaStream_t stream = nullptr;
     // instrumentation: kernels launched so far; optional CUDA-event timing of the colour-pass kernel
     uint64_t launches = 0;
+    uint64_t jitLaunches = 0;     // of those, launches of NVRTC-specialised kernels (mcg_pass_m0/m1, mcg_topo)
     bool profilePasses = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> passEvents;
     mcg::StructuredSystem *st = nullptr;   // structured (descriptor) path state, owned
+    mcg::PtState *pt = nullptr;            // parallel-tempering state (mcg_pt_setup), owned
     size_t real_size() const { return prec == 32 ? 4 : 8; }
     ~mcg_system();
 };

@@ -68,6 +68,9 @@ class _TableArrays:
         self.rNbr = i32(rNbr if rNbr is not None else []).reshape(-1)
         self.nR = self.rOrb.size
         self.nC = self.rCl.size // self.nR if self.nR else 0
+        if self.nR and (self.rCl.size != self.nR * self.nC or self.rNbr.size != self.nR * self.maxL):
+            raise ValueError("rOrbCluster needs nR*nC and linkedOrb_rnorm nR*maxNLinking entries (got %d, %d for nR=%d)"
+                             % (self.rCl.size, self.rNbr.size, self.nR))
         self.ignoreOffDiag = int(ignoreOffDiag)
 
     @classmethod
@@ -232,6 +235,12 @@ class System:
     def launch_count(self):
         n = C.c_int64(0)
         check(_ffi.lib().mcg_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def jit_launch_count(self):
+        """Launches of NVRTC-specialised kernels so far (0 = the offline runtime-table kernels ran)."""
+        n = C.c_int64(0)
+        check(_ffi.lib().mcg_jit_launch_count(self._h, C.byref(n)))
         return n.value
 
     def profile_passes(self, on=True):

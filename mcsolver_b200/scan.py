@@ -22,14 +22,15 @@ def shard(n_points, rank, world):
 
 
 def run_points(spec, model, T, H, nthermal, nsweep, ninterval=0, algorithm=engine.METROPOLIS, precision=32, seed=1,
-               rank=0, world=1, device=-1, flunc=0.0, spin_frames=0, tables=False, want_groups=False, block_spin=False):
+               rank=0, world=1, device=-1, flunc=0.0, spin_frames=0, tables=False, want_groups=False, block_spin=False,
+               info=None):
     """Run the points (T[i], H[i]) owned by `rank` and return (indices, results[n,27|10], frames).
 
     spec: LatticeSpec (bond templates + supercell).  ninterval<=0 means N (mcMain.py:145).
     tables=True forces the table-driven engine (always full tuples); default is the structured path, which fills the
     block-spin slots 11-19 (Ising 6-7) only when block_spin=True (one more read of the configuration per sweep).
     Result rows have the reference's tuple layout with E, E2 still in beta units (caller rescales
-    exactly as mcMain.py:251 does)."""
+    exactly as mcMain.py:251 does).  info: optional dict, filled with the launch counters of the job."""
     T = np.atleast_1d(np.asarray(T, dtype=float))
     H = np.atleast_1d(np.asarray(H, dtype=float))
     if T.shape != H.shape:
@@ -57,6 +58,8 @@ def run_points(spec, model, T, H, nthermal, nsweep, ninterval=0, algorithm=engin
         res = [s.results(r) for r in range(idx.size)]
         out = np.stack([r[0] for r in res])
         groups = np.stack([r[1] for r in res]) if (model != engine.ISING and res[0][1] is not None and res[0][1].size) else None
+        if info is not None:
+            info.update(launches=s.launch_count(), jit_launches=s.jit_launch_count(), colours=s.num_colours())
     return idx, ((out, groups) if want_groups else out), frames
 
 

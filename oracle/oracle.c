@@ -342,14 +342,17 @@ static void on_attempt_philox(const orc_sys *s, double *sp, int i, const uint32_
  * uniform of a bond is keyed by its lower-id endpoint and that endpoint's link slot, seed site
  * and plane normal come from stream WSEED; halfMove=0 evaluates the residual with the full move. */
 static uint32_t bond_uniform_word(const orc_sys *s, uint64_t seed, uint32_t replica, uint64_t step, int a, int k) {
-    /* one Philox word per bond, keyed by (lower site id, higher site id, step, replica): engine convention rng_bond() */
-    int b = s->nbr[(size_t)a * s->maxL + k];
+    /* one Philox word per bond, keyed by (lower site id, higher site id, occurrence, step, replica): engine convention
+     * rng_bond().  occurrence = how many earlier link slots of this site lead to the same neighbour (duplicate links of a
+     * pair - forceAdd'ed dipole links next to an exchange bond, Lattice.py:298 - are independent bonds, heisenbergLib.c:355-366) */
+    int b = s->nbr[(size_t)a * s->maxL + k], occ = 0;
+    for (int j = 0; j < k; j++) occ += s->nbr[(size_t)a * s->maxL + j] == b;
     uint32_t lo = (uint32_t)(a < b ? a : b), hi = (uint32_t)(a < b ? b : a);
-    uint32_t ctr[4] = {lo, hi, ((uint32_t)STREAM_WBOND << 24) | (uint32_t)((step >> 16) & 0xFFFFFFu),
+    uint32_t ctr[4] = {lo, hi, ((uint32_t)STREAM_WBOND << 24) | (((uint32_t)occ >> 2) << 16) | (uint32_t)((step >> 16) & 0xFFFFu),
                        (replica & 0xFFFFu) | ((uint32_t)(step & 0xFFFFu) << 16)};
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, out[4];
     orc_philox4x32(ctr, key, out);
-    return out[0];
+    return out[occ & 3];
 }
 
 static void on_block_update(const orc_sys *s, double *sp, orc_state *st, int mode, uint64_t seed, uint32_t replica,

@@ -2,7 +2,7 @@
 
 Needs /root/reference (host Python, imported with tkinter/matplotlib stubbed) and oracle/_ref
 (the reference C engines compiled by oracle/Makefile; xylib with the 2-line seedID fix).
-Run:  python tests/golden/make_golden.py [tables] [kat] [runs] [stats]
+Run:  python tests/golden/make_golden.py [tables] [kat] [runs] [stats] [dipole] [u4cross] [stats32]
 Writes tests/golden/{tables,kat,runs,stats}.json(+npz).  None of the tests reads
 /root/reference at run time: they read these files.
 
@@ -237,8 +237,39 @@ def make_u4cross():
     print("u4cross: %d runs in %.0fs" % (len(jobs), time.time() - t0))
 
 
+# ---- the size at which the engine's DEFAULT path is the NVRTC-specialised colour pass (N*R >= 2^20): sc 32^3, three
+# temperatures x 16 seeds = 48 replicas in one batch on the GPU side ----
+S32_T = [1.30, 1.45, 1.70]
+S32_L = 32
+S32_SWEEPS = (600, 2400)
+S32_K = 16
+
+
+def _s32_job(job):
+    T, seed = job
+    t = build_tables(spec_of("cubic", (S32_L,) * 3), T, 3)
+    res = rh.run_ref_engine(3, t.on_args(0, S32_SWEEPS[0], S32_SWEEPS[1], t.N, 0.0, 0.0, 0), seed=seed)
+    return T, seed, list(res[:27])
+
+
+def make_stats32():
+    import multiprocessing as mp
+    jobs = [(T, k) for T in S32_T for k in range(1, S32_K + 1)]
+    t0 = time.time()
+    with mp.get_context("fork").Pool(processes=min(8, os.cpu_count() or 1)) as pool:
+        res = pool.map(_s32_job, jobs, chunksize=1)
+    out = []
+    for T in S32_T:
+        rows = np.array([r[2] for r in res if r[0] == T])
+        out.append(dict(tag="C5_cubic32", spec="cubic", L=(S32_L,) * 3, model=3, algo=0, T=T, H=0.0, nthermal=S32_SWEEPS[0],
+                        nsweep=S32_SWEEPS[1], ninterval=S32_L ** 3, K=S32_K, mean=rows.mean(axis=0).tolist(),
+                        sigma=rows.std(axis=0, ddof=1).tolist(), rows=rows.tolist()))
+    json.dump(out, open(os.path.join(HERE, "stats32.json"), "w"))
+    print("stats32: %d runs in %.0fs" % (len(jobs), time.time() - t0))
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["tables", "kat", "runs", "stats", "dipole"]
     assert rh.have_reference_host() and rh.have_ref_engine(), "needs /root/reference and oracle/_ref (make -f oracle/Makefile)"
     for w in what:
-        {"tables": make_tables, "kat": make_kat, "runs": make_runs, "stats": make_stats, "dipole": make_dipole, "u4cross": make_u4cross}[w]()
+        {"tables": make_tables, "kat": make_kat, "runs": make_runs, "stats": make_stats, "dipole": make_dipole, "u4cross": make_u4cross, "stats32": make_stats32}[w]()

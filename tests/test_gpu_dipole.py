@@ -42,6 +42,56 @@ def test_all_pairs_dipole_on_the_table_path_matches_oracle(model):
         assert np.max(np.abs(got - r["spins"].reshape(got.shape))) < 1e-9
 
 
+@pytest.mark.parametrize("model", [1, 3])
+def test_wolff_with_duplicate_pair_links_matches_oracle_and_metropolis(model):
+    """Tables from add_dipole_all_pairs hold TWO link slots for nearest neighbours (exchange bond + forceAdd'ed dipole
+    link, Lattice.py:298).  Each slot is an independent bond of the cluster construction (heisenbergLib.c:355-366,
+    isingLib.c:183-185): its uniform is keyed by the occurrence index as well, the clusters equal the oracle's FIFO
+    growth step for step, and - the property that breaks if two slots share a uniform (pair added with max(p1,p2)
+    instead of 1-(1-p1)(1-p2)) - the Wolff chain samples the same distribution as the Metropolis chain."""
+    eng = _eng()
+    spec = spec_of("cubic", (3, 3, 2)) if model == 3 else spec_of("square", (4, 4, 1))
+    T = 2.2 if model == 1 else 1.3
+    alpha = -0.6 if model == 1 else 0.0            # Ising: ferromagnetic 1/r^3 tail so that BOTH slots of a pair can activate
+    t = build_tables(spec, T, model)
+    if model == 1:
+        t = add_dipole_all_pairs(spec, t, alpha / T)
+    else:                                          # O(3): duplicate every exchange link by hand (isotropic: no residual)
+        import dataclasses
+        assert np.all(t.nlink == t.maxL)
+        rNbr = np.full((t.rNbr.shape[0], 2 * t.maxL), -1, dtype=np.int32)
+        rNbr[:, :t.maxL] = t.rNbr
+        t = dataclasses.replace(t, maxL=2 * t.maxL, nbr=np.concatenate([t.nbr, t.nbr], axis=1), J=np.concatenate([0.5 * t.J, 0.5 * t.J], axis=1),
+                                nlink=(2 * t.nlink).astype(np.int32), rNbr=rNbr)
+    o = util.oracle_system(t, 0.0)
+    o.nR = 0
+    nb = np.asarray(t.nbr).reshape(t.N, -1)
+    assert any(len(set(row[:n])) < n for row, n in zip(nb, np.asarray(t.nlink)))       # the tables do hold duplicate pairs
+    with eng.System.from_tables(t, precision=64, seed=8) as s:
+        start = np.random.RandomState(3).choice([-1.0, 1.0], size=t.N) if model == 1 else o.init_spins_philox(0.9, seed=8)
+        s.set_spins(start)
+        r = o.run(3, 40, 1, 1, seed=8, spins=start)
+        s.wolff_steps(41)
+        got = s.get_spins()
+        assert np.max(np.abs(got - r["spins"].reshape(got.shape))) < 1e-9
+        assert s.counters() == tuple(int(v) for v in r["counters"])
+    # detailed balance: K independent Wolff chains against K Metropolis chains of the same tables
+    K = 32
+    rows = {}
+    for algo in (0, 1):
+        with eng.System.from_tables(t, precision=64, nReplica=K, seed=77 + algo) as s:
+            s.init_spins(0.0)
+            s.run(algo, 2000, 20000, t.N if algo == 0 else 2)
+            rows[algo] = np.array([s.results(k)[0] for k in range(K)])
+    eslot, mslot = (4, 0) if model == 1 else (8, 10)
+    for k in (eslot, mslot):
+        if model == 1 and k == eslot:
+            continue                               # isingLib's Metropolis energy is relative to the start (SURVEY 8 quirks)
+        a, b = rows[0][:, k], rows[1][:, k]
+        se = np.sqrt(a.var(ddof=1) / K + b.var(ddof=1) / K)
+        assert abs(a.mean() - b.mean()) <= 4.0 * se + 1e-9, (k, a.mean(), b.mean(), se)
+
+
 @pytest.mark.parametrize("model,L", [(3, (8, 8, 8)), (3, (12, 6, 6)), (1, (8, 8, 8))])
 def test_dipole_stencil_on_the_structured_path_matches_oracle(model, L):
     """Cut-off periodic dipole stencil (32 neighbours on sc within r<=2) = ordinary bond templates for the

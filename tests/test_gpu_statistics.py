@@ -7,6 +7,8 @@ the C ABI and the two sample means are compared with the combined standard error
 autoCorr (slot 7) depends on the update dynamics (random site vs colour sweeps) and is not compared;
 Ising <e> of the reference's Metropolis path is relative to an arbitrary zero and is
 compared only for Wolff."""
+import os
+
 import numpy as np
 import pytest
 
@@ -23,28 +25,21 @@ ON_SLOTS = [0, 1, 2, 6, 8, 9, 10, 20, 22, 23, 25, 26]
 ISING_SLOTS = [0, 2, 8, 9]
 
 
-def _run_gpu(p, precision, tables):
+def _run_gpu(p, precision, tables, info=None):
     from mcsolver_b200 import engine, scan
     spec = spec_of(p["spec"], tuple(p["L"]))
     K = p["K"]
     T = np.full(K, p["T"])
     H = np.full(K, p["H"])
     idx, rows, _ = scan.run_points(spec, p["model"], T, H, p["nthermal"], p["nsweep"], ninterval=p["ninterval"],
-                                   algorithm=p["algo"], precision=precision, seed=2024, tables=tables)
+                                   algorithm=p["algo"], precision=precision, seed=2024, tables=tables, info=info)
     return rows
 
 
-@pytest.mark.parametrize("p", STATS, ids=IDS)
-@pytest.mark.parametrize("path", ["structured-fp32", "tables-fp64"])
-def test_equilibrium_observables_within_3_sigma_of_reference(p, path):
-    if path == "structured-fp32" and p["algo"] == 1:
-        pytest.skip("Wolff runs on the table path")
-    rows = _run_gpu(p, 32 if path == "structured-fp32" else 64, tables=(path != "structured-fp32"))
-    ref = np.array(p["rows"])
-    K = p["K"]
-    slots = ISING_SLOTS if p["model"] == 1 else ON_SLOTS
-    if p["model"] == 1:
-        slots = [0, 2, 8] + ([4, 5] if p["algo"] == 1 else [])
+def _compare(rows, ref, K, model, algo):
+    slots = ISING_SLOTS if model == 1 else ON_SLOTS
+    if model == 1:
+        slots = [0, 2, 8] + ([4, 5] if algo == 1 else [])
     bad = []
     for k in slots:
         g, r = rows[:, k], ref[:, k]
@@ -57,6 +52,46 @@ def test_equilibrium_observables_within_3_sigma_of_reference(p, path):
     # 12 slots x 3 sigma: allow one marginal excursion up to 4.5 sigma before calling it a failure
     hard = [b for b in bad if abs(b[1] - b[2]) > 4.5 * b[3] + 1e-9 + 2e-4 * max(abs(b[1]), abs(b[2]))]
     assert not hard and len(bad) <= 1, bad
+
+
+@pytest.mark.parametrize("p", STATS, ids=IDS)
+@pytest.mark.parametrize("path", ["structured-fp32-offline", "structured-fp32-jit", "tables-fp64"])
+def test_equilibrium_observables_within_3_sigma_of_reference(p, path, monkeypatch):
+    """structured-fp32 runs twice: the offline runtime-table kernels (MCG_JIT=0) and the NVRTC-specialised build of the
+    same source (MCG_JIT=1 - the kernels behind the bench number); Wolff (algo 1) runs its union-find kernels over the
+    structured topology in fp32 there."""
+    structured = path.startswith("structured")
+    info = {}
+    if structured:
+        monkeypatch.setenv("MCG_JIT", "1" if path.endswith("jit") else "0")
+        if p["algo"] == 1 and path.endswith("jit"):
+            pytest.skip("Wolff has no specialised kernels: one structured run covers it")
+    rows = _run_gpu(p, 32 if structured else 64, tables=not structured, info=info)
+    if structured and p["algo"] == 0:
+        assert (info["jit_launches"] > 0) == path.endswith("jit"), info
+    _compare(rows, np.array(p["rows"]), p["K"], p["model"], p["algo"])
+
+
+STATS32 = util.load_json("stats32.json") if os.path.exists(os.path.join(util.GOLDEN, "stats32.json")) else []
+
+
+@pytest.mark.skipif(not STATS32, reason="tests/golden/stats32.json not generated")
+def test_default_path_at_jit_size_within_3_sigma_of_reference():
+    """sc 32^3, three temperatures x 16 seeds = 48 replicas in ONE batch: N*R = 1.57e6 >= 2^20, so the engine's default
+    choice (no MCG_JIT override) is the NVRTC-specialised colour pass mcg_pass_m0/m1 - the kernel of the bench number -
+    and its equilibrium observables are compared with 16 seeded runs of the reference's compiled engine per temperature
+    (tests/golden/stats32.json, make_golden.py stats32; heisenbergLib.c:441-473, 661-831)."""
+    from mcsolver_b200 import scan
+    assert "MCG_JIT" not in os.environ
+    p0 = STATS32[0]
+    K = p0["K"]
+    spec = spec_of(p0["spec"], tuple(p0["L"]))
+    T = np.repeat([p["T"] for p in STATS32], K)
+    info = {}
+    _, rows, _ = scan.run_points(spec, 3, T, np.zeros_like(T), p0["nthermal"], p0["nsweep"], precision=32, seed=31, info=info)
+    assert info["jit_launches"] >= 2 * (p0["nthermal"] + p0["nsweep"]), info      # every colour pass was a specialised launch
+    for i, p in enumerate(STATS32):
+        _compare(rows[i * K:(i + 1) * K], np.array(p["rows"]), K, 3, 0)
 
 
 def test_parallel_tempering_matches_independent_scan():

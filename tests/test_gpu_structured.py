@@ -28,8 +28,17 @@ def _start(o, t, model, seed):
     return o.init_spins_philox(0.8, seed=seed)
 
 
+def _check_jit_ran(s, jit_mode):
+    """MCG_JIT=1 must really have run the specialised kernels wherever the lattice has vector items (V > 1: the grouped
+    Philox layout tells); V == 1 lattices always take the scalar runtime-table kernel."""
+    if jit_mode == "offline":
+        assert s.jit_launch_count() == 0
+    elif s.rng_layout()[1] > 1:
+        assert s.jit_launch_count() > 0, "MCG_JIT=1 but the offline kernel ran"
+
+
 @pytest.mark.parametrize("case", CASES, ids=IDS)
-def test_structured_energy_observables_and_trajectory_fp64(case):
+def test_structured_energy_observables_and_trajectory_fp64(case, jit_mode):
     eng = _eng()
     name, L, T, model, h = case
     spec = spec_of(name, L)
@@ -62,10 +71,11 @@ def test_structured_energy_observables_and_trajectory_fp64(case):
         assert np.max(np.abs(got - r["spins"].reshape(got.shape))) < 1e-9
         att, acc, _ = s.counters()
         assert (att, acc) == (int(r["counters"][0]), int(r["counters"][1]))
+        _check_jit_ran(s, jit_mode)
 
 
 @pytest.mark.parametrize("case", CASES[:11], ids=IDS[:11])
-def test_structured_whole_run_fused_measurement_matches_oracle(case):
+def test_structured_whole_run_fused_measurement_matches_oracle(case, jit_mode):
     """mcg_run on a structured system: the measurement sums come out of the colour passes
     themselves (fused); the result tuple must equal the oracle's restatement of the same loop."""
     eng = _eng()
@@ -80,6 +90,7 @@ def test_structured_whole_run_fused_measurement_matches_oracle(case):
         s.init_spins(0.3)
         fr = s.run(0, 4, 15, 2 * t.N, spinFrame=3)
         out, grp = s.results()
+        _check_jit_ran(s, jit_mode)
     r = o.run(2, 4, 15, 2 * t.N, flunc=0.3, spinFrame=3, order=order, seed=17)
     for k in util.ON_CORE_SLOTS + [7]:
         assert abs(out[k] - r["out"][k]) <= 1e-9 * max(1.0, abs(r["out"][k])), (k, out[k], r["out"][k])

@@ -85,3 +85,39 @@ def test_decide_detailed_balance_limits():
     n = 4000
     f = sum(pt.decide(beta, [0, 0], [0.0, 1.0], [0, 0], [0, 1], 0, 11, s)[1][0] for s in range(n)) / n
     assert abs(f - np.exp(-0.5)) < 4 * np.sqrt(0.6065 * 0.3935 / n)
+
+
+ID_WORKER = r'''
+import os, sys, hashlib
+sys.path.insert(0, os.environ["MCG_ROOT"])
+from mcsolver_b200 import pt
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+cid = pt.comm_id(rank, world)
+assert len(cid) == pt.COMM_ID_BYTES and "torch" not in sys.modules
+open(os.environ["MCG_OUT"] + ".%d" % rank, "w").write(hashlib.sha256(cid).hexdigest())
+'''
+
+
+def test_communicator_id_reaches_every_rank_without_torch(tmp_path):
+    """The NCCL communicator id of the in-library tempering driver: made by rank 0 (ncclGetUniqueId through the C ABI,
+    works without a GPU) and passed over a TCP socket at the launcher's MASTER_ADDR / MASTER_PORT + 29."""
+    from mcsolver_b200 import _ffi
+    import ctypes
+    buf = ctypes.create_string_buffer(128)
+    if _ffi.lib().mcg_comm_unique_id(buf, 128) != 0:
+        import pytest
+        pytest.skip("libnccl not loadable here: " + _ffi.lib().mcg_last_error().decode())
+    script = tmp_path / "idworker.py"
+    script.write_text(ID_WORKER)
+    out = str(tmp_path / "id")
+    port = _free_port()
+    world = 3
+    procs = []
+    for rank in reversed(range(world)):      # clients first: they must retry until rank 0 listens
+        env = dict(os.environ, MCG_ROOT=ROOT, MCG_OUT=out, RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        o, _ = p.communicate(timeout=120)
+        assert p.returncode == 0, o[-2000:]
+    ids = [open(out + ".%d" % r).read() for r in range(world)]
+    assert len(set(ids)) == 1 and len(ids[0]) == 64
