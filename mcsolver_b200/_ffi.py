@@ -14,7 +14,12 @@ _lib = None
 class McgError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("mcsolver_b200 error %d: %s" % (code, msg))
-        self.code = code
+        self.code, self.msg = code, msg
+
+    def __reduce__(self):
+        # must survive pickling: the reference runs MCMainFunction inside multiprocessing.Pool workers (win.py:90-91) and
+        # an exception that cannot be rebuilt in the parent wedges the pool instead of surfacing
+        return (McgError, (self.code, self.msg))
 
 
 class Tables(C.Structure):

@@ -17,6 +17,7 @@ import types
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
 REFERENCE_SRC = "/root/reference/mcsolver"
+HOST_DIR = os.path.join(REF_DIR, "host")          # sourceless bytecode of the reference's host modules (oracle/Makefile: host)
 
 _libc = None
 
@@ -34,7 +35,20 @@ def have_ref_engine():
 
 
 def have_reference_host():
-    return os.path.isfile(os.path.join(REFERENCE_SRC, "Lattice.py"))
+    """The reference's host Python is importable: from /root/reference (build container) or from the compiled copy."""
+    return os.path.isfile(os.path.join(REFERENCE_SRC, "Lattice.py")) or os.path.isfile(os.path.join(HOST_DIR, "Lattice.pyc"))
+
+
+def reference_host_dir():
+    return REFERENCE_SRC if os.path.isfile(os.path.join(REFERENCE_SRC, "Lattice.py")) else HOST_DIR
+
+
+def sample_file(name):
+    """Path of one of the reference's sample parameter files (samples/<name>)."""
+    for d in (os.path.join(os.path.dirname(REFERENCE_SRC), "samples"), os.path.join(HOST_DIR, "samples")):
+        if os.path.isfile(os.path.join(d, name)):
+            return os.path.join(d, name)
+    raise FileNotFoundError(name)
 
 
 def load_ref_engine(name):
@@ -86,8 +100,9 @@ def load_reference_host():
                 importlib.import_module(n)
             except Exception:
                 _stub(n)
-    if REFERENCE_SRC not in sys.path:
-        sys.path.insert(0, REFERENCE_SRC)
+    src = reference_host_dir()
+    if src not in sys.path:
+        sys.path.insert(0, src)
     import Lattice
     import mcMain
     import win

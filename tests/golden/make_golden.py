@@ -2,7 +2,7 @@
 
 Needs /root/reference (host Python, imported with tkinter/matplotlib stubbed) and oracle/_ref
 (the reference C engines compiled by oracle/Makefile; xylib with the 2-line seedID fix).
-Run:  python tests/golden/make_golden.py [tables] [kat] [runs] [stats] [dipole] [u4cross] [stats32]
+Run:  python tests/golden/make_golden.py [tables] [kat] [runs] [stats] [dipole] [u4cross] [stats32] [refhost]
 Writes tests/golden/{tables,kat,runs,stats}.json(+npz).  None of the tests reads
 /root/reference at run time: they read these files.
 
@@ -268,8 +268,66 @@ def make_stats32():
     print("stats32: %d runs in %.0fs" % (len(jobs), time.time() - t0))
 
 
+# ---- the REAL call chain, reference host + reference engines: win.startSimulation(updateGUI=False, rpath=<sample>) ----
+REFHOST_K = 12
+
+
+def _refhost_run(job):
+    """One whole run of the reference (host Python + its compiled engines) on an edited sample file, in a scratch
+    directory; returns the three output files verbatim."""
+    name, seed = job
+    import tempfile
+    from tests.refhost_cases import CASES, edited
+    sys.path.insert(0, rh.REF_DIR)                       # `from xylib import MCMainFunction` -> the reference's C engine
+    for m in ("isinglib", "xylib", "heisenberglib"):
+        sys.modules.pop(m, None)
+    Lattice, mcMain, win, fileio = rh.load_reference_host()
+    d = tempfile.mkdtemp(prefix="refhost_")
+    cwd = os.getcwd()
+    os.chdir(d)
+    try:
+        open("param", "w").write(edited(open(rh.sample_file(name)).read(), **CASES[name]))
+        rh.srand(seed)                                   # forked Pool workers inherit the stream (SURVEY 8 quirks)
+        fd = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(1)
+        os.dup2(fd, 1)
+        try:
+            win.startSimulation(updateGUI=False, rpath="param")
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(fd)
+            os.close(saved)
+        return name, seed, {f: open(f).read() for f in ("result.txt", "out", "spinDotSpin.txt")}
+    finally:
+        os.chdir(cwd)
+
+
+def make_refhost():
+    """Reference-produced golden result.txt / out / spinDotSpin.txt (SURVEY 4 'interface' row; win.py:152-156,
+    mcMain.py:261-265, 274-289): K seeded whole runs per sample for the 3-sigma comparison of every result.txt column,
+    and the files of seed 1 verbatim for the byte-level layout checks."""
+    import multiprocessing as mp
+    from tests.refhost_cases import CASES, parse_result
+    out = {}
+    t0 = time.time()
+    for name in CASES:
+        runs = []
+        for seed in range(1, REFHOST_K + 1):             # one at a time, each in a fresh process: startSimulation brings its own Pool
+            ctx = mp.get_context("fork")
+            rx, tx = ctx.Pipe(duplex=False)
+            pr = ctx.Process(target=lambda: tx.send(_refhost_run((name, seed))))
+            pr.start()
+            runs.append(rx.recv())
+            pr.join()
+        rows = [parse_result(r[2]["result.txt"])[1] for r in runs]
+        out[name] = dict(edits=CASES[name], K=REFHOST_K, rows=rows, files=runs[0][2])
+        print("%s: %d runs (%.0fs)" % (name, len(runs), time.time() - t0), flush=True)
+    json.dump(out, open(os.path.join(HERE, "refhost.json"), "w"))
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["tables", "kat", "runs", "stats", "dipole"]
     assert rh.have_reference_host() and rh.have_ref_engine(), "needs /root/reference and oracle/_ref (make -f oracle/Makefile)"
     for w in what:
-        {"tables": make_tables, "kat": make_kat, "runs": make_runs, "stats": make_stats, "dipole": make_dipole, "u4cross": make_u4cross, "stats32": make_stats32}[w]()
+        {"tables": make_tables, "kat": make_kat, "runs": make_runs, "stats": make_stats, "dipole": make_dipole, "u4cross": make_u4cross, "stats32": make_stats32, "refhost": make_refhost}[w]()

@@ -86,3 +86,12 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(root, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
                 assert "liboracle" not in src and "refharness" not in src, f
+
+
+def test_engine_errors_survive_the_process_pool_of_the_reference_host():
+    """win.py:90-91 runs MCMainFunction inside multiprocessing.Pool workers: an exception raised there travels to the
+    parent by pickle.  One that cannot be rebuilt wedges the pool for ever (observed: a hang instead of MCG_ERR_CUDA)."""
+    import pickle
+    from mcsolver_b200.engine import McgError
+    e = pickle.loads(pickle.dumps(McgError(2, "no usable CUDA device")))
+    assert isinstance(e, McgError) and e.code == 2 and "no usable CUDA device" in str(e)
