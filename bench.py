@@ -3,9 +3,11 @@
 
 Workload (config.workload): 3D Heisenberg, simple cubic 256^3 (N = 16 777 216 spins), J = diag(-1,-1,-1)
 on [100],[010],[001], initial state polarised (S,0,0) as in the reference, temperature scan with 8
-replicas per GPU (the 64-point ladder of BASELINE configs[4] sharded over 8 GPUs; dipole term not in
-this round).  One "step" = SWEEPS colour-class Metropolis sweeps over all replicas of the rank, every
-sweep followed by the reference's per-sweep measurement (fused into the colour passes).
+replicas per GPU (the 64-point ladder of BASELINE configs[4] sharded over 8 GPUs).  One "step" = SWEEPS
+colour-class Metropolis sweeps over all replicas of the rank, every sweep followed by the reference's
+per-sweep measurement (fused into the colour passes).  Beside the headline the same line carries, at every N:
+"configs" (C1-C5 and C5 + dipole at their named sizes, replica-sharded the same way) and "pt" (the C5 ladder with
+the dipole stencil as parallel tempering: ncclAllGather inside the library at every exchange step).
 
   python bench.py --gpus N --steps K --warmup W              # our engine (torchrun for N>1)
   python bench.py --impl reference --gpus N --steps K ...    # the reference's own C engine on host cores
@@ -107,11 +109,25 @@ def run_reference_arm(a, rank, world):
     wall = time.time() - t0
     val = att / eng
     sample = "sc %d^3 Heisenberg, %d temperature points (1 process each), %d+%d sweeps per point per step, engine-call time only" % (L, cores, nth, nsw)
+    # second sample at the largest size a reference process builds and runs inside a minute: the rate hardly depends on the
+    # lattice once it leaves the cache (the engine chases pointers through 264-byte structs either way)
+    big = None
+    try:
+        xb, eb, _ = reference_step(cores, a.ref_L2, 1, 6)
+        big = {"value": xb / eb, "unit": "attempts/s", "sample": "sc %d^3, %d points x (1+6) sweeps, engine-call time %.1f s" % (a.ref_L2, cores, eb)}
+    except Exception as e:      # memory-starved host: the headline sample stands alone
+        big = {"error": str(e)[:200]}
+    cfg = workload_config(a, world)
+    # the metric (a rate) is the one of the GPU arm's workload; the reference cannot BUILD that workload (Python object graph:
+    # 80 us + 3.3 kB per orbital), so the lattice it actually runs is named here
+    cfg["reference_arm_runs"] = {"lattice": "simple cubic %d^3" % L, "spins": L ** 3, "points": cores, "sweeps_per_point_per_step": nth + nsw,
+                                 "precision": "fp64 (the reference has no other)", "inputs": "mcsolver_b200.lattice.build_tables == the reference's own "
+                                 "flattening (tests/golden/tables.json); engine-call time only, Python graph build excluded"}
     line = {"impl": "reference", "metric": "attempted Metropolis spin updates per second", "value": val, "unit": "attempts/s",
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * eng / max(1, a.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(a, world), "gpu_launches": 0,
-            "cpu_baseline": {"value": val, "unit": "attempts/s", "cores": cores, "kind": ref_kind(), "sample": sample},
+            "config": cfg, "gpu_launches": 0,
+            "cpu_baseline": {"value": val, "unit": "attempts/s", "cores": cores, "kind": ref_kind(), "sample": sample, "larger_sample": big},
             "e2e": {"value": val, "unit": "attempts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": wall}
     print(json.dumps(line), flush=True)
@@ -123,7 +139,7 @@ def workload_config(a, world):
             "sweeps_per_step": a.sweeps, "measurement": "every sweep (fused M,E; reference definitions)",
             "state": "fp32 SoA planes, 12 B/spin", "parallelism": "replica-sharded x%d (no data-path collective)" % world,
             "l2": "inputs larger than L2: %.0f MB of spin state per colour pass" % (a.replicas * a.L ** 3 * 12 / 1e6),
-            "dipole": "not included (SURVEY 8 f2)"}
+            "dipole": "not in the headline workload; the 'configs' and 'pt' legs of this line run C5 with the dipole stencil"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -199,6 +215,108 @@ def wolff_metric(device, L=4096, steps=100):
             "algorithm": "bond activation + atomicCAS union-find over the whole lattice, seed's cluster reflected"}
 
 
+# ---------------------------------------------------------------------------------------------
+# every BASELINE.json config at its named size (north_star: "reported at 1, 2, 4 and 8 GPUs"), replica-sharded like the
+# headline: each rank runs `R` points of the config's scan, device-timed sweeps with every sweep measured, max over ranks
+# ---------------------------------------------------------------------------------------------
+def square_spec(L):
+    from mcsolver_b200.lattice import LatticeSpec
+    return LatticeSpec(L=(L, L, 1), S=[1.0], bonds=[(0, 0, (1, 0, 0), J_ISO), (0, 0, (0, 1, 0), J_ISO)])
+
+
+def config_table():
+    """name -> (spec factory, model, precision, replicas per GPU, T(n), H(n), coordination z, sweeps timed)"""
+    from tests.specs import spec_of
+    from mcsolver_b200.lattice import add_dipole_stencil
+    lin = lambda a, b: (lambda n: np.linspace(a, b, n))
+    zero = lambda n: np.zeros(n)
+    return [
+        ("C1 XY square 4096^2 T-scan", lambda: square_spec(4096), 2, 32, 8, lin(0.9, 1.2), zero, 4, 20),
+        ("C2 Ising square 4096^2 T-scan", lambda: square_spec(4096), 1, 32, 16, lin(2.0, 2.6), zero, 4, 20),
+        ("C3 CrI3 honeycomb 512^2 x 2 (1NN+2NN+3NN, D)", lambda: spec_of("cri3", (512, 512, 1)), 3, 32, 21, lin(30, 50), zero, 12, 40),
+        ("C4 skyrmion hex 1024^2 x 2 (DMI, D, h; Q every sweep)", lambda: spec_of("skyrmion", (1024, 1024, 1)), 3, 32, 16, lambda n: np.full(n, 0.3), lin(0, 0.7), 3, 40),
+        ("C5 Heisenberg sc 256^3 T-scan, fp64 state", lambda: cubic_spec(256), 3, 64, 8, ladder, zero, 6, 10),
+        ("C5 + dipole stencil r<=2 (32 full-tensor links) sc 256^3", lambda: add_dipole_stencil(cubic_spec(256), 0.1, 2.0), 3, 32, 8, ladder, zero, 32, 8),
+    ]
+
+
+def config_legs(rank, world, local, barrier_max, peak, only=None):
+    from mcsolver_b200 import engine
+    rows = []
+    for name, mk, model, prec, R, Tf, Hf, z, nsw in config_table():
+        if only and not any(name.startswith(o) for o in only):
+            continue
+        try:
+            spec = mk()
+            T, H = Tf(R * world)[rank * R:(rank + 1) * R], Hf(R * world)[rank * R:(rank + 1) * R]
+            with engine.System.from_spec(spec, model, precision=prec, nReplica=R, beta=1 / np.asarray(T, float), field=H, seed=1,
+                                         replica_offset=rank * R, device=local) as s:
+                C = s.num_colours()
+                s.init_spins(0.0)
+                s.timed_sweeps(3, with_measure=True)
+                barrier_max(0.0)
+                ms = s.timed_sweeps(nsw, with_measure=True)
+                jit = s.jit_launch_count() > 0
+            t = barrier_max(ms / 1e3)
+            att = world * R * spec.nsite * nsw / t
+            w = (prec // 8) * model
+            balg = (2 + min(C - 1, z)) * w
+            rows.append({"config": name, "spins": spec.nsite, "replicas_per_gpu": R, "colours": C, "state": "fp%d" % prec, "sweeps_timed": nsw,
+                         "attempts_per_s": att, "bytes_per_attempt": balg, "roofline_frac_per_gpu": att / world * balg / (peak * 1e9),
+                         "specialised_kernels": jit})
+        except Exception as e:        # one config must not take the contract line down
+            rows.append({"config": name, "error": str(e)[:300]})
+    return rows
+
+
+def pt_leg(rank, world, local, barrier_max, peak, L=256, R=8, sweeps=40, sps=5):
+    """BASELINE configs[4] as named: sc 256^3 Heisenberg + dipole stencil, a ladder of 8 labels per GPU (64 on 8 GPUs), an
+    exchange step every `sps` sweeps.  The whole loop runs inside the library (mcg_pt_run): per exchange step one
+    ncclAllGather of 3 doubles per replica on the compute stream, then a decide-and-relabel kernel; no host round trip."""
+    from mcsolver_b200 import pt
+    from mcsolver_b200.lattice import add_dipole_stencil
+    out = {}
+    spec = add_dipole_stencil(cubic_spec(L), 0.1, 2.0)
+    n = R * world
+    p = pt.ParallelTempering(spec, 3, ladder(n), precision=32, seed=3, rank=rank, world=world, device=local)
+    try:
+        p.sys.timed_sweeps(2, with_measure=True)
+        p.run(0, sps, sweeps_per_swap=sps, want_results=False)            # first NCCL call (connection set-up) stays untimed
+        barrier_max(0.0)
+        t_plain = barrier_max(p.sys.timed_sweeps(sweeps, with_measure=True) / 1e3)
+        barrier_max(0.0)
+        p.run(0, sweeps, sweeps_per_swap=sps, want_results=False)
+        t_swap = barrier_max(p.device_ms / 1e3)
+        att = n * spec.nsite * sweeps
+        C = p.sys.num_colours()
+        balg = (2 + min(C - 1, 32)) * 12
+        out = {"workload": "heisenberg_sc_%d^3 + dipole stencil r<=2 (32 links), %d-label ladder (%d per GPU), exchange every %d sweeps" % (L, n, R, sps),
+               "value": att / t_swap, "unit": "attempts/s", "no_swap_value": att / t_plain, "swap_cost_frac": t_swap / t_plain - 1.0,
+               "exchange_steps_timed": sweeps // sps, "bytes_per_attempt": balg, "roofline_frac_per_gpu": att / world / t_swap * balg / (peak * 1e9),
+               "collective": "ncclAllGather of 3 doubles per replica inside libmcsolver_b200 (dlopen'ed libnccl, no PyTorch), world=%d" % world,
+               "swap_rates_at_this_size": [round(float(x), 3) for x in p.swap_rates()]}
+    finally:
+        p.close()
+    # a ladder that does exchange: same machinery at 64^3 (nearest-neighbour exchange only), temperatures 0.25 % apart around Tc
+    spec = cubic_spec(64)
+    T = TC * (1.0 + 0.0025 * (np.arange(n) - n / 2))
+    p = pt.ParallelTempering(spec, 3, T, precision=32, seed=3, rank=rank, world=world, device=local)
+    try:
+        p.run(200, 10, sweeps_per_swap=2, want_results=False)
+        barrier_max(0.0)
+        p.run(0, 400, sweeps_per_swap=2, want_results=False)
+        t = barrier_max(p.device_ms / 1e3)
+        rows = p.results()
+        rates = p.swap_rates()
+        out["swapping_ladder"] = {"workload": "heisenberg_sc_64^3, %d labels, dT/T = 0.25 %% around Tc, exchange every 2 sweeps" % n,
+                                  "attempts_per_s": n * spec.nsite * 400 / t, "swap_rate_mean": float(rates.mean()), "swap_rate_min": float(rates.min()),
+                                  "swap_rate_max": float(rates.max()), "labels_displaced": int(np.sum(p.holders() != np.arange(n))),
+                                  "e_over_kT_first_last": [float(rows[0, 8]), float(rows[-1, 8])]}
+    finally:
+        p.close()
+    return out
+
+
 def fp64_state_metric(device, spec, Ts, sweeps, peak):
     """The same workload with fp64 spin state (the shims' default precision; 24 B/spin, 72 B per attempt): device-timed
     sweeps with every sweep measured, outside the timed region of the headline number.  Informational."""
@@ -226,6 +344,9 @@ def main():
     ap.add_argument("--sweeps", type=int, default=100, help="Metropolis sweeps (each measured) per step")
     ap.add_argument("--ref-L", type=int, default=32)
     ap.add_argument("--ref-sweeps", type=int, default=60)
+    ap.add_argument("--ref-L2", type=int, default=48, help="second, larger CPU sample of the reference arm")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config legs (C1-C5 at their named sizes)")
+    ap.add_argument("--no-pt", action="store_true", help="skip the parallel-tempering leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-wolff", action="store_true")
     a = ap.parse_args()
@@ -273,6 +394,7 @@ def main():
         s.timed_sweeps(a.sweeps, with_measure=True)
     s.reset_measurements()
     s.profile_passes(True)
+    module_key = s.jit_module_key(1) if s.jit_launch_count() > 0 else None     # identity of the kernel the roofline line is about
     l0 = s.launch_count()
     clocks = ClockSampler(local)
     clocks.start()
@@ -300,14 +422,22 @@ def main():
     avg_launch_s = pass_ms / 1e3 / max(1, npass)
     achieved = attempts_per_launch * b_alg / avg_launch_s / 1e9
     peak, peak_src = measured_peak()
-    traffic = None
+    # DRAM traffic per launch comes from an ncu capture of EXACTLY this module (profiles/traffic.json is keyed by the module
+    # key = the hash of the generated lattice prologue and the kernel headers); any other build of the kernel gets null
+    traffic, traffic_note = None, "no ncu capture on record"
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        tj = json.load(open(tp))
+        if module_key is not None and tj.get("module_key") == module_key:
+            traffic, traffic_note = tj.get("dram_bytes_per_launch"), tj.get("source")
+        else:
+            traffic_note = "profiles/traffic.json was captured for module %s, this run launched %s" % (tj.get("module_key"), module_key)
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "kernel": "mcg_pass_m1 = pass_body<NC=3,float,diagJ,MODE=1 (update + fused measurement),V=4>, NVRTC-specialised for the lattice (struct_pass.cuh)", "bytes_per_attempt": b_alg,
             "attempts_per_launch": attempts_per_launch, "avg_launch_ms": avg_launch_s * 1e3, "launches_timed": npass,
-            "kernel_share_of_step": pass_ms / dev_ms, "peak_source": peak_src}
+            "kernel_share_of_step": pass_ms / dev_ms, "peak_source": peak_src,
+            "module_key": module_key, "traffic_source": traffic_note,
+            "algorithmic_bytes_per_launch": attempts_per_launch * b_alg}
 
     # ---- e2e: whole jobs through the public API, host descriptors in, host result rows out
     e2e_steps = max(1, min(a.steps, 5))
@@ -336,12 +466,21 @@ def main():
     if rank == 0 and world == 1 and not a.no_wolff:
         f64 = fp64_state_metric(local, spec, Ts, 20, measured_peak()[0])
 
+    # ---- every BASELINE config at its named size and the parallel-tempering ladder (C5 as named), at every N
+    configs = None if a.no_configs else config_legs(rank, world, local, barrier_max, peak)
+    ptres = None
+    if not a.no_pt:
+        try:
+            ptres = pt_leg(rank, world, local, barrier_max, peak)
+        except Exception as e:
+            ptres = {"error": str(e)[:300]}
+
     if rank == 0:
         line = {"metric": "attempted Metropolis spin updates per second", "value": value, "unit": "attempts/s", "n_gpus": world,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_max / a.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(a, world), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roof, "cpu_baseline": cpu, "wolff": wolff, "fp64_state": f64, "host_wall_s": wall,
+                "roofline": roof, "cpu_baseline": cpu, "wolff": wolff, "fp64_state": f64, "configs": configs, "pt": ptres, "host_wall_s": wall,
                 "check": {"replica0_T": float(Ts[0]), "e_per_site_over_kT": float(out0[8]), "U4": float(out0[10])}}
         print(json.dumps(line), flush=True)
     if dist is not None:

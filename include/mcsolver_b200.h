@@ -173,6 +173,9 @@ MCG_API int mcg_counters(mcg_system *sys, int replica, int64_t *attempts, int64_
  * test prove which build of the colour pass it exercised. */
 MCG_API int mcg_launch_count(mcg_system *sys, int64_t *launches);
 MCG_API int mcg_jit_launch_count(mcg_system *sys, int64_t *launches);
+/* identity of the specialised module of one colour (hash of the generated lattice prologue and the kernel headers = the file
+ * name of its cubin in the cache): measurements taken under a profiler are keyed by it (profiles/traffic.json) */
+MCG_API int mcg_jit_module_key(mcg_system *sys, int colour, uint64_t *key);
 MCG_API int mcg_profile_passes(mcg_system *sys, int on);
 MCG_API int mcg_profile_read(mcg_system *sys, double *total_ms, int64_t *nlaunches);
 

@@ -73,6 +73,7 @@ SIGNATURES = {
     "mcg_counters": (_i, [_vp, _i, _vp, _vp, _vp]),
     "mcg_launch_count": (_i, [_vp, _vp]),
     "mcg_jit_launch_count": (_i, [_vp, _vp]),
+    "mcg_jit_module_key": (_i, [_vp, _i, _vp]),
     "mcg_profile_passes": (_i, [_vp, _i]),
     "mcg_profile_read": (_i, [_vp, _vp, _vp]),
     "mcg_run": (_i, [_vp, _i, _i64, _i64, _i64, _i, _vp]),

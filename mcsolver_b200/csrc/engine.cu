@@ -917,6 +917,9 @@ MCG_API int mcg_launch_count(mcg_system *sys, int64_t *launches) {
 MCG_API int mcg_jit_launch_count(mcg_system *sys, int64_t *launches) {
     return guarded([&] { MCG_REQUIRE(sys && launches, "NULL argument"); *launches = (int64_t)sys->jitLaunches; });
 }
+MCG_API int mcg_jit_module_key(mcg_system *sys, int colour, uint64_t *key) {
+    return guarded([&] { MCG_REQUIRE(sys && key, "NULL argument"); *key = structured_jit_key(sys, colour); });
+}
 MCG_API int mcg_profile_passes(mcg_system *sys, int on) {
     return guarded([&] { MCG_REQUIRE(sys, "system is NULL"); sys->profilePasses = on != 0; });
 }

@@ -820,14 +820,23 @@ static std::string read_file(const std::string &path) {
     }
     return out;
 }
+// identity of a specialised module: generated prologue + the kernel headers it includes
+static uint64_t cache_key(const std::string &src) {
+    uint64_t h = fnv1a(src);
+    for (const char *f : {"/struct_pass.cuh", "/topo_pass.cuh", "/devmath.cuh", "/rng.cuh"}) h = fnv1a(read_file(csrc_dir() + f), h);
+    return h;
+}
+uint64_t structured_jit_key(const mcg_system *s, int colour) {
+    if (!s->structured || colour < 0 || colour >= s->C) throw Error(MCG_ERR_ARG, "not a structured system / colour out of range");
+    return cache_key(jit_prologue(s, colour, false));
+}
 static std::string cache_path(const std::string &src) {
     const char *dir = getenv("MCG_CACHE_DIR");
     std::string d;
     if (dir && dir[0]) d = dir;
     else d = csrc_dir() + "/../build/jitcache";
     if (getenv("MCG_NO_DISK_CACHE")) return "";
-    uint64_t h = fnv1a(src);
-    for (const char *f : {"/struct_pass.cuh", "/topo_pass.cuh", "/devmath.cuh", "/rng.cuh"}) h = fnv1a(read_file(csrc_dir() + f), h);
+    uint64_t h = cache_key(src);
     std::string mk = "mkdir -p '" + d + "' 2>/dev/null";
     if (system(mk.c_str()) != 0) return "";
     char name[64];

@@ -243,6 +243,12 @@ class System:
         check(_ffi.lib().mcg_jit_launch_count(self._h, C.byref(n)))
         return n.value
 
+    def jit_module_key(self, colour=0):
+        """'%016x' cache key of the colour's NVRTC-specialised module (name of its cubin file)."""
+        k = C.c_uint64(0)
+        check(_ffi.lib().mcg_jit_module_key(self._h, int(colour), C.byref(k)))
+        return "%016x" % k.value
+
     def profile_passes(self, on=True):
         check(_ffi.lib().mcg_profile_passes(self._h, int(bool(on))))
 
