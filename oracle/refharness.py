@@ -36,11 +36,24 @@ def have_ref_engine():
 
 def have_reference_host():
     """The reference's host Python is importable: from /root/reference (build container) or from the compiled copy."""
-    return os.path.isfile(os.path.join(REFERENCE_SRC, "Lattice.py")) or os.path.isfile(os.path.join(HOST_DIR, "Lattice.pyc"))
+    return os.path.isfile(os.path.join(REFERENCE_SRC, "Lattice.py")) or os.path.isfile(os.path.join(HOST_DIR, "Lattice.mcb"))
 
 
 def reference_host_dir():
     return REFERENCE_SRC if os.path.isfile(os.path.join(REFERENCE_SRC, "Lattice.py")) else HOST_DIR
+
+
+class _HostFinder:
+    """Imports the staged host modules (oracle/_ref/host/<name>.mcb = sourceless bytecode) under their script-mode names."""
+
+    @staticmethod
+    def find_spec(name, path=None, target=None):
+        import importlib.machinery
+        import importlib.util
+        f = os.path.join(HOST_DIR, name + ".mcb")
+        if "." in name or not os.path.isfile(f):
+            return None
+        return importlib.util.spec_from_loader(name, importlib.machinery.SourcelessFileLoader(name, f))
 
 
 def sample_file(name):
@@ -101,7 +114,10 @@ def load_reference_host():
             except Exception:
                 _stub(n)
     src = reference_host_dir()
-    if src not in sys.path:
+    if src == HOST_DIR:
+        if not any(f is _HostFinder for f in sys.meta_path):
+            sys.meta_path.append(_HostFinder)      # after the path finders: real modules of the same name win
+    elif src not in sys.path:
         sys.path.insert(0, src)
     import Lattice
     import mcMain
