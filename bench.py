@@ -232,7 +232,8 @@ def config_table():
     zero = lambda n: np.zeros(n)
     return [
         ("C1 XY square 4096^2 T-scan", lambda: square_spec(4096), 2, 32, 8, lin(0.9, 1.2), zero, 4, 20),
-        ("C2 Ising square 4096^2 T-scan", lambda: square_spec(4096), 1, 32, 16, lin(2.0, 2.6), zero, 4, 20),
+        ("C2 Ising square 4096^2 T-scan, int8 state", lambda: square_spec(4096), 1, 8, 16, lin(2.0, 2.6), zero, 4, 20),
+        ("C2 Ising square 4096^2 T-scan, fp32 state", lambda: square_spec(4096), 1, 32, 16, lin(2.0, 2.6), zero, 4, 20),
         ("C3 CrI3 honeycomb 512^2 x 2 (1NN+2NN+3NN, D)", lambda: spec_of("cri3", (512, 512, 1)), 3, 32, 21, lin(30, 50), zero, 12, 40),
         ("C4 skyrmion hex 1024^2 x 2 (DMI, D, h; Q every sweep)", lambda: spec_of("skyrmion", (1024, 1024, 1)), 3, 32, 16, lambda n: np.full(n, 0.3), lin(0, 0.7), 3, 40),
         ("C5 Heisenberg sc 256^3 T-scan, fp64 state", lambda: cubic_spec(256), 3, 64, 8, ladder, zero, 6, 10),
@@ -261,7 +262,7 @@ def config_legs(rank, world, local, barrier_max, peak, only=None):
             att = world * R * spec.nsite * nsw / t
             w = (prec // 8) * model
             balg = (2 + min(C - 1, z)) * w
-            rows.append({"config": name, "spins": spec.nsite, "replicas_per_gpu": R, "colours": C, "state": "fp%d" % prec, "sweeps_timed": nsw,
+            rows.append({"config": name, "spins": spec.nsite, "replicas_per_gpu": R, "colours": C, "state": "int8" if prec == 8 else "fp%d" % prec, "sweeps_timed": nsw,
                          "attempts_per_s": att, "bytes_per_attempt": balg, "roofline_frac_per_gpu": att / world * balg / (peak * 1e9),
                          "specialised_kernels": jit})
         except Exception as e:        # one config must not take the contract line down

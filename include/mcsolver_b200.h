@@ -107,7 +107,9 @@ typedef struct {
 } mcg_lattice_desc;
 
 typedef struct {
-    int32_t precision;        /* 32: fp32 spin state and arithmetic; 64: fp64 (parity level 1) */
+    int32_t precision;        /* 32: fp32 spin state and arithmetic; 64: fp64 (parity level 1);
+                                 8 (mcg_create_lattice, Ising, one exchange constant and one |S|): spins as int8, 1 byte per spin,
+                                 acceptance by integer thresholds of the fp64 probabilities - same decisions as precision 64 */
     int32_t nReplica;         /* independent (T,H) points / PT replicas resident on this GPU */
     const double *beta;       /* [nReplica] multiplies J and D;  NULL = 1.0 (tables pre-scaled) */
     const double *field;      /* [nReplica] h (units of the table energies; multiplied by beta) */

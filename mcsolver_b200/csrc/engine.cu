@@ -772,7 +772,7 @@ MCG_API int mcg_create_lattice(const mcg_lattice_desc *d, const mcg_config *cfg,
     return guarded([&] {
         MCG_REQUIRE(out, "out is NULL");
         MCG_REQUIRE(d && cfg, "descriptor/config is NULL");
-        MCG_REQUIRE(cfg->precision == 32 || cfg->precision == 64, "precision must be 32 or 64");
+        MCG_REQUIRE(cfg->precision == 32 || cfg->precision == 64 || cfg->precision == 8, "precision must be 64, 32 or (Ising lattices) 8");
         MCG_REQUIRE(cfg->nReplica >= 1, "nReplica must be >= 1");
         std::unique_ptr<mcg_system> sys(new mcg_system());
         select_device(cfg, sys.get());
@@ -793,7 +793,7 @@ MCG_API int mcg_create_lattice(const mcg_lattice_desc *d, const mcg_config *cfg,
 MCG_API int mcg_jit_check(const mcg_lattice_desc *d, int precision, int *ncompiled, char *report, int report_len) {
     return guarded([&] {
         MCG_REQUIRE(d && ncompiled, "NULL argument");
-        MCG_REQUIRE(precision == 32 || precision == 64, "precision must be 32 or 64");
+        MCG_REQUIRE(precision == 32 || precision == 64 || precision == 8, "precision must be 64, 32 or 8");
         std::string rep;
         *ncompiled = structured_jit_check(d, precision, rep);
         if (report && report_len > 0) { std::strncpy(report, rep.c_str(), report_len - 1); report[report_len - 1] = 0; }

@@ -84,18 +84,23 @@ struct IsingWords {
 // from shared blocks instead: group index G = (id / (V*S))*S + id % S is the first counter word, member m = (id / S) % V,
 // the t-th word of member m is word k = W*m + t of the group (W = words per attempt = number of spin components), i.e.
 // word k & 3 of the block drawn with sub-stream k >> 2.  V = 4: 3 Philox calls per item instead of 4 (O(3)), 2 (O(2)),
-// 1 (Ising).  The attempt-probability uniform of partial sweeps is word m of the block with sub-stream 7.
+// 1 (Ising).  The attempt-probability uniform of partial sweeps is word m & 3 of the block with sub-stream 7 + (m >> 2)
+// (items of more than four sites: the int8 Ising pass, V = 16, W = 1 - its acceptance words use sub-streams 0..3).
 // Still a pure function of (site id, S, V) - the oracle restates it (oracle.c: grouped_words).
 template <int W, int V> struct ItemWords {
     static constexpr int NCALL = (W * V + 3) / 4;
+    static constexpr int NPART = (V + 3) / 4;
     uint32_t c[NCALL][4];
-    uint32_t p[4];
+    uint32_t p[NPART][4];
     uint32_t G;
     int have;   // blocks drawn so far (a compile-time constant after unrolling)
     __host__ __device__ __forceinline__ void begin(const RngKey &key, uint32_t replica, uint64_t sweep, uint32_t id0, uint32_t S, bool partial) {
         G = (id0 / (V * S)) * S + id0 % S;
         have = 0;
-        if (partial) rng4(key, replica, STREAM_METRO, 7u, sweep, G, p);
+        if (partial) {
+#pragma unroll
+            for (int i = 0; i < NPART; i++) rng4(key, replica, STREAM_METRO, 7u + (uint32_t)i, sweep, G, p[i]);
+        }
     }
     // draw the blocks that hold the words of members [0, mEnd): called right before those members are processed, so that
     // at most the words of the members in flight are live (drawing all blocks up front spills the 64-register pass kernel)
@@ -113,7 +118,7 @@ template <int W, int V> struct ItemWords {
         if (W == 3) { w[0] = word(m, 0); w[1] = word(m, 1); w[2] = word(m, 2); }
         else if (W == 2) { w[0] = word(m, 0); w[1] = 0u; w[2] = word(m, 1); }
         else { w[0] = 0u; w[1] = 0u; w[2] = word(m, 0); }
-        w[3] = partial ? p[m] : 0u;
+        w[3] = partial ? p[m >> 2][m & 3] : 0u;
     }
 };
 

@@ -23,6 +23,7 @@
 
 #include "structured.hpp"
 #include "struct_pass.cuh"
+#include "ising8.cuh"
 #include "topo_pass.cuh"
 #include "jit.hpp"
 #include "kernels_wolff.cuh"
@@ -53,6 +54,7 @@ struct StructuredSystem {
     std::vector<double> JHost;           // [nclass][MAXLINK][JW]
     std::vector<char> fastOK;            // per colour: pass table fits the __grid_constant__ fast path
     std::vector<std::vector<char>> passTables;   // per colour: PassTable<real> bytes
+    std::vector<I8Table> i8Tables;       // per colour: link tables of the int8 Ising pass (precision 8)
     std::vector<void *> jitResolved;     // [colour*2 + partial] -> JitPass* once looked up (nullptr = not yet)
     void *jitTopo = nullptr;             // JitPass* of the specialised topological-charge kernel, once looked up
     SClassD *d_classes = nullptr;
@@ -677,6 +679,34 @@ __global__ void __launch_bounds__(256) k_struct_frame(StructArgs a, int r, doubl
 }
 
 
+// ---- int8 Ising planes (precision 8, ising8.cuh): initial state, frame gather / scatter, pair correlation ----
+static __global__ void __launch_bounds__(256) k_i8_init(StructArgs a) {
+    const int r = blockIdx.y, p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.N) return;
+    ((signed char *)a.spin)[(size_t)r * a.N + p] = a.classes[p / a.ncellc].S < 0 ? -1 : 1;   // initSpin carries the signed S (isingLib.c:23-40)
+}
+template <bool GATHER> static __global__ void __launch_bounds__(256) k_i8_frame(StructArgs a, int r, double *buf) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.N) return;
+    signed char *sp = (signed char *)a.spin + (size_t)r * a.N;
+    const size_t i = (size_t)struct_site_id(a, p);
+    if (GATHER) buf[i] = (double)sp[p] * fabs(a.classes[p / a.ncellc].S);
+    else sp[p] = buf[i] < 0 ? -1 : 1;
+}
+static __global__ void __launch_bounds__(256) k_i8_pairs(StructArgs a, int ps, int pt, int d0, int d1, int d2, double *sums) {
+    __shared__ double smem[32];
+    const int r = blockIdx.y, cell = blockIdx.x * blockDim.x + threadIdx.x;
+    double v[1] = {0.0};
+    if (cell < a.Lx * a.Ly * a.Lz) {
+        const int z = cell % a.Lz, y = (cell / a.Lz) % a.Ly, x = cell / (a.Lz * a.Ly);
+        const int pi = struct_pos(a, x, y, z, ps);
+        const int pj = struct_pos(a, (x + d0 + a.Lx) % a.Lx, (y + d1 + a.Ly) % a.Ly, (z + d2 + a.Lz) % a.Lz, pt);
+        const signed char *sp = (const signed char *)a.spin + (size_t)r * a.N;
+        v[0] = (double)(sp[pi] * sp[pj]) * fabs(a.classes[pi / a.ncellc].S) * fabs(a.classes[pj / a.ncellc].S);
+    }
+    block_accumulate<1>(v, sums + (size_t)r * NSUM + SUM_SIJ, smem);
+}
+
 // ---------------------------------------------------------------------------------------------
 // JIT: generate the prologue (lattice as literals), compile struct_pass.cuh with NVRTC for sm_100a,
 // load the cubin through the driver API.  libnvrtc / libcuda are dlopen'ed lazily so that the
@@ -885,6 +915,7 @@ std::vector<char> jit_compile_cubin(const std::string &src, std::string &log) {
 }
 
 static bool jit_enabled(const mcg_system *s) {
+    if (s->prec == 8) return false;   // the int8 Ising pass is an offline kernel
     const char *e = getenv("MCG_JIT");
     if (e && e[0] == '0') return false;
     if (e && e[0] == '1') return true;
@@ -1158,6 +1189,11 @@ static void structured_build_host(mcg_system *s, const mcg_lattice_desc *d, std:
     st->nrows = st->Xd * st->Yd;
     int Vmax = s->prec == 32 ? 4 : 2;
     st->V = (st->Zd % Vmax == 0) ? Vmax : 1;
+    if (s->prec == 8) {   // int8 Ising items: 16 sites (one 16-byte load) or 4 (one word)
+        MCG_REQUIRE(d->model == 1, "precision 8 (int8 spins) is for the Ising model");
+        MCG_REQUIRE(st->Zd % 4 == 0, "precision 8 needs the innermost coarse dimension to be a multiple of 4: use precision 32");
+        st->V = st->Zd % 16 == 0 ? 16 : 4;
+    }
 
     // classes sorted by colour (stable), classOf = inverse
     std::vector<int> order(bestN);
@@ -1285,8 +1321,35 @@ static void structured_build_host(mcg_system *s, const mcg_lattice_desc *d, std:
         st->passTables[colour] = buf;
         st->fastOK[colour] = (char)G;
     };
-    for (int c = 0; c < bestC; c++) {
+    for (int c = 0; c < bestC && s->prec != 8; c++) {
         if (s->prec == 32) build_pass(float(0), c); else build_pass(double(0), c);
+    }
+    if (s->prec == 8) {
+        // ising8.cuh: one exchange constant and one |S| for the whole lattice, every bond image within one row / one cell
+        const char *why = "precision 8 (int8 Ising spins) needs ONE exchange constant, one |S|, no self-images and bonds within the "
+                          "neighbouring coarse cells: use precision 32 for this lattice";
+        MCG_REQUIRE(!st->hasSelf && d->block_spin == 0, d->block_spin ? "block_spin statistics are not available at precision 8" : why);
+        const double J0 = Jt.empty() ? 0.0 : Jt[0], S0 = std::fabs(st->classes[0].S);
+        st->i8Tables.assign(bestC, I8Table());
+        for (int c = 0; c < bestC; c++) {
+            I8Table &T = st->i8Tables[c];
+            const int q0 = st->colourClassStart[c], nqc = st->colourClassStart[c + 1] - q0;
+            MCG_REQUIRE(nqc >= 1 && nqc <= PT_MAXC, why);
+            T.nqc = nqc; T.JS2 = J0 * S0 * S0; T.S = S0;
+            for (int j = 0; j < nqc; j++) {
+                const SClassD &cl = st->classes[q0 + j];
+                I8Class &C = T.c[j];
+                MCG_REQUIRE(std::fabs(cl.S) == S0 && cl.nlink >= 1 && cl.nlink <= I8_MAXZ, why);
+                C.nl = cl.nlink; C.nlow = cl.pad; C.lowmode = cl.lowmode; C.ca = cl.a; C.cb = cl.b; C.cc = cl.c; C.co = cl.o;
+                for (int k = 0; k < cl.nlink; k++) {
+                    const size_t li = (size_t)(q0 + j) * MAXLINK + k;
+                    const int cx = st->cXs[li], cy = st->cYs[li], cz = links[li].cZ;
+                    MCG_REQUIRE(Jt[li] == J0 && cx >= -1 && cx <= 1 && cy >= -1 && cy <= 1 && cz >= -1 && cz <= 1, why);
+                    C.delta[k] = (links[li].qn - (q0 + j)) * st->ncellc + (cx * st->Yd + cy) * st->Zd;
+                    C.wx[k] = (signed char)cx; C.wy[k] = (signed char)cy; C.cz[k] = (signed char)cz;
+                }
+            }
+        }
     }
     // orbital groups
     s->nG = (d->model != 1 && d->ngroup > 0) ? d->ngroup : 0;
@@ -1495,7 +1558,7 @@ int structured_jit_check(const mcg_lattice_desc *d, int precision, std::string &
     std::ostringstream o;
     o << "colours=" << tmp.C << " classes=" << tmp.st->nclass << " period=" << tmp.st->p[0] << "x" << tmp.st->p[1] << "x" << tmp.st->p[2]
       << " V=" << tmp.st->V << "\n";
-    for (int c = 0; c < tmp.C; c++) {
+    for (int c = 0; c < tmp.C && precision != 8; c++) {
         if (!tmp.st->fastOK[c] || tmp.st->V == 1 || !jit_worthwhile(&tmp, c)) { o << "colour " << c << ": not eligible for specialisation\n"; continue; }
         std::string log;
         std::vector<char> cubin = jit_compile_cubin(jit_prologue(&tmp, c, false), log);
@@ -1538,7 +1601,8 @@ void structured_init_spins(mcg_system *s, double flunc) {
     StructArgs a = struct_args(s);
     dim3 g((s->N + 255) / 256, s->R);
     s->launches++;
-    sdispatch(s, [&]<int NC, typename real, bool FJ>() { k_struct_init<NC, real><<<g, 256, 0, s->stream>>>(a, flunc); });
+    if (s->prec == 8) k_i8_init<<<g, 256, 0, s->stream>>>(a);
+    else sdispatch(s, [&]<int NC, typename real, bool FJ>() { k_struct_init<NC, real><<<g, 256, 0, s->stream>>>(a, flunc); });
     MCG_CUDA(cudaGetLastError());
 }
 
@@ -1553,7 +1617,8 @@ void structured_set_spins(mcg_system *s, int r, const double *spins) {
     size_t n = (size_t)s->N * (s->NC == 1 ? 1 : 3);
     MCG_CUDA(cudaMemcpyAsync(buf, spins, n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
     s->launches++;
-    sdispatch(s, [&]<int NC, typename real, bool FJ>() { k_struct_frame<NC, real, false><<<(s->N + 255) / 256, 256, 0, s->stream>>>(a, r, buf); });
+    if (s->prec == 8) k_i8_frame<false><<<(s->N + 255) / 256, 256, 0, s->stream>>>(a, r, buf);
+    else sdispatch(s, [&]<int NC, typename real, bool FJ>() { k_struct_frame<NC, real, false><<<(s->N + 255) / 256, 256, 0, s->stream>>>(a, r, buf); });
     MCG_CUDA(cudaGetLastError());
     MCG_CUDA(cudaStreamSynchronize(s->stream));
 }
@@ -1563,7 +1628,8 @@ void structured_get_spins(mcg_system *s, int r, double *spins) {
     double *buf = stage(s);
     size_t n = (size_t)s->N * (s->NC == 1 ? 1 : 3);
     s->launches++;
-    sdispatch(s, [&]<int NC, typename real, bool FJ>() { k_struct_frame<NC, real, true><<<(s->N + 255) / 256, 256, 0, s->stream>>>(a, r, buf); });
+    if (s->prec == 8) k_i8_frame<true><<<(s->N + 255) / 256, 256, 0, s->stream>>>(a, r, buf);
+    else sdispatch(s, [&]<int NC, typename real, bool FJ>() { k_struct_frame<NC, real, true><<<(s->N + 255) / 256, 256, 0, s->stream>>>(a, r, buf); });
     MCG_CUDA(cudaGetLastError());
     MCG_CUDA(cudaMemcpyAsync(spins, buf, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     MCG_CUDA(cudaStreamSynchronize(s->stream));
@@ -1605,6 +1671,16 @@ template <int MODE> static void launch_pass(mcg_system *s, int colour, uint64_t 
     const bool prof = s->profilePasses && MODE != 2;
     if (prof) { MCG_CUDA(cudaEventCreate(&e0)); MCG_CUDA(cudaEventCreate(&e1)); MCG_CUDA(cudaEventRecord(e0, s->stream)); }
     s->launches++;
+    if (s->prec == 8) {   // int8 Ising pass (ising8.cuh): items of 16 or 4 sites
+        const I8Table &T8 = st->i8Tables[colour];
+        auto go = [&]<bool PARTIAL>() {
+            if (st->V == 16) k_i8_pass<MODE, PARTIAL, 4><<<grid, block, 0, s->stream>>>(a, T8, q0, rowsPerBlock, nrb, sweep, pAtt);
+            else k_i8_pass<MODE, PARTIAL, 1><<<grid, block, 0, s->stream>>>(a, T8, q0, rowsPerBlock, nrb, sweep, pAtt);
+        };
+        if (MODE != 2 && pAtt < 1.0) go.template operator()<true>(); else go.template operator()<false>();
+        if (prof) { MCG_CUDA(cudaEventRecord(e1, s->stream)); s->passEvents.emplace_back(e0, e1); }
+        return;
+    }
     const int G = (MODE != 2 && st->V > 1 && !getenv("MCG_NO_FAST")) ? st->fastOK[colour] : 0;
     if (G) {
         bool launched = false;
@@ -1673,7 +1749,8 @@ static void fold_and_extras(mcg_system *s) {
     if (!st->selfPairs) {
         dim3 g((s->nLat + 255) / 256, s->R);
         s->launches++;
-        sdispatch(s, [&]<int NC, typename real, bool FJ>() {
+        if (s->prec == 8) k_i8_pairs<<<g, 256, 0, s->stream>>>(a, st->pair_s, st->pair_t, st->pair_d[0], st->pair_d[1], st->pair_d[2], s->d_sums);
+        else sdispatch(s, [&]<int NC, typename real, bool FJ>() {
             k_struct_pairs<NC, real><<<g, 256, 0, s->stream>>>(a, st->pair_s, st->pair_t, st->pair_d[0], st->pair_d[1], st->pair_d[2], s->d_sums);
         });
     }
@@ -1701,6 +1778,7 @@ static void fold_and_extras(mcg_system *s) {
 }
 
 int structured_wolff_step(mcg_system *s, const WolffArgs &w, bool primed, bool needResidual) {
+    MCG_REQUIRE(s->prec != 8, "Wolff updates run on fp32/fp64 state: create the system with precision 32");
     StructArgs a = struct_args(s);
     int launches = 0;
     sdispatch(s, [&]<int NC, typename real, bool FJ>() {

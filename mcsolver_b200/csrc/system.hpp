@@ -98,6 +98,6 @@ struct mcg_system {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> passEvents;
     mcg::StructuredSystem *st = nullptr;   // structured (descriptor) path state, owned
     mcg::PtState *pt = nullptr;            // parallel-tempering state (mcg_pt_setup), owned
-    size_t real_size() const { return prec == 32 ? 4 : 8; }
+    size_t real_size() const { return prec == 8 ? 1 : (prec == 32 ? 4 : 8); }   // prec 8: Ising spins as int8 (structured path)
     ~mcg_system();
 };

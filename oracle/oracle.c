@@ -89,7 +89,7 @@ static void rng4(uint64_t seed, uint32_t replica, uint32_t stream, uint32_t sub,
  *   stride 0 : per-site blocks (counter word 0 = id); Ising: four consecutive ids share the block id >> 2, word id & 3,
  *              sub-stream 1 for the attempt-probability uniform.
  *   stride S : grouped streams - group G = (id/(V*S))*S + id%S, member m = (id/S)%V, word k = W*m + t is word k&3 of the
- *              block drawn with sub-stream k>>2; attempt probability: word m of sub-stream 7.       (csrc/rng.cuh) */
+ *              block drawn with sub-stream k>>2; attempt probability: word m&3 of sub-stream 7+(m>>2).  (csrc/rng.cuh) */
 static void site_words(const orc_sys *s, uint64_t seed, uint32_t replica, uint64_t sweep, uint32_t id, int partial, uint32_t r[4]) {
     const int W = s->model;
     uint32_t b[4];
@@ -113,7 +113,7 @@ static void site_words(const orc_sys *s, uint64_t seed, uint32_t replica, uint64
     if (W == 3) { r[0] = w[0]; r[1] = w[1]; r[2] = w[2]; }
     else if (W == 2) { r[0] = w[0]; r[2] = w[1]; }
     else r[2] = w[0];
-    if (partial) { rng4(seed, replica, STREAM_METRO, 7, sweep, G, b); r[3] = b[m]; }
+    if (partial) { rng4(seed, replica, STREAM_METRO, 7 + (m >> 2), sweep, G, b); r[3] = b[m & 3]; }
 }
 static double u01(uint32_t r) { return ((double)r + 0.5) * (1.0 / 4294967296.0); }
 /* fp32 engine convention: 23 random bits, (k+0.5)/2^23, evaluated exactly in double here */

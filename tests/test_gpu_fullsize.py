@@ -85,8 +85,8 @@ def test_c2_ising_square_4096_bit_exact_dyadic_energy_and_determinism():
     # beta|J| = 0.5 is dyadic: every bond term is +-0.5 and every partial sum is exact in fp64, so the
     # energy equals (number of unsatisfied - satisfied bonds)/2 bit for bit, in any summation order
     finals = []
-    for rep in range(2):
-        with eng.System.from_spec(spec, 1, precision=64, nReplica=1, beta=[0.5], seed=11) as s:
+    for prec in (64, 64, 8, 8):      # fp64 planes; int8 planes (1 byte per spin, integer acceptance thresholds)
+        with eng.System.from_spec(spec, 1, precision=prec, nReplica=1, beta=[0.5], seed=11) as s:
             s.init_spins(0.0)
             assert s.energy(0) == -2.0 * N * 0.5
             s.metropolis_sweeps(3)
@@ -96,7 +96,10 @@ def test_c2_ising_square_4096_bit_exact_dyadic_energy_and_determinism():
             bonds = (x * np.roll(x, -1, 0)).sum() + (x * np.roll(x, -1, 1)).sum()
             assert E == -0.5 * bonds                    # bit-exact
             finals.append(sp)
+            a0, c0, _ = s.counters(0)
+            assert a0 == 3 * N and 0 < c0 < a0
     assert np.array_equal(finals[0], finals[1])         # same seed, same trajectory
+    assert np.array_equal(finals[2], finals[3])
 
 
 def test_c4_skyrmion_hex_1024_topological_charge_of_uniform_and_tilted_states():

@@ -55,13 +55,20 @@ def _compare(rows, ref, K, model, algo):
 
 
 @pytest.mark.parametrize("p", STATS, ids=IDS)
-@pytest.mark.parametrize("path", ["structured-fp32-offline", "structured-fp32-jit", "tables-fp64"])
+@pytest.mark.parametrize("path", ["structured-fp32-offline", "structured-fp32-jit", "tables-fp64", "structured-int8"])
 def test_equilibrium_observables_within_3_sigma_of_reference(p, path, monkeypatch):
     """structured-fp32 runs twice: the offline runtime-table kernels (MCG_JIT=0) and the NVRTC-specialised build of the
     same source (MCG_JIT=1 - the kernels behind the bench number); Wolff (algo 1) runs its union-find kernels over the
     structured topology in fp32 there."""
     structured = path.startswith("structured")
     info = {}
+    if path == "structured-int8":
+        if p["model"] != 1 or p["algo"] != 0:
+            pytest.skip("int8 state: Ising Metropolis")
+        rows = _run_gpu(p, 8, tables=False, info=info)
+        assert info["jit_launches"] == 0
+        _compare(rows, np.array(p["rows"]), p["K"], p["model"], p["algo"])
+        return
     if structured:
         monkeypatch.setenv("MCG_JIT", "1" if path.endswith("jit") else "0")
         if p["algo"] == 1 and path.endswith("jit"):
