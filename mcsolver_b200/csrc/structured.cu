@@ -683,15 +683,15 @@ __global__ void __launch_bounds__(256) k_struct_frame(StructArgs a, int r, doubl
 static __global__ void __launch_bounds__(256) k_i8_init(StructArgs a) {
     const int r = blockIdx.y, p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.N) return;
-    ((signed char *)a.spin)[(size_t)r * a.N + p] = a.classes[p / a.ncellc].S < 0 ? -1 : 1;   // initSpin carries the signed S (isingLib.c:23-40)
+    ((unsigned char *)a.spin)[(size_t)r * a.N + p] = a.classes[p / a.ncellc].S < 0 ? 1 : 0;   // byte = "spin is down"; initSpin carries the signed S (isingLib.c:23-40)
 }
 template <bool GATHER> static __global__ void __launch_bounds__(256) k_i8_frame(StructArgs a, int r, double *buf) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.N) return;
-    signed char *sp = (signed char *)a.spin + (size_t)r * a.N;
+    unsigned char *sp = (unsigned char *)a.spin + (size_t)r * a.N;
     const size_t i = (size_t)struct_site_id(a, p);
-    if (GATHER) buf[i] = (double)sp[p] * fabs(a.classes[p / a.ncellc].S);
-    else sp[p] = buf[i] < 0 ? -1 : 1;
+    if (GATHER) buf[i] = (sp[p] ? -1.0 : 1.0) * fabs(a.classes[p / a.ncellc].S);
+    else sp[p] = buf[i] < 0 ? 1 : 0;
 }
 static __global__ void __launch_bounds__(256) k_i8_pairs(StructArgs a, int ps, int pt, int d0, int d1, int d2, double *sums) {
     __shared__ double smem[32];
@@ -701,8 +701,8 @@ static __global__ void __launch_bounds__(256) k_i8_pairs(StructArgs a, int ps, i
         const int z = cell % a.Lz, y = (cell / a.Lz) % a.Ly, x = cell / (a.Lz * a.Ly);
         const int pi = struct_pos(a, x, y, z, ps);
         const int pj = struct_pos(a, (x + d0 + a.Lx) % a.Lx, (y + d1 + a.Ly) % a.Ly, (z + d2 + a.Lz) % a.Lz, pt);
-        const signed char *sp = (const signed char *)a.spin + (size_t)r * a.N;
-        v[0] = (double)(sp[pi] * sp[pj]) * fabs(a.classes[pi / a.ncellc].S) * fabs(a.classes[pj / a.ncellc].S);
+        const unsigned char *sp = (const unsigned char *)a.spin + (size_t)r * a.N;
+        v[0] = (sp[pi] != sp[pj] ? -1.0 : 1.0) * fabs(a.classes[pi / a.ncellc].S) * fabs(a.classes[pj / a.ncellc].S);
     }
     block_accumulate<1>(v, sums + (size_t)r * NSUM + SUM_SIJ, smem);
 }
@@ -828,6 +828,38 @@ std::string jit_prologue(const mcg_system *s, int colour, bool partial) {
     return o.str();
 }
 
+// the int8 Ising pass (ising8.cuh) with the lattice as literals: same entry-point names, so the loader below serves both
+std::string jit_i8_prologue(const mcg_system *s, int colour, bool partial) {
+    const StructuredSystem *st = s->st;
+    const I8Table &T = st->i8Tables[colour];
+    const int minb = getenv("MCG_JIT_MINB") ? atoi(getenv("MCG_JIT_MINB")) : 4;
+    std::ostringstream o;
+    o << "#define MCG_JIT_I8 1\n#define JIT_NW " << st->V / 4 << "\n#define JIT_PARTIAL " << (partial ? "true" : "false") << "\n#define JIT_NQC " << T.nqc
+      << "\n#define JIT_MINB " << minb << "\n#define JIT_JS2 " << lit(T.JS2, false) << "\n#define JIT_S " << lit(T.S, false) << "\n";
+    o << "#define JIT_Xd " << st->Xd << "\n#define JIT_Yd " << st->Yd << "\n#define JIT_Zd " << st->Zd << "\n#define JIT_Zc "
+      << st->Zd / st->V << "\n#define JIT_N " << s->N << "\n#define JIT_px " << st->p[0] << "\n#define JIT_py " << st->p[1]
+      << "\n#define JIT_pz " << st->p[2] << "\n#define JIT_norb " << st->norb << "\n#define JIT_Ly " << st->L[1]
+      << "\n#define JIT_Lz " << st->L[2] << "\n#define JIT_nrows " << st->nrows << "\n#define JIT_nclass " << st->nclass << "\n";
+    o << "namespace mcg {\ntemplate <int J> struct I8Ct;\n";
+    for (int j = 0; j < T.nqc; j++) {
+        const I8Class &c = T.c[j];
+        o << "template <> struct I8Ct<" << j << "> { static constexpr int nl=" << c.nl << ", nlow=" << c.nlow << ", lowmode=" << c.lowmode << ", ca=" << c.ca
+          << ", cb=" << c.cb << ", cc=" << c.cc << ", co=" << c.co << ";\n";
+        auto arr = [&](const char *name, auto get) {
+            o << "  static __device__ constexpr int " << name << "(int k) { constexpr int v[" << c.nl << "] = {";
+            for (int k = 0; k < c.nl; k++) o << (k ? "," : "") << get(k);
+            o << "}; return v[k]; }\n";
+        };
+        arr("delta", [&](int k) { return c.delta[k]; });
+        arr("wx", [&](int k) { return (int)c.wx[k]; });
+        arr("wy", [&](int k) { return (int)c.wy[k]; });
+        arr("cz", [&](int k) { return (int)c.cz[k]; });
+        o << "};\n";
+    }
+    o << "}\n#include \"ising8.cuh\"\n";
+    return o.str();
+}
+
 struct JitPass {
     CUfunction f[2] = {nullptr, nullptr};
     bool failed = false;
@@ -853,12 +885,12 @@ static std::string read_file(const std::string &path) {
 // identity of a specialised module: generated prologue + the kernel headers it includes
 static uint64_t cache_key(const std::string &src) {
     uint64_t h = fnv1a(src);
-    for (const char *f : {"/struct_pass.cuh", "/topo_pass.cuh", "/devmath.cuh", "/rng.cuh"}) h = fnv1a(read_file(csrc_dir() + f), h);
+    for (const char *f : {"/struct_pass.cuh", "/ising8.cuh", "/topo_pass.cuh", "/devmath.cuh", "/rng.cuh"}) h = fnv1a(read_file(csrc_dir() + f), h);
     return h;
 }
 uint64_t structured_jit_key(const mcg_system *s, int colour) {
     if (!s->structured || colour < 0 || colour >= s->C) throw Error(MCG_ERR_ARG, "not a structured system / colour out of range");
-    return cache_key(jit_prologue(s, colour, false));
+    return cache_key(s->prec == 8 ? jit_i8_prologue(s, colour, false) : jit_prologue(s, colour, false));
 }
 static std::string cache_path(const std::string &src) {
     const char *dir = getenv("MCG_CACHE_DIR");
@@ -915,7 +947,6 @@ std::vector<char> jit_compile_cubin(const std::string &src, std::string &log) {
 }
 
 static bool jit_enabled(const mcg_system *s) {
-    if (s->prec == 8) return false;   // the int8 Ising pass is an offline kernel
     const char *e = getenv("MCG_JIT");
     if (e && e[0] == '0') return false;
     if (e && e[0] == '1') return true;
@@ -946,7 +977,7 @@ bool jit_launch_pass(mcg_system *s, int colour, int mode, const StructArgs &a, i
     JitPass *jp = static_cast<JitPass *>(st->jitResolved[slotIdx]);
     if (!jp) {
         std::lock_guard<std::mutex> lock(g_jit_mutex);
-        auto key = std::make_pair(s->device, jit_prologue(s, colour, pAtt < 1.0));
+        auto key = std::make_pair(s->device, s->prec == 8 ? jit_i8_prologue(s, colour, pAtt < 1.0) : jit_prologue(s, colour, pAtt < 1.0));
         auto it = g_jit_cache.find(key);
         if (it == g_jit_cache.end()) {
             JitPass np;
@@ -1566,6 +1597,13 @@ int structured_jit_check(const mcg_lattice_desc *d, int precision, std::string &
         if (cubin.empty()) { report = o.str(); return -1; }
         ncompiled++;
     }
+    for (int c = 0; c < tmp.C && precision == 8; c++) {
+        std::string log;
+        std::vector<char> cubin = jit_compile_cubin(jit_i8_prologue(&tmp, c, false), log);
+        o << "colour " << c << " (int8): cubin " << cubin.size() << " bytes" << (log.empty() ? "" : " log: " + log.substr(0, 1500)) << "\n";
+        if (cubin.empty()) { report = o.str(); return -1; }
+        ncompiled++;
+    }
     if (jit_topo_worthwhile(tmp.st) && tmp.NC == 3) {
         std::string log;
         std::vector<char> cubin = jit_compile_cubin(jit_topo_prologue(&tmp), log);
@@ -1659,7 +1697,9 @@ template <int MODE> static void launch_pass(mcg_system *s, int colour, uint64_t 
     if (nqc == 0) return;
     int Zc = st->Zd / st->V;
     int bx = 1;
-    while (bx < Zc && bx < 64) bx <<= 1;
+    // int8 items (16 sites): four items of a row per thread amortise the per-row address set-up
+    const int bxTarget = s->prec == 8 ? std::max(1, Zc / 4) : Zc;
+    while (bx < bxTarget && bx < 64) bx <<= 1;
     int by = 256 / bx;
     int iters = 8;
     auto nblocks = [&](int it) { return (long long)s->R * nqc * ((st->nrows + by * it - 1) / (by * it)); };
@@ -1673,9 +1713,22 @@ template <int MODE> static void launch_pass(mcg_system *s, int colour, uint64_t 
     s->launches++;
     if (s->prec == 8) {   // int8 Ising pass (ising8.cuh): items of 16 or 4 sites
         const I8Table &T8 = st->i8Tables[colour];
+        if constexpr (MODE != 2) {
+            if (jit_launch_pass(s, colour, MODE, a, q0, rowsPerBlock, nrb, sweep, pAtt, grid, block)) {
+                if (prof) { MCG_CUDA(cudaEventRecord(e1, s->stream)); s->passEvents.emplace_back(e0, e1); }
+                return;
+            }
+        }
+        bool small = true;
+        for (int j = 0; j < T8.nqc; j++) small = small && T8.c[j].nl <= RtI8Class::NLMAX;
         auto go = [&]<bool PARTIAL>() {
-            if (st->V == 16) k_i8_pass<MODE, PARTIAL, 4><<<grid, block, 0, s->stream>>>(a, T8, q0, rowsPerBlock, nrb, sweep, pAtt);
-            else k_i8_pass<MODE, PARTIAL, 1><<<grid, block, 0, s->stream>>>(a, T8, q0, rowsPerBlock, nrb, sweep, pAtt);
+            if (st->V == 16) {
+                if (small) k_i8_pass<MODE, PARTIAL, 4, true><<<grid, block, 0, s->stream>>>(a, T8, q0, rowsPerBlock, nrb, sweep, pAtt);
+                else k_i8_pass<MODE, PARTIAL, 4, false><<<grid, block, 0, s->stream>>>(a, T8, q0, rowsPerBlock, nrb, sweep, pAtt);
+            } else {
+                if (small) k_i8_pass<MODE, PARTIAL, 1, true><<<grid, block, 0, s->stream>>>(a, T8, q0, rowsPerBlock, nrb, sweep, pAtt);
+                else k_i8_pass<MODE, PARTIAL, 1, false><<<grid, block, 0, s->stream>>>(a, T8, q0, rowsPerBlock, nrb, sweep, pAtt);
+            }
         };
         if (MODE != 2 && pAtt < 1.0) go.template operator()<true>(); else go.template operator()<false>();
         if (prof) { MCG_CUDA(cudaEventRecord(e1, s->stream)); s->passEvents.emplace_back(e0, e1); }

@@ -38,7 +38,7 @@ IDS = ["%s-%s-S%g-J%g" % (c[0], "x".join(map(str, c[1])), c[4], c[5]) for c in C
 
 @pytest.mark.parametrize("case", CASES, ids=IDS)
 @pytest.mark.parametrize("p_att", [1.0, 0.37])
-def test_int8_ising_energy_trajectory_and_counters_match_oracle(case, p_att):
+def test_int8_ising_energy_trajectory_and_counters_match_oracle(case, p_att, jit_mode):
     from mcsolver_b200.lattice import build_tables
     eng = _eng()
     name, L, T, h, S, J, V = case
@@ -63,11 +63,11 @@ def test_int8_ising_energy_trajectory_and_counters_match_oracle(case, p_att):
         assert np.array_equal(got, r["spins"].reshape(got.shape))              # +-S exactly: same decision at every attempt
         att, acc, _ = s.counters()
         assert (att, acc) == (int(r["counters"][0]), int(r["counters"][1]))
-        assert s.jit_launch_count() == 0
+        assert (s.jit_launch_count() > 0) == (jit_mode == "jit")      # both builds of the pass: runtime tables / lattice as literals
 
 
 @pytest.mark.parametrize("case", CASES[:4], ids=IDS[:4])
-def test_int8_ising_whole_run_with_fused_measurement_matches_oracle(case):
+def test_int8_ising_whole_run_with_fused_measurement_matches_oracle(case, jit_mode):
     from mcsolver_b200.lattice import build_tables
     eng = _eng()
     name, L, T, h, S, J, V = case

@@ -66,7 +66,6 @@ def test_equilibrium_observables_within_3_sigma_of_reference(p, path, monkeypatc
         if p["model"] != 1 or p["algo"] != 0:
             pytest.skip("int8 state: Ising Metropolis")
         rows = _run_gpu(p, 8, tables=False, info=info)
-        assert info["jit_launches"] == 0
         _compare(rows, np.array(p["rows"]), p["K"], p["model"], p["algo"])
         return
     if structured:
