@@ -194,25 +194,58 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def wolff_metric(device, L=4096, steps=100):
+def wolff_metric(device, L=4096, steps=100, peak=None):
+    """BASELINE.json's second metric (Wolff cluster flips/sec) on configs[1]: 2D Ising 4096^2 across Tc.  Per temperature, 8
+    replicas of that temperature in one batch, the engine's default path (adaptive hybrid: frontier growth from the seed when
+    the cluster is small, global bond passes + union-find when it percolates) next to the global passes alone."""
     from mcsolver_b200 import engine
     from mcsolver_b200.lattice import LatticeSpec
     spec = LatticeSpec(L=(L, L, 1), S=[1.0], bonds=[(0, 0, (1, 0, 0), J_ISO), (0, 0, (0, 1, 0), J_ISO)])
-    T = np.array([2.0, 2.2, 2.269, 2.35, 2.6])
-    with engine.System.from_spec(spec, 1, precision=32, nReplica=len(T), beta=1 / T, seed=1, device=device) as s:
-        s.init_spins(0.0)
-        s.metropolis_sweeps(20)
-        s.wolff_steps(20)
-        s.reset_measurements()
-        t0 = time.time()
-        s.wolff_steps(steps)          # synchronous: returns after the stream has drained
-        dt = time.time() - t0
-        flipped = sum(s.counters(r)[2] for r in range(len(T)))
-        sizes = [s.counters(r)[2] / max(1, s.counters(r)[1]) / spec.nsite for r in range(len(T))]
-    return {"workload": "ising_square_%d^2, Wolff single-cluster updates at T=%s (J=-1), 5 replicas in one batch" % (L, T.tolist()),
-            "cluster_updates_per_s": steps * len(T) / dt, "flipped_spins_per_s": flipped / dt,
-            "mean_cluster_fraction_per_T": [round(float(x), 5) for x in sizes],
-            "algorithm": "bond activation + atomicCAS union-find over the whole lattice, seed's cluster reflected"}
+    R = 8
+    rows = []
+    saved = os.environ.get("MCG_WOLFF_FRONTIER")
+    try:
+        for T in [2.0, 2.2, 2.269, 2.35, 2.6]:
+            row = {"T": T}
+            for mode, key in (("0", "global_passes_only"), (None, "default")):
+                if mode is None:
+                    os.environ.pop("MCG_WOLFF_FRONTIER", None)
+                else:
+                    os.environ["MCG_WOLFF_FRONTIER"] = mode
+                n = steps if mode is None else max(10, steps // 4)
+                with engine.System.from_spec(spec, 1, precision=32, nReplica=R, beta=np.full(R, 1 / T), seed=1, device=device) as s:
+                    s.init_spins(0.0)
+                    s.metropolis_sweeps(20)
+                    s.wolff_steps(20)
+                    c0 = [s.counters(r) for r in range(R)]
+                    f0 = sum(s.wolff_frontier_steps(r) for r in range(R))
+                    t0 = time.time()
+                    s.wolff_steps(n)          # synchronous: returns after the stream has drained
+                    dt = time.time() - t0
+                    c1 = [s.counters(r) for r in range(R)]
+                    flipped = sum(b[2] - a[2] for a, b in zip(c0, c1))
+                    nfront = sum(s.wolff_frontier_steps(r) for r in range(R)) - f0
+                row[key] = {"cluster_updates_per_s": n * R / dt, "flipped_spins_per_s": flipped / dt,
+                            "mean_cluster_fraction": flipped / (n * R) / spec.nsite, "steps_by_frontier_growth": nfront / (n * R)}
+                if mode == "0" and peak:
+                    # bond pass: spin + own forest word read, forest word written; flip pass: forest word + spin read, spin and the
+                    # next step's forest word written: 7 words of 4 B per site per update (finds through the forest come on top)
+                    row[key]["hbm_frac_at_28B_per_site"] = n * R * spec.nsite * 28 / dt / (peak * 1e9)
+            row["speedup"] = row["default"]["cluster_updates_per_s"] / row["global_passes_only"]["cluster_updates_per_s"]
+            rows.append(row)
+    finally:
+        if saved is None:
+            os.environ.pop("MCG_WOLFF_FRONTIER", None)
+        else:
+            os.environ["MCG_WOLFF_FRONTIER"] = saved
+    tot = sum(r["default"]["cluster_updates_per_s"] for r in rows)
+    return {"workload": "ising_square_%d^2 (J=-1), Wolff single-cluster updates, %d replicas per temperature" % (L, R),
+            "per_temperature": rows, "cluster_updates_per_s": tot / len(rows),
+            "flipped_spins_per_s": sum(r["default"]["flipped_spins_per_s"] for r in rows) / len(rows),
+            "algorithm": "per step and replica: breadth-first growth from the seed over per-bond Philox words (one thread block, O(cluster)); "
+                         "clusters that outgrow the 32768-site queue take the global passes (bond activation + atomicCAS union-find, O(N)); "
+                         "same clusters either way (tests/test_gpu_wolff_frontier.py)",
+            "bound": "global passes: HBM + atomics; frontier growth: latency (one L2/HBM round trip per breadth-first level)"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -461,7 +494,7 @@ def main():
     #      2D Ising 4096^2 (configs[1]) at five temperatures across Tc, union-find cluster updates
     wolff = None
     if rank == 0 and world == 1 and not a.no_wolff:
-        wolff = wolff_metric(local)
+        wolff = wolff_metric(local, peak=peak)
 
     f64 = None
     if rank == 0 and world == 1 and not a.no_wolff:

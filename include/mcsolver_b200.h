@@ -158,6 +158,10 @@ MCG_API int mcg_metropolis_sweeps(mcg_system *sys, int64_t nsweeps, double pAtte
 MCG_API int mcg_timed_sweeps(mcg_system *sys, int64_t nsweeps, double pAttempt, int with_measure, double *elapsed_ms);
 /* nsteps Wolff single-cluster updates (blockUpdate) by bond activation + union-find labelling */
 MCG_API int mcg_wolff_steps(mcg_system *sys, int64_t nsteps);
+/* how many of the replica's Wolff steps so far were completed by frontier growth from the seed (O(cluster) work) instead of
+ * the global bond passes (O(N)); lattices of >= 65536 sites choose per step and per replica (MCG_WOLFF_FRONTIER=0 disables).
+ * Same clusters either way: the reference grows its FIFO from the seed, isingLib.c:165-236, heisenbergLib.c:310-439 */
+MCG_API int mcg_wolff_frontier_steps(mcg_system *sys, int replica, int64_t *steps);
 
 /* ---- measurement (heisenbergLib.c:661-831 definitions) ---- */
 MCG_API int mcg_measure(mcg_system *sys);              /* accumulate one "sweep" worth of observables */

@@ -71,6 +71,7 @@ SIGNATURES = {
     "mcg_reset_measurements": (_i, [_vp]),
     "mcg_results": (_i, [_vp, _i, _vp, _vp]),
     "mcg_counters": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "mcg_wolff_frontier_steps": (_i, [_vp, _i, _vp]),
     "mcg_launch_count": (_i, [_vp, _vp]),
     "mcg_jit_launch_count": (_i, [_vp, _vp]),
     "mcg_jit_module_key": (_i, [_vp, _i, _vp]),

@@ -469,6 +469,13 @@ static void metropolis_sweeps(mcg_system *s, int64_t n, double pAtt) {
     MCG_CUDA(cudaGetLastError());
 }
 
+// frontier/global hybrid of the per-phase Wolff path: 0 = off, 1 = adaptive, 2 = frontier always tried first, 3 = hybrid sequence
+// with the frontier kernel declining every step (exercises the hybrid bookkeeping of the global passes alone)
+static int wolff_hybrid_mode(const mcg_system *s) {
+    if (const char *e = getenv("MCG_WOLFF_FRONTIER")) return atoi(e);
+    return s->N >= 65536 ? 1 : 0;    // below that a global pass is a handful of microseconds
+}
+
 static void wolff_steps(mcg_system *s, int64_t n) {
     MCG_REQUIRE(n >= 0, "negative step count");
     const size_t RN = (size_t)s->R * s->N;
@@ -485,12 +492,53 @@ static void wolff_steps(mcg_system *s, int64_t n) {
     WolffArgs w;
     w.wres = s->d_wres; w.N = s->N; w.R = s->R; w.spin = s->d_spin;
     w.beta = s->d_beta; w.field = s->d_field; w.cnt = s->d_cnt; w.key = make_rng_key(s->seed); w.replica0 = s->replica0;
+    const int hyb = wolff_hybrid_mode(s);
+    if (hyb) {
+        if (!s->d_wmode) {
+            const char *e = getenv("MCG_WOLFF_FRONTIER_CAP");
+            s->wolffCap = std::max(4, std::min(s->N, e ? atoi(e) : 32768));
+            s->d_wmode = dalloc<int32_t>((size_t)s->R * WM_N);
+            s->d_wstamp = (uint32_t *)pool_alloc(RN * sizeof(uint32_t));
+            s->d_wqueue = (int32_t *)pool_alloc((size_t)s->R * s->wolffCap * sizeof(int32_t));
+            s->d_hparent = (int32_t *)pool_alloc(2 * RN * sizeof(int32_t));
+            MCG_CUDA(cudaMemsetAsync(s->d_wmode, 0, sizeof(int32_t) * s->R * WM_N, s->stream));
+            MCG_CUDA(cudaMemsetAsync(s->d_wstamp, 0, RN * sizeof(uint32_t), s->stream));
+            // half 0 of every replica's forest pair starts as the identity (positions are replica-local)
+            for (int r = 0; r < s->R; r++) k_wolff_identity<<<148 * 4, 256, 0, s->stream>>>(s->d_hparent + (size_t)r * s->N, (size_t)s->N);
+            s->wolffTag = 0;
+            s->wolffPrimed = false;
+        }
+        w.mode = s->d_wmode; w.stamp = s->d_wstamp; w.queue = s->d_wqueue; w.cap = s->wolffCap;
+        w.parent = s->d_hparent; w.parentNext = nullptr; w.proj = s->d_proj; w.projNext = nullptr;
+        const int force = hyb == 2 ? 1 : hyb == 3 ? 2 : 0;
+        for (int64_t it = 0; it < n; it++) {
+            w.step = s->wolffCtr++;
+            if (++s->wolffTag == 0xFFFFFFFFu) {   // stamps of 2^32 steps ago must not read as this step's
+                MCG_CUDA(cudaMemsetAsync(s->d_wstamp, 0, RN * sizeof(uint32_t), s->stream));
+                s->wolffTag = 1;
+                s->wolffPrimed = false;
+            }
+            w.tag = s->wolffTag;
+            w.hostPrimed = s->wolffPrimed ? 1 : 0;
+            if (s->structured) s->launches += structured_wolff_step(s, w, s->wolffPrimed, needResidual, force);
+            else {
+                GenArgs a = gen_args(s);
+                dispatch(s, [&]<int NC, typename real, bool FJ>() {
+                    TableTopo<NC, real> topo{a, s->d_pos_of};
+                    s->launches += wolff_launch_hybrid<NC, real, FJ>(topo, w, s->stream, s->maxL, needResidual, force, 148 * 8);
+                });
+            }
+            s->wolffPrimed = true;
+        }
+        MCG_CUDA(cudaGetLastError());
+        return;
+    }
     for (int64_t it = 0; it < n; it++) {
         w.step = s->wolffCtr++;
         const int b = (int)(w.step & 1);
         w.parent = s->d_parent + (size_t)b * RN; w.parentNext = s->d_parent + (size_t)(1 - b) * RN;
         w.proj = (char *)s->d_proj + (size_t)b * RN * s->real_size(); w.projNext = (char *)s->d_proj + (size_t)(1 - b) * RN * s->real_size();
-        if (s->structured) s->launches += structured_wolff_step(s, w, s->wolffPrimed, needResidual);
+        if (s->structured) s->launches += structured_wolff_step(s, w, s->wolffPrimed, needResidual, 0);
         else {
             GenArgs a = gen_args(s);
             dispatch(s, [&]<int NC, typename real, bool FJ>() {
@@ -730,11 +778,14 @@ mcg_system::~mcg_system() {
     if (stream) cudaStreamSynchronize(stream);   // nothing of this system may still be running when its pages go back to the pool
     mcg::pool_free(d_spin);
     mcg::pool_free(d_parent);
+    mcg::pool_free(d_wstamp);
+    mcg::pool_free(d_wqueue);
+    mcg::pool_free(d_hparent);
     mcg::pool_free(d_proj);
     d_spin = nullptr; d_parent = nullptr; d_proj = nullptr;
     void *bufs[] = {d_nbrp, d_site_of, d_pos_of, d_pairs, d_tri, d_mi, d_mj, d_jtype, d_cls, d_Jtab, d_clsS, d_clsD, d_spin,
                     d_signS, d_beta, d_field, d_sums, d_acc, d_cnt, d_scratch, d_parent, d_proj, d_wres, d_slot, d_last, d_rPos, d_rCl, d_rNbrRow, d_rNl, d_pairRowI, d_pairRowJ, d_groups, d_ms, d_rsums,
-                    d_gsum, d_gacc, d_colourStart};
+                    d_gsum, d_gacc, d_colourStart, d_wmode};
     for (void *b : bufs) mcg::pool_free(b);
     if (st) mcg::structured_destroy(st);
     if (pt) mcg::pt_destroy(pt);
@@ -899,6 +950,19 @@ MCG_API int mcg_acc_set(mcg_system *sys, int label, const double *row) {
         MCG_CUDA(cudaMemcpy(sys->d_acc + (size_t)label * NACC, row, sizeof(double) * NACC, cudaMemcpyHostToDevice));
     });
 }
+MCG_API int mcg_wolff_frontier_steps(mcg_system *sys, int replica, int64_t *steps) {
+    SYS_GUARD({
+        MCG_REQUIRE(replica >= 0 && replica < sys->R && steps, "bad replica index");
+        *steps = 0;
+        if (sys->d_wmode) {
+            int32_t m[WM_N];
+            MCG_CUDA(cudaStreamSynchronize(sys->stream));
+            MCG_CUDA(cudaMemcpy(m, sys->d_wmode + (size_t)replica * WM_N, sizeof(m), cudaMemcpyDeviceToHost));
+            *steps = m[WM_NFRONT];
+        }
+    });
+}
+
 MCG_API int mcg_counters(mcg_system *sys, int replica, int64_t *attempts, int64_t *accepted, int64_t *cluster_sites) {
     SYS_GUARD({
         MCG_REQUIRE(replica >= 0 && replica < sys->R, "bad replica index");

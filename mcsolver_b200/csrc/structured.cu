@@ -135,6 +135,13 @@ template <int NC, typename real> struct StructTopo {
         iq = ((xn * a.Ly + yn) * a.Lz + zn) * a.norb + L.o2;
         return true;
     }
+    __device__ __forceinline__ int nbr_id(const Ctx &c, int k, int) const {
+        const SLinkD &L = a.links[c.q * MAXLINK + k];
+        int xn = c.x + L.dx; if (xn >= a.Lx) xn -= a.Lx;
+        int yn = c.y + L.dy; if (yn >= a.Ly) yn -= a.Ly;
+        int zn = c.z + L.dz; if (zn >= a.Lz) zn -= a.Lz;
+        return ((xn * a.Ly + yn) * a.Lz + zn) * a.norb + L.o2;
+    }
     // bond templates with the same (orbital, offset) are merged when the class tables are built: a pair is linked once
     __device__ __forceinline__ uint32_t occurrence(const Ctx &, int, int) const { return 0u; }
     __device__ __forceinline__ int site_id_of(int q) const { return struct_site_id(a, q); }
@@ -1830,13 +1837,18 @@ static void fold_and_extras(mcg_system *s) {
     MCG_CUDA(cudaGetLastError());
 }
 
-int structured_wolff_step(mcg_system *s, const WolffArgs &w, bool primed, bool needResidual) {
+int structured_wolff_step(mcg_system *s, const WolffArgs &w, bool primed, bool needResidual, int force) {
     MCG_REQUIRE(s->prec != 8, "Wolff updates run on fp32/fp64 state: create the system with precision 32");
     StructArgs a = struct_args(s);
     int launches = 0;
     sdispatch(s, [&]<int NC, typename real, bool FJ>() {
         auto lg = [](int v) { int sh = 0; while ((1 << sh) < v) sh++; return (1 << sh) == v ? sh : -1; };
         StructTopo<NC, real> topo{a, lg(a.Zd), lg(a.Yd), lg(a.ncellc)};
+        if (w.mode) {
+            int maxL = 1;
+            for (const SClassD &c : s->st->classes) maxL = std::max(maxL, c.nlink);
+            launches = wolff_launch_hybrid<NC, real, FJ>(topo, w, s->stream, maxL, needResidual, force, 148 * 8);
+        } else
         launches = wolff_launch_step<NC, real, FJ>(topo, w, s->stream, primed, needResidual);
     });
     return launches;

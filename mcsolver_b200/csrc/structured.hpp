@@ -14,7 +14,7 @@ void structured_sweeps(mcg_system *s, int64_t n, double pAtt, bool fusedMeasure)
 void structured_colour_order(const mcg_system *s, int32_t *order);
 void structured_rng_layout(const mcg_system *s, int32_t *stride, int32_t *group);
 struct WolffArgs;
-int structured_wolff_step(mcg_system *s, const WolffArgs &w, bool primed, bool needResidual);   // returns kernels launched
+int structured_wolff_step(mcg_system *s, const WolffArgs &w, bool primed, bool needResidual, int force);   // returns kernels launched
 uint64_t structured_jit_key(const mcg_system *s, int colour);   // cache key (= cubin file name) of a colour's specialised module
 int structured_jit_check(const mcg_lattice_desc *d, int precision, std::string &report);
 }  // namespace mcg

@@ -89,6 +89,12 @@ struct mcg_system {
     bool wolffPrimed = false;            // buffers of the next step were prepared by the previous step's flip kernel
     bool isoNoOnsite = false;            // every J is a multiple of the identity and every D is 0 (no exchange-anisotropy residual)
     double *d_wres = nullptr;            // [R][2] residual, cluster size
+    // frontier/global hybrid (kernels_wolff.cuh: k_wolff_frontier): per-replica state words, visit stamps, member queues and
+    // its own forest pair (the plain sequence and the cooperative kernel keep d_parent to themselves)
+    int32_t *d_wmode = nullptr, *d_wqueue = nullptr, *d_hparent = nullptr;
+    uint32_t *d_wstamp = nullptr;
+    int wolffCap = 0;
+    uint32_t wolffTag = 0;
     std::vector<double> beta_host, field_host;
     cudaStream_t stream = nullptr;
     // instrumentation: kernels launched so far; optional CUDA-event timing of the colour-pass kernel

@@ -278,6 +278,12 @@ class System:
         check(_ffi.lib().mcg_counters(self._h, int(replica), C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
+    def wolff_frontier_steps(self, replica=0):
+        """Wolff steps of this replica completed by frontier growth from the seed (the others ran the global bond passes)"""
+        a = C.c_int64(0)
+        check(_ffi.lib().mcg_wolff_frontier_steps(self._h, int(replica), C.byref(a)))
+        return a.value
+
     def run(self, algorithm, nthermal, nsweep, ninterval, spinFrame=0):
         fr = None
         if spinFrame > 0:
