@@ -126,7 +126,46 @@ template <> __device__ __forceinline__ void r_sincos2pi<float>(float u, float &s
     __sincosf(6.283185307179586f * (u - 0.5f), &s, &c);
     s = -s; c = -c;
 }
-template <> __device__ __forceinline__ void r_sincos2pi<double>(double u, double &s, double &c) { sincospi(2.0 * u, &s, &c); }
+// fp64: written out instead of sincospi() (profiles/r02a: 69 of the 309 instructions per attempt of the fp64 pass, two thirds of
+// them moves of polynomial coefficients into uniform registers and special-case handling).  2 pi u = (pi/2)(k + r) with
+// k = rint(4u) in 0..4 and r in [-1/2, 1/2]; Taylor polynomials of sin/cos(pi r / 2) in r^2 (truncation < 2.3e-16), the
+// coefficients in constant memory so that each DFMA reads its own as an operand; the quadrant is a swap and two sign flips.
+static __constant__ double MCG_SINC[8] = {1.5707963267948966192, -0.64596409750624625366, 0.079692626246167045121, -0.0046817541353186881007,
+                                          0.00016044118478735982187, -3.5988432352120853405e-6, 5.6921729219679268118e-8, -6.6880351098114672325e-10};
+static __constant__ double MCG_COSC[9] = {1.0, -1.2337005501361698274, 0.25366950790104801364, -0.020863480763352960873, 0.00091926027483942658024,
+                                          -0.000025202042373060605481, 4.7108747788181715037e-7, -6.3866030837918522411e-9, 6.5659631149794723622e-11};
+template <> __device__ __forceinline__ void r_sincos2pi<double>(double u, double &s, double &c) {
+    const double t = 4.0 * u;
+    const double tm = t + 6755399441055744.0;          // 2^52 + 2^51: the low word of the sum is rint(t)
+    const int k = __double2loint(tm);
+    const double r = t - (tm - 6755399441055744.0);
+    const double x = r * r;
+    double ps = MCG_SINC[7], pc = MCG_COSC[8];
+#pragma unroll
+    for (int j = 6; j >= 0; j--) ps = fma(ps, x, MCG_SINC[j]);
+#pragma unroll
+    for (int j = 7; j >= 0; j--) pc = fma(pc, x, MCG_COSC[j]);
+    ps *= r;
+    // k: 0 (s, c)   1 (c, -s)   2 (-s, -c)   3 (-c, s)   4 (s, c)
+    const double a = (k & 1) ? pc : ps, b = (k & 1) ? ps : pc;
+    s = (k & 2) ? -a : a;
+    c = ((k + 1) & 2) ? -b : b;
+}
+
+// Metropolis test  exp(x) > u  with u = u01<real>(word)  (heisenbergLib.c:461, isingLib.c:244-252; x <= 0 is -dE, x > 0 always accepts).
+// fp64: exp() is 47 instructions of the fp64 pass.  The decision is taken from the fp32 approximation whenever that is certain -
+// |e32 - u32| exceeds every error of the approximation (ex2.approx 2^-22, argument rounding < 1.1e-5 for |x log2 e| <= 126, and the
+// 2^-23 between the 23-bit and the 32-bit uniform of one word) - and from the full-precision exp() in the remaining ~2e-5 of the
+// attempts: the outcome is the one the fp64 comparison gives, always.
+template <typename real> __device__ __forceinline__ bool metro_accept(real x, uint32_t word);
+template <> __device__ __forceinline__ bool metro_accept<float>(float x, uint32_t word) { return r_exp<float>(x) > u01<float>(word); }
+template <> __device__ __forceinline__ bool metro_accept<double>(double x, uint32_t word) {
+    if (x >= 0.0) return true;
+    const float e = r_exp<float>((float)x);
+    const float d = e - u01<float>(word);
+    if (fabsf(d) > fmaf(e, 2e-5f, 3e-7f)) return d > 0.f;
+    return exp(x) > u01<double>(word);
+}
 
 // proposal direction from two Philox words: uniform on S^2 (NC=3) / S^1 (NC=2)
 template <int NC, typename real>

@@ -59,7 +59,7 @@ __device__ __forceinline__ void metro_site(const GenArgs &a, real *sp, int r, in
         if (NC == 1) {
             // isingLib.c:242-252: corr = 2*(sum J s_i s_j - h s_i); flip if corr>=0 or exp(corr)>u
             real corr = real(2) * (beta * s[0] * H[0] - hf * s[0]);
-            if (corr >= real(0) || r_exp<real>(corr) > u01<real>(w[2])) {
+            if (metro_accept<real>(corr, w[2])) {
                 sp[p] = -s[0];
                 accepted++;
             }
@@ -77,7 +77,7 @@ __device__ __forceinline__ void metro_site(const GenArgs &a, real *sp, int r, in
             real dOn = D[0] * (t[0] * t[0] - s[0] * s[0]) + D[1] * (t[1] * t[1] - s[1] * s[1]);
             if (NC == 3) dOn += D[2] * (t[2] * t[2] - s[2] * s[2]);
             dE = beta * (dE + dOn) - hf * (NC == 3 ? tr[2] : tr[0]);
-            if (dE <= real(0) || r_exp<real>(-dE) > u01<real>(w[2])) {   // heisenbergLib.c:461
+            if (metro_accept<real>(-dE, w[2])) {   // heisenbergLib.c:461
                 if (sizeof(real) == 4) {
                     // fp32 state: pin |s| = S so rounding cannot random-walk the spin length
                     real S = ((const real *)a.clsS)[c];

@@ -371,8 +371,16 @@ struct AsClass : RtClass<float> {
 };
 #endif
 
+// cp.async.bulk.prefetch.L2: one instruction asks the L2 for `bytes` (multiple of 16) starting at a 16-byte aligned address
+__device__ __forceinline__ void bulk_prefetch_l2(const void *p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "r"(bytes) : "memory");
+}
+
 // dims: runtime fields offline, literals under JIT (the generated prologue defines JIT_Xd ...)
 #ifdef MCG_JIT
+#ifndef JIT_PF
+#define JIT_PF 0
+#endif
 #define MCG_DIM(a, f) (JIT_##f)
 #else
 #define MCG_DIM(a, f) ((a).f)
@@ -437,6 +445,37 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
         const int wxp = X == Xd - 1 ? -planeX : 0, wxm = X == 0 ? planeX : 0;
         const int wyp = Y == Yd - 1 ? -planeY : 0, wym = Y == 0 ? planeY : 0;
         const bool edgeRow = (wxp | wxm | wyp | wym) != 0;
+#ifdef MCG_JIT
+        if constexpr (JIT_PF != 0) {
+            // Bulk L2 prefetch of everything the NEXT row of this thread row will read (own row and every neighbour row, whole
+            // rows of Zd cells): one cp.async.bulk.prefetch.L2 per row and component, issued by one thread, a full item's worth
+            // of arithmetic (microseconds) ahead of the loads.  The passes that run two blocks per SM (fp64 state, long link
+            // lists) are bound by exposed DRAM latency, not by issue slots or bandwidth (profiles/r02a: fp64 pass 49 % issue
+            // utilisation, 51 % DRAM utilisation, long-scoreboard stalls on the first use of a neighbour value).
+            const int rowN = row + (int)blockDim.y;
+            if (threadIdx.x == 0 && rowN < rowEnd) {
+                const int Xn = rowN / Yd, Yn = rowN - Xn * Yd;
+                const int rowBaseN = ((q * Xd + Xn) * Yd + Yn) * Zd;
+                const int wxpN = Xn == Xd - 1 ? -planeX : 0, wxmN = Xn == 0 ? planeX : 0;
+                const int wypN = Yn == Yd - 1 ? -planeY : 0, wymN = Yn == 0 ? planeY : 0;
+                constexpr unsigned rowBytes = (unsigned)(JIT_Zd * sizeof(real));
+                static_assert(rowBytes % 16 == 0, "bulk prefetch: rows are multiples of 16 bytes");
+#pragma unroll
+                for (int c = 0; c < NC; c++) bulk_prefetch_l2(sp + (size_t)c * N + rowBaseN, rowBytes);
+                auto nbOfN = [&](auto L) { return nb_of(L, rowBaseN, true, wxpN, wxmN, wypN, wymN); };
+                // 1: every neighbour row (doubles the L2 request traffic: each is wanted by up to z rows of this colour);
+                // 2: the own row only - the one certain DRAM miss;  3: own row + the first link's row: one direction maps the
+                // rows of this colour one-to-one onto rows of the other, so every neighbour row is asked for about once
+                if constexpr (JIT_PF == 1 || JIT_PF == 3)
+                cls.for_links(LinkCtx<real>{sp, (size_t)N, 0, Zd}, nbOfN, [&](auto L) {
+                    if (JIT_PF == 3 && L.idx() != 0) return;
+                    const int nb = nbOfN(L);
+#pragma unroll
+                    for (int c = 0; c < NC; c++) bulk_prefetch_l2(sp + (size_t)c * N + nb, rowBytes);
+                }, [&]() {});
+            }
+        }
+#endif
         const int xy = ((X * px + cls.ca()) * Ly + (Y * py + cls.cb())) * Lz;
         for (int zc = threadIdx.x; zc < Zc; zc += blockDim.x) {
             const int Z0 = zc * V;
@@ -694,7 +733,7 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                     const real corr = real(2) * (beta * sx * hx - hf * sx);                     // isingLib.c:242
                     // isingLib.c:244-252 accepts if corr >= 0 or exp(corr) > u; since u < 1 <= exp(corr) for corr >= 0 the
                     // second test alone decides identically
-                    acc = att & (r_exp<real>(corr) > u01<real>(w[2]));
+                    acc = att & metro_accept<real>(corr, w[2]);
                     sx = acc ? -sx : sx;
                 } else {
                     real n[3];
@@ -711,7 +750,7 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                         dE += beta * dOn;
                     }
                     // heisenbergLib.c:461 accepts if dE <= 0 or exp(-dE) > u; u < 1 <= exp(-dE) for dE <= 0, so one test decides
-                    acc = att & (r_exp<real>(-dE) > u01<real>(w[2]));
+                    acc = att & metro_accept<real>(-dE, w[2]);
                     sx = acc ? nx : sx; sy = acc ? ny : sy; sz = acc ? nz : sz;
                     if (renorm) {   // every site, accepted or not
                         const real f = S * r_rsqrt<real>(sx * sx + sy * sy + sz * sz);

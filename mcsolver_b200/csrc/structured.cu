@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(256) k_struct(StructArgs a, int q0, int nqc, i
                         natt++;
                         if (NC == 1) {
                             real corr = real(2) * (beta * sv[0] * Hv[0] - hf * sv[0]);      // isingLib.c:242
-                            if (corr >= real(0) || r_exp<real>(corr) > u01<real>(w[2])) { sv[0] = -sv[0]; nacc++; }
+                            if (metro_accept<real>(corr, w[2])) { sv[0] = -sv[0]; nacc++; }
                         } else {
                             real n[3];
                             random_dir<NC, real>(w[0], w[1], n);
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(256) k_struct(StructArgs a, int q0, int nqc, i
                             real dOn = D[0] * (t1[0] * t1[0] - sv[0] * sv[0]) + D[1] * (t1[1] * t1[1] - sv[1] * sv[1]);
                             if (NC == 3) dOn += D[2] * (t1[2] * t1[2] - sv[2] * sv[2]);
                             dE = beta * (dE + dOn) - hf * (NC == 3 ? tr[2] : tr[0]);
-                            if (dE <= real(0) || r_exp<real>(-dE) > u01<real>(w[2])) {       // heisenbergLib.c:461
+                            if (metro_accept<real>(-dE, w[2])) {       // heisenbergLib.c:461
                                 if (sizeof(real) == 4) {
                                     real f = S * r_rsqrt<real>(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]);
                                     t1[0] *= f; t1[1] *= f; t1[2] *= f;
@@ -807,6 +807,12 @@ std::string jit_prologue(const mcg_system *s, int colour, bool partial) {
     std::ostringstream o;
     o << "#define MCG_JIT 1\ntypedef " << (f32 ? "float" : "double") << " jit_real;\n";
     if (getenv("MCG_NO_F32X2")) o << "#define MCG_NO_F32X2 1\n";   // A/B switch: scalar fp32 arithmetic instead of packed pairs
+    // bulk L2 prefetch of the next row's operands (struct_pass.cuh)
+    // 3 (own row + first link's row) pays where the pass is latency-bound with nothing saturated: fp64 state on short rows
+    // (sc 256^3: 0.66 -> 0.75 of the HBM roofline); it costs 2-18 % elsewhere (fp32, long 2D rows), and asking for every
+    // neighbour row (1) doubles the L2 request traffic and loses 7-20 % everywhere: profiles/r02b_prefetch_ab.txt
+    const int pf = getenv("MCG_JIT_PF") ? atoi(getenv("MCG_JIT_PF")) : (!f32 && st->Zd / st->V <= 64 && st->Xd > 1 ? 3 : 0);
+    o << "#define JIT_PF " << pf << "\n";
     o << "#define JIT_NC " << s->NC << "\n#define JIT_FULLJ " << (s->fullJ ? "true" : "false") << "\n#define JIT_V " << st->V
       << "\n#define JIT_PARTIAL " << (partial ? "true" : "false") << "\n#define JIT_NQC " << nqc << "\n#define JIT_MINB " << minb << "\n";
     o << "#define JIT_Xd " << st->Xd << "\n#define JIT_Yd " << st->Yd << "\n#define JIT_Zd " << st->Zd << "\n#define JIT_Zc "
