@@ -381,11 +381,16 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void *p, unsigned bytes) 
 #ifndef JIT_PF
 #define JIT_PF 0
 #endif
+#ifndef JIT_ACC
+#define JIT_ACC 1      // per-thread fused M,E accumulators: 1 fp64, 0 fp32 (A/B switch)
+#endif
 #define MCG_DIM(a, f) (JIT_##f)
 #else
 #define MCG_DIM(a, f) ((a).f)
 #endif
 
+template <bool NARROW, typename real> struct AccT { typedef double type; };
+template <typename real> struct AccT<true, real> { typedef real type; };
 template <int I> struct IC { static constexpr int value = I; };
 template <int I, int N, typename F> __device__ __forceinline__ void ct_for(F &&f) {
     if constexpr (I < N) {
@@ -435,7 +440,18 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
     real *sp = (real *)a.spin + (size_t)r * NC * N;
     const int idStrideZ = pz * norb;
     const int planeY = Yd * Zd, planeX = planeY * Xd;
-    real accM[3] = {0, 0, 0}, accE = 0;
+    // fused M and E: fp32 only inside one item (four sites), fp64 from the item level on (north_star: fp64 accumulation; fused
+    // energy == recomputed energy to 5e-9 at 8 x 256^3 instead of 1e-6).  Costs 1.6 % of the fp32 sc pass (profiles/r02b_accumulators.txt:
+    // parking the accumulators in shared memory instead of registers costs 5 %); JIT_ACC=0 compiles the fp32 accumulators for A/B runs.
+#ifdef MCG_JIT
+    typedef typename AccT<JIT_ACC == 0, real>::type acc_t;
+#else
+    typedef double acc_t;
+#endif
+    acc_t accM[3] = {0, 0, 0}, accE = 0;
+    auto acc_add = [&](double m0, double m1, double m2, double e) {
+        accM[0] += (acc_t)m0; accM[1] += (acc_t)m1; accM[2] += (acc_t)m2; accE += (acc_t)e;
+    };
     int natt = 0, nacc = 0;
 
     const int rowEnd = min(nrows, (rb + 1) * rowsPerBlock);
@@ -626,8 +642,7 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                     }
                 }
                 if (MODE == 1) {
-                    accM[0] += (real)(aM[0].x + aM[0].y); accM[1] += (real)(aM[1].x + aM[1].y); accM[2] += (real)(aM[2].x + aM[2].y);
-                    accE += (real)(aE.x + aE.y);
+                    acc_add((double)(aM[0].x + aM[0].y), (double)(aM[1].x + aM[1].y), NC == 3 ? (double)(aM[2].x + aM[2].y) : 0.0, (double)(aE.x + aE.y));
                 }
                 if (!PARTIAL) natt += V;
                 float *ownw = (float *)sp + rowBase + Z0;
@@ -719,6 +734,7 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
             const uint32_t id0 = (uint32_t)((xy + Z0 * pz + cls.cc()) * norb + cls.co());
             ItemWords<NC, V> iw;   // V > 1: the item's sites share their Philox blocks (rng.cuh); V == 1: per-site streams
             if (V > 1) iw.begin(a.key, a.replica0 + r, sweep, id0, (uint32_t)idStrideZ, PARTIAL);
+            real iM[3] = {0, 0, 0}, iE = 0;   // this item's contribution to the fused sums
 #pragma unroll
             for (int v = 0; v < V; v++) {
                 real sx = s[0][v], sy = s[1][v], sz = s[2][v];
@@ -761,16 +777,17 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
                 nacc += acc ? 1 : 0;
                 s[0][v] = sx; s[1][v] = sy; s[2][v] = sz;
                 if (MODE == 1) {
-                    accM[0] += sx; accM[1] += sy; accM[2] += sz;
+                    iM[0] += sx; iM[1] += sy; iM[2] += sz;
                     real eb;
                     if (lowmode == 1) eb = sx * hx + sy * hy + sz * hz;
                     else if (lowmode == 2) eb = sx * Hl[0][v] + sy * Hl[1][v] + sz * Hl[2][v];
                     else eb = real(0);
                     real eon = -hf * (NC == 3 ? sz : sx);
                     if (hasD && NC > 1) eon += beta * (D0 * sx * sx + D1 * sy * sy + (NC == 3 ? D2 * sz * sz : real(0)));
-                    accE += beta * eb + eon;
+                    iE += beta * eb + eon;
                 }
             }
+            if (MODE == 1) acc_add((double)iM[0], (double)iM[1], (double)iM[2], (double)iE);
             if (!PARTIAL) natt += V;
             real *ownw = sp + rowBase + Z0;
 #pragma unroll

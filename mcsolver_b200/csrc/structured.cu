@@ -813,6 +813,7 @@ std::string jit_prologue(const mcg_system *s, int colour, bool partial) {
     // neighbour row (1) doubles the L2 request traffic and loses 7-20 % everywhere: profiles/r02b_prefetch_ab.txt
     const int pf = getenv("MCG_JIT_PF") ? atoi(getenv("MCG_JIT_PF")) : (!f32 && st->Zd / st->V <= 64 && st->Xd > 1 ? 3 : 0);
     o << "#define JIT_PF " << pf << "\n";
+    if (getenv("MCG_JIT_ACC")) o << "#define JIT_ACC " << atoi(getenv("MCG_JIT_ACC")) << "\n";   // A/B: see struct_pass.cuh
     o << "#define JIT_NC " << s->NC << "\n#define JIT_FULLJ " << (s->fullJ ? "true" : "false") << "\n#define JIT_V " << st->V
       << "\n#define JIT_PARTIAL " << (partial ? "true" : "false") << "\n#define JIT_NQC " << nqc << "\n#define JIT_MINB " << minb << "\n";
     o << "#define JIT_Xd " << st->Xd << "\n#define JIT_Yd " << st->Yd << "\n#define JIT_Zd " << st->Zd << "\n#define JIT_Zc "
@@ -1024,6 +1025,8 @@ static bool jit_topo_worthwhile(const StructuredSystem *st) {
     return st->ncircuit > 0 && st->ncircuit <= 32 && st->nvert <= 16 && npar * st->nvert <= 256;
 }
 
+static int topo_ypt(const StructuredSystem *st) { return st->Xd >= TOPO_XPT ? 1 : TOPO_YPT; }
+
 std::string jit_topo_prologue(const mcg_system *s) {
     const StructuredSystem *st = s->st;
     const bool f32 = s->prec == 32;
@@ -1031,7 +1034,7 @@ std::string jit_topo_prologue(const mcg_system *s) {
     std::ostringstream o;
     o << "#define MCG_JIT_TOPO 1\ntypedef " << (f32 ? "float" : "double") << " jit_real;\n";
     o << "#define JT_NV " << st->nvert << "\n#define JT_NT " << st->ncircuit << "\n#define JT_NPAR " << npar << "\n#define JT_Xd " << st->Xd
-      << "\n#define JT_Yd " << st->Yd << "\n#define JT_Zd " << st->Zd << "\n#define JT_N " << s->N << "\n";
+      << "\n#define JT_Yd " << st->Yd << "\n#define JT_Zd " << st->Zd << "\n#define JT_N " << s->N << "\n#define JT_YPT " << topo_ypt(st) << "\n";
     o << "namespace mcg {\ntemplate <int PAR, int K> struct CtVert;\ntemplate <int T> struct CtTri;\n";
     for (int par = 0; par < npar; par++) {
         const int cc = par % pz, cb = (par / pz) % py, ca = par / (pz * py);
@@ -1078,6 +1081,10 @@ static bool jit_launch_topo(mcg_system *s, const StructArgs &a, int nzc, int nyc
     }
     if (jp->failed) return false;
     double *sums = s->d_sums;
+    const int ypt = topo_ypt(st);
+    const int npar = st->p[0] * st->p[1] * st->p[2];
+    nyc = (st->Yd + (int)block.y * ypt - 1) / ((int)block.y * ypt);
+    grid.x = (unsigned)(nzc * nyc * npar);
     void *params[] = {(void *)&a, &nzc, &nyc, &sums};
     CUresult r = api.launchKernel(jp->f[0], grid.x, (grid.y + TOPO_XPT - 1) / TOPO_XPT, grid.z, block.x, block.y, 1, 0, (CUstream)s->stream, params, nullptr);
     if (r != CUDA_SUCCESS) throw Error(MCG_ERR_CUDA, "cuLaunchKernel of the JIT topological-charge kernel failed");

@@ -37,6 +37,7 @@ template <typename T> __device__ __forceinline__ T tri_area_unit(const T (&a)[3]
 // cells along X handled by one thread of the specialised kernel: the block reduction (two rounds of double-precision
 // shuffles, a barrier and one atomic per block) was a fifth of the instructions per cell; it is paid once per TOPO_XPT cells
 constexpr int TOPO_XPT = 4;
+constexpr int TOPO_YPT = 8;   // cells along Y per thread where X offers fewer than TOPO_XPT
 
 #ifdef MCG_JIT_TOPO
 // ---- JIT entry: JT_NV, JT_NT, JT_NPAR, JT_Xd, JT_Yd, JT_Zd, JT_N, jit_real, CtVert<PAR,K>, CtTri<T> from the prologue ----
@@ -73,19 +74,23 @@ __device__ __forceinline__ double topo_case(int par, const jit_real *__restrict_
         return topo_case<PAR + 1>(par, sp, X, Y, Z);
     } else return 0.0;
 }
-// Thread (tz, ty) of block (zc + nzc*(yc + nyc*parity), X / TOPO_XPT, r) handles coarse cells (X.., yc*TY + ty, zc*TZ + tz) of one
-// sublattice parity: every vertex then lies in a block-uniform class at a literal coarse offset.
+// Thread (tz, ty) of block (zc + nzc*(yc + nyc*parity), X / TOPO_XPT, r) handles coarse cells (X.., Y0.., zc*TZ + tz) of one sublattice
+// parity - TOPO_XPT cells along X and JT_YPT along Y (2D lattices have Xd == 1: the cells per thread then come from Y) - so that every
+// vertex lies in a block-uniform class at a literal coarse offset and the block index arithmetic and the reduction (86 of 367
+// instructions per cell at one cell per thread, profiles/r02a) are paid once per thread.
 extern "C" __global__ void __launch_bounds__(128) mcg_topo(const __grid_constant__ StructArgs a, int nzc, int nyc, double *sums) {
     __shared__ double smem[32];
     const int par = blockIdx.x / (nzc * nyc), rest = blockIdx.x - par * (nzc * nyc);
     const int yc = rest / nzc, zc = rest - yc * nzc;
     const int r = blockIdx.z;
-    const int Y = yc * blockDim.y + threadIdx.y, Z = zc * blockDim.x + threadIdx.x;
+    const int Y0 = (yc * blockDim.y + threadIdx.y) * JT_YPT, Z = zc * blockDim.x + threadIdx.x;
     double v[1] = {0.0};
-    if (Y < JT_Yd && Z < JT_Zd) {
+    if (Z < JT_Zd) {
         const jit_real *sp = (const jit_real *)a.spin + (size_t)r * 3 * JT_N;
 #pragma unroll 1
-        for (int X = blockIdx.y * TOPO_XPT; X < JT_Xd && X < (int)(blockIdx.y + 1) * TOPO_XPT; X++) v[0] += topo_case<0>(par, sp, X, Y, Z);
+        for (int Y = Y0; Y < JT_Yd && Y < Y0 + JT_YPT; Y++)
+#pragma unroll 1
+            for (int X = blockIdx.y * TOPO_XPT; X < JT_Xd && X < (int)(blockIdx.y + 1) * TOPO_XPT; X++) v[0] += topo_case<0>(par, sp, X, Y, Z);
     }
     block_accumulate<1>(v, sums + (size_t)r * NSUM + SUM_AREA, smem);
 }
