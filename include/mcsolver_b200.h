@@ -136,6 +136,11 @@ MCG_API int mcg_colour_order(const mcg_system *sys, int32_t *order /*[N] site id
  * id = base + m*S of one vector item share their blocks. */
 MCG_API int mcg_rng_layout(const mcg_system *sys, int32_t *stride, int32_t *group);
 MCG_API int mcg_set_params(mcg_system *sys, const double *beta, const double *field); /* per replica */
+/* Reuse a created system for another job on the same lattice (the reference creates every grid point from scratch in a fresh
+ * pool worker, win.py:90-91 / mcMain.py:150-223): new per-replica beta/field (NULL keeps them), new seed and replica offset, all
+ * RNG counters, measurement accumulators and attempt counters back to zero.  After mcg_init_spins the run is bit for bit the one
+ * a fresh mcg_create_* with the same configuration performs. */
+MCG_API int mcg_recycle(mcg_system *sys, const double *beta, const double *field, uint64_t seed, int replica_offset);
 
 /* ---- state ---- */
 /* initial state of establishLattice (heisenbergLib.c:157-172): normalise((S,0,0)+flunc*n)*|S| */

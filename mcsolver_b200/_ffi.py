@@ -60,6 +60,7 @@ SIGNATURES = {
     "mcg_colour_order": (_i, [_vp, _vp]),
     "mcg_rng_layout": (_i, [_vp, _vp, _vp]),
     "mcg_set_params": (_i, [_vp, _vp, _vp]),
+    "mcg_recycle": (_i, [_vp, _vp, _vp, _u64, _i]),
     "mcg_init_spins": (_i, [_vp, _d]),
     "mcg_set_spins": (_i, [_vp, _i, _vp]),
     "mcg_get_spins": (_i, [_vp, _i, _vp]),

@@ -892,6 +892,31 @@ MCG_API int mcg_set_params(mcg_system *sys, const double *beta, const double *fi
     });
 }
 
+// A created system back to the state mcg_create_* leaves it in, with new replica parameters and Philox streams: every
+// counter that feeds the RNG (sweep, Wolff step, measurement) restarts at zero, so a recycled system run with (seed, offset)
+// produces bit for bit what a fresh system created with them produces - without the allocation, table upload, colouring
+// search and module load of a creation.  The spins are whatever the previous job left: callers re-initialise them.
+MCG_API int mcg_recycle(mcg_system *sys, const double *beta, const double *field, uint64_t seed, int replica_offset) {
+    SYS_GUARD({
+        MCG_REQUIRE(!sys->pt && sys->nLabel == sys->R, "a system set up for parallel tempering cannot be recycled");
+        MCG_REQUIRE(replica_offset >= 0, "negative replica offset");
+        MCG_CUDA(cudaStreamSynchronize(sys->stream));
+        sys->seed = seed; sys->replica0 = (uint32_t)replica_offset;
+        sys->sweepCtr = 0; sys->wolffCtr = 0; sys->wolffPrimed = false;
+        sys->launches = 0; sys->jitLaunches = 0;
+        if (sys->d_wmode) {   // frontier/global hybrid bookkeeping: rebuilt on the next Wolff step
+            pool_free(sys->d_wmode); pool_free(sys->d_wstamp); pool_free(sys->d_wqueue); pool_free(sys->d_hparent);
+            sys->d_wmode = nullptr; sys->d_wstamp = nullptr; sys->d_wqueue = nullptr; sys->d_hparent = nullptr;
+        }
+        if (beta) sys->beta_host.assign(beta, beta + sys->R);
+        if (field) sys->field_host.assign(field, field + sys->R);
+        MCG_CUDA(cudaMemcpyAsync(sys->d_beta, sys->beta_host.data(), sizeof(double) * sys->R, cudaMemcpyHostToDevice, sys->stream));
+        MCG_CUDA(cudaMemcpyAsync(sys->d_field, sys->field_host.data(), sizeof(double) * sys->R, cudaMemcpyHostToDevice, sys->stream));
+        reset_measurements_async(sys);
+        MCG_CUDA(cudaStreamSynchronize(sys->stream));
+    });
+}
+
 MCG_API int mcg_init_spins(mcg_system *sys, double flunc) { SYS_GUARD(init_spins(sys, flunc)); }
 MCG_API int mcg_set_spins(mcg_system *sys, int replica, const double *spins) { SYS_GUARD(set_spins(sys, replica, spins)); }
 MCG_API int mcg_get_spins(mcg_system *sys, int replica, double *spins) { SYS_GUARD(get_spins(sys, replica, spins)); }

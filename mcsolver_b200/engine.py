@@ -202,6 +202,15 @@ class System:
         h = f64(field) if field is not None else None
         check(_ffi.lib().mcg_set_params(self._h, ptr(b) if b is not None else None, ptr(h) if h is not None else None))
 
+    def recycle(self, beta=None, field=None, seed=1, replica_offset=0):
+        """Back to the state of a freshly created system with these replica parameters and Philox streams (mcg_recycle):
+        after init_spins() a run reproduces a fresh system's bit for bit, without paying for the creation."""
+        b = f64(beta).reshape(-1) if beta is not None else None
+        h = f64(field).reshape(-1) if field is not None else None
+        if (b is not None and b.size != self.R) or (h is not None and h.size != self.R):
+            raise ValueError("beta/field need one entry per replica")
+        check(_ffi.lib().mcg_recycle(self._h, ptr(b) if b is not None else None, ptr(h) if h is not None else None, int(seed), int(replica_offset)))
+
     def init_spins(self, flunc=0.0):
         check(_ffi.lib().mcg_init_spins(self._h, float(flunc)))
 

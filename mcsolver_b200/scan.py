@@ -21,6 +21,52 @@ def shard(n_points, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+# ---- created systems kept for the next job on the same lattice ----
+# A scan is usually followed by another scan of the same lattice (next seed, refined grid, next field value): creation - device
+# allocation, table build and upload, colouring search, loading the specialised kernels - then costs more than a short job's
+# sweeps.  run_points() keeps the systems it created (per process, keyed by everything creation depends on, at most POOL_MAX of
+# them) and recycles them through mcg_recycle, which restarts every RNG counter: results are bit for bit those of a fresh system
+# (tests/test_gpu_pool.py).  MCG_POOL=0 or clear_pool() turn it off / give the memory back.
+import os as _os
+
+POOL_MAX = 2
+_pool = {}          # key -> System (insertion order = age)
+
+
+def clear_pool():
+    for s in _pool.values():
+        s.close()
+    _pool.clear()
+
+
+def _spec_key(spec):
+    return (tuple(spec.L), tuple(np.asarray(spec.S, float).ravel()), tuple(np.asarray(spec.D, float).ravel()),
+            tuple((b[0], b[1], tuple(b[2]), tuple(float(x) for x in b[3])) for b in spec.bonds), repr(spec.pair), repr(spec.circuits),
+            repr(spec.groups), bool(spec.groupInSC))
+
+
+def _acquire(key, make, beta, field, seed, lo):
+    if _os.environ.get("MCG_POOL", "1") == "0":
+        return make(), False
+    s = _pool.pop(key, None)
+    if s is not None:
+        try:
+            s.recycle(beta=beta, field=field, seed=seed, replica_offset=lo)
+            return s, True
+        except Exception:
+            s.close()
+    return make(), True
+
+
+def _release(key, s, pooled):
+    if not pooled:
+        s.close()
+        return
+    _pool[key] = s
+    while len(_pool) > POOL_MAX:
+        _pool.pop(next(iter(_pool))).close()
+
+
 def run_points(spec, model, T, H, nthermal, nsweep, ninterval=0, algorithm=engine.METROPOLIS, precision=32, seed=1,
                rank=0, world=1, device=-1, flunc=0.0, spin_frames=0, tables=False, want_groups=False, block_spin=False,
                info=None):
@@ -44,15 +90,19 @@ def run_points(spec, model, T, H, nthermal, nsweep, ninterval=0, algorithm=engin
     beta, field = 1.0 / Tl, H[lo:hi]
     N = spec.nsite
     nint = N if ninterval <= 0 else int(ninterval)
-    if tables:
-        from .lattice import build_tables
-        t = build_tables(spec, 1.0, model)     # unscaled tables, beta per replica
-        sysm = engine.System.from_tables(t, precision=precision, nReplica=idx.size, beta=beta, field=field, seed=seed,
-                                         replica_offset=lo, device=device)
-    else:
-        sysm = engine.System.from_spec(spec, model, precision=precision, nReplica=idx.size, beta=beta, field=field,
+    key = (_spec_key(spec), int(model), int(precision), int(idx.size), int(device), bool(tables), bool(block_spin))
+
+    def make():
+        if tables:
+            from .lattice import build_tables
+            t = build_tables(spec, 1.0, model)     # unscaled tables, beta per replica
+            return engine.System.from_tables(t, precision=precision, nReplica=idx.size, beta=beta, field=field, seed=seed,
+                                             replica_offset=lo, device=device)
+        return engine.System.from_spec(spec, model, precision=precision, nReplica=idx.size, beta=beta, field=field,
                                        seed=seed, replica_offset=lo, device=device, block_spin=block_spin)
-    with sysm as s:
+
+    s, pooled = _acquire(key, make, beta, field, seed, lo)
+    try:
         s.init_spins(flunc)
         frames = s.run(algorithm, nthermal, nsweep, nint, spinFrame=spin_frames)
         res = [s.results(r) for r in range(idx.size)]
@@ -60,6 +110,10 @@ def run_points(spec, model, T, H, nthermal, nsweep, ninterval=0, algorithm=engin
         groups = np.stack([r[1] for r in res]) if (model != engine.ISING and res[0][1] is not None and res[0][1].size) else None
         if info is not None:
             info.update(launches=s.launch_count(), jit_launches=s.jit_launch_count(), colours=s.num_colours())
+    except BaseException:
+        s.close()
+        raise
+    _release(key, s, pooled)
     return idx, ((out, groups) if want_groups else out), frames
 
 
