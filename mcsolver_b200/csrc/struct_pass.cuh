@@ -382,7 +382,7 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void *p, unsigned bytes) 
 #define JIT_PF 0
 #endif
 #ifndef JIT_ACC
-#define JIT_ACC 1      // per-thread fused M,E accumulators: 1 fp64, 0 fp32 (A/B switch)
+#define JIT_ACC 0      // per-thread fused M,E accumulators: 0 fp32 (a thread sums at most a few dozen sites), 1 fp64 - see pass_body
 #endif
 #define MCG_DIM(a, f) (JIT_##f)
 #else
@@ -440,9 +440,11 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
     real *sp = (real *)a.spin + (size_t)r * NC * N;
     const int idStrideZ = pz * norb;
     const int planeY = Yd * Zd, planeX = planeY * Xd;
-    // fused M and E: fp32 only inside one item (four sites), fp64 from the item level on (north_star: fp64 accumulation; fused
-    // energy == recomputed energy to 5e-9 at 8 x 256^3 instead of 1e-6).  Costs 1.6 % of the fp32 sc pass (profiles/r02b_accumulators.txt:
-    // parking the accumulators in shared memory instead of registers costs 5 %); JIT_ACC=0 compiles the fp32 accumulators for A/B runs.
+    // fused M and E.  A thread sums its own sites - a few dozen - in fp32 and everything from the warp reduction on is fp64; the
+    // rounding of those short partial sums averages out over the ~1e6 threads of a pass (fused E == recomputed E to ~1e-8 at
+    // 256^3).  JIT_ACC=1 makes the per-thread sums fp64 from the item level (5e-9 ... 5e-11): -1.6 % in bursts but -9.4 % sustained
+    // on the sc 256^3 fp32 pass - under the board power cap the eight fp64-pipe instructions per item are paid in clock
+    // (profiles/r02b_accumulators.txt) - so it is opt-in (MCG_JIT_ACC=1).
 #ifdef MCG_JIT
     typedef typename AccT<JIT_ACC == 0, real>::type acc_t;
 #else
