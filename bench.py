@@ -92,7 +92,7 @@ def ref_kind():
     return "reference" if rh.have_ref_engine() else "port"
 
 
-def run_reference_arm(a, rank, world):
+def run_reference_arm(a, rank, world, emit):
     if rank != 0:
         return
     cores = min(host_cores(), 128)
@@ -145,7 +145,7 @@ def run_reference_arm(a, rank, world):
             "cpu_baseline": {"value": val, "unit": "attempts/s", "cores": cores, "kind": ref_kind(), "sample": sample, "larger_sample": big},
             "e2e": {"value": val, "unit": "attempts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": wall}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(a, world):
@@ -423,10 +423,19 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries ONE JSON line: whatever libraries print to fd 1 on the way (NCCL's version banner, the reference's PyInit
+    # printf) goes to stderr instead; the line itself is written to the original descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
 
     if a.impl == "reference":
         a.steps = min(a.steps, 100)    # each step is a bounded ~1.5 s CPU sample: K steps stay within a few minutes
-        run_reference_arm(a, rank, world)
+        run_reference_arm(a, rank, world, emit)
         return
 
     # ---- CPU baseline first (rank 0, N=1): forks workers, so it must precede CUDA initialisation
@@ -555,7 +564,7 @@ def main():
                 "config": workload_config(a, world), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roof, "cpu_baseline": cpu, "wolff": wolff, "fp64_state": f64, "configs": configs, "pt": ptres, "host_wall_s": wall,
                 "check": {"replica0_T": float(Ts[0]), "e_per_site_over_kT": float(out0[8]), "U4": float(out0[10])}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

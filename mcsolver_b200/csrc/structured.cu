@@ -1598,6 +1598,12 @@ void structured_create(mcg_system *s, const mcg_lattice_desc *d) {
 
 // host-only check used by the CPU tests: build the class tables of a descriptor and compile the
 // specialised pass kernels of every colour with NVRTC (no device needed up to the cubin)
+static std::string jit_key_hex(const std::string &src) {
+    char b[32];
+    snprintf(b, sizeof b, "%016llx", (unsigned long long)cache_key(src));
+    return b;
+}
+
 int structured_jit_check(const mcg_lattice_desc *d, int precision, std::string &report) {
     mcg_system tmp;
     tmp.prec = precision;
@@ -1612,22 +1618,25 @@ int structured_jit_check(const mcg_lattice_desc *d, int precision, std::string &
     for (int c = 0; c < tmp.C && precision != 8; c++) {
         if (!tmp.st->fastOK[c] || tmp.st->V == 1 || !jit_worthwhile(&tmp, c)) { o << "colour " << c << ": not eligible for specialisation\n"; continue; }
         std::string log;
-        std::vector<char> cubin = jit_compile_cubin(jit_prologue(&tmp, c, false), log);
-        o << "colour " << c << ": cubin " << cubin.size() << " bytes" << (log.empty() ? "" : " log: " + log.substr(0, 1500)) << "\n";
+        const std::string src = jit_prologue(&tmp, c, false);
+        std::vector<char> cubin = jit_compile_cubin(src, log);
+        o << "colour " << c << ": module " << jit_key_hex(src) << " cubin " << cubin.size() << " bytes" << (log.empty() ? "" : " log: " + log.substr(0, 1500)) << "\n";
         if (cubin.empty()) { report = o.str(); return -1; }
         ncompiled++;
     }
     for (int c = 0; c < tmp.C && precision == 8; c++) {
         std::string log;
-        std::vector<char> cubin = jit_compile_cubin(jit_i8_prologue(&tmp, c, false), log);
-        o << "colour " << c << " (int8): cubin " << cubin.size() << " bytes" << (log.empty() ? "" : " log: " + log.substr(0, 1500)) << "\n";
+        const std::string src = jit_i8_prologue(&tmp, c, false);
+        std::vector<char> cubin = jit_compile_cubin(src, log);
+        o << "colour " << c << " (int8): module " << jit_key_hex(src) << " cubin " << cubin.size() << " bytes" << (log.empty() ? "" : " log: " + log.substr(0, 1500)) << "\n";
         if (cubin.empty()) { report = o.str(); return -1; }
         ncompiled++;
     }
     if (jit_topo_worthwhile(tmp.st) && tmp.NC == 3) {
         std::string log;
-        std::vector<char> cubin = jit_compile_cubin(jit_topo_prologue(&tmp), log);
-        o << "topological charge: cubin " << cubin.size() << " bytes" << (log.empty() ? "" : " log: " + log.substr(0, 1500)) << "\n";
+        const std::string src = jit_topo_prologue(&tmp);
+        std::vector<char> cubin = jit_compile_cubin(src, log);
+        o << "topological charge: module " << jit_key_hex(src) << " cubin " << cubin.size() << " bytes" << (log.empty() ? "" : " log: " + log.substr(0, 1500)) << "\n";
         if (cubin.empty()) { report = o.str(); return -1; }
     }
     report = o.str();
