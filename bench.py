@@ -369,6 +369,37 @@ def pt_leg(rank, world, local, barrier_max, peak, L=256, R=8, sweeps=40, sps=5):
     return out
 
 
+def slab_leg(rank, world, local, barrier_max, a, peak, sweeps=40):
+    """ONE lattice over all GPUs (SURVEY 8e "largest lattice"): Heisenberg sc (256 N) x 256 x 256 cut into N slabs along x, the same
+    8 replicas and 256^3 sites per GPU as the headline.  After every colour pass the boundary planes go to the neighbours' ghost
+    planes (ncclSend/ncclRecv inside the library, on the compute stream) and the raw measurement sums are all-reduced, so the
+    number next to the headline's is the price of the halo exchange; N = 1 runs the same code with its own periodic images."""
+    from mcsolver_b200 import engine, pt
+    from mcsolver_b200.lattice import LatticeSpec
+    L, R = a.L, a.replicas
+    spec = LatticeSpec(L=(L * world, L, L), S=[1.0], bonds=[(0, 0, (1, 0, 0), J_ISO), (0, 0, (0, 1, 0), J_ISO), (0, 0, (0, 0, 1), J_ISO)])
+    port = int(os.environ.get("MASTER_PORT", "29500")) + 31
+    cid = pt.comm_id(rank, world, port=port)
+    Ts = ladder(R)                                     # every rank holds a slab of each of the R replicas
+    with engine.System.from_spec_slab(spec, 3, rank, world, comm_id=cid, precision=32, nReplica=R, beta=1 / Ts, seed=1, device=local) as s:
+        s.init_spins(0.0)
+        s.timed_sweeps(5, with_measure=True)
+        barrier_max(0.0)
+        ms = s.timed_sweeps(sweeps, with_measure=True)
+        e_check = s.results(0)[0][8]
+        info = dict(s.slab)
+    t = barrier_max(ms / 1e3)
+    att = R * spec.nsite * sweeps / t
+    plane_bytes = R * 3 * 4 * (L // 2) * (L // 2) * 4 * 2      # per colour pass and direction: replicas x components x classes x coarse plane x 4 B ... x2 directions
+    return {"workload": "heisenberg_sc_%dx%dx%d (one lattice, %d slabs along x), %d replicas, fp32" % (L * world, L, L, world, R),
+            "value": att, "unit": "attempts/s", "sweeps_timed": sweeps, "roofline_frac_per_gpu": att / world * 36 / (peak * 1e9),
+            "halo_bytes_per_colour_pass_per_gpu": plane_bytes if world > 1 else 0, "slab_of_rank0": info,
+            "collectives": "per colour pass ncclSend/ncclRecv of the boundary coarse planes to both neighbours; per measured sweep one "
+                           "ncclAllReduce of 12 doubles per replica (dlopen'ed libnccl, no PyTorch)" if world > 1 else
+                           "world = 1: ghost planes are the slab's own periodic images (device copy), no collective",
+            "check_e_per_site_over_kT_replica0": float(e_check)}
+
+
 def fp64_state_leg(rank, world, local, barrier_max, spec, Ts, a, peak):
     """The headline workload with fp64 spin state - the reference's own precision, the shims' default (24 B/spin, 72 B per
     attempt) - timed exactly like the headline: W warm-up steps, then K steps of `sweeps` measured sweeps, CUDA events on the
@@ -417,6 +448,7 @@ def main():
     ap.add_argument("--no-pt", action="store_true", help="skip the parallel-tempering leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-wolff", action="store_true")
+    ap.add_argument("--no-slab", action="store_true", help="skip the one-lattice-over-all-GPUs (slab decomposition) leg")
     ap.add_argument("--no-fp64", action="store_true", help="skip the fp64-state leg of the headline workload")
     ap.add_argument("--e2e-sweeps", type=int, default=1000, help="measured sweeps per end-to-end job")
     a = ap.parse_args()
@@ -557,12 +589,19 @@ def main():
         except Exception as e:
             ptres = {"error": str(e)[:300]}
 
+    slab = None
+    if not a.no_slab:
+        try:
+            slab = slab_leg(rank, world, local, barrier_max, a, peak)
+        except Exception as e:
+            slab = {"error": str(e)[:300]}
+
     if rank == 0:
         line = {"metric": "attempted Metropolis spin updates per second", "value": value, "unit": "attempts/s", "n_gpus": world,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_max / a.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(a, world), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roof, "cpu_baseline": cpu, "wolff": wolff, "fp64_state": f64, "configs": configs, "pt": ptres, "host_wall_s": wall,
+                "roofline": roof, "cpu_baseline": cpu, "wolff": wolff, "fp64_state": f64, "configs": configs, "pt": ptres, "slab": slab, "host_wall_s": wall,
                 "check": {"replica0_T": float(Ts[0]), "e_per_site_over_kT": float(out0[8]), "U4": float(out0[10])}}
         emit(line)
     if dist is not None:

@@ -131,6 +131,23 @@ MCG_API int mcg_destroy(mcg_system *sys);
 MCG_API int mcg_jit_check(const mcg_lattice_desc *d, int precision, int *ncompiled, char *report, int report_len);
 MCG_API int mcg_num_colours(const mcg_system *sys, int *ncolours);
 MCG_API int mcg_colour_order(const mcg_system *sys, int32_t *order /*[N] site ids, colour-major*/);
+/* ---- one lattice over several GPUs ("the largest lattice can optionally be domain-decomposed with halo exchange"; the
+ * reference has no decomposition, README.md:99) ----
+ * desc describes the WHOLE lattice (three-dimensional supercell); rank r of world creates the slab of L[0]/world planes it owns plus
+ * one ghost colouring period on either side.  comm_id: mcg_comm_unique_id() of rank 0 (NULL for world == 1).  Metropolis sweeps
+ * (mcg_run, mcg_metropolis_sweeps, mcg_timed_sweeps, mcg_measure, mcg_energy) are collective over the ranks: after every colour
+ * pass the boundary planes travel to the neighbours' ghosts (ncclSend/ncclRecv on the compute stream) and the raw measurement
+ * sums are all-reduced, so mcg_results is the whole lattice's on every rank.  RNG streams are keyed by the global site ids: the
+ * slabs together reproduce the undivided lattice's trajectory bit for bit.  mcg_get_spins / mcg_set_spins address the local
+ * planes, ghosts included (mcg_slab_info: {rank, world, first own x, own planes, ghost planes per side, global L[0]}); after
+ * mcg_set_spins call mcg_slab_sync (collective) to refresh the ghosts.  Not decomposed: Wolff updates, topological charge,
+ * block-spin and orbital-group statistics, int8 state. */
+MCG_API int mcg_create_lattice_slab(const mcg_lattice_desc *desc, const mcg_config *cfg, int rank, int world, const char *comm_id, mcg_system **out);
+MCG_API int mcg_slab_info(const mcg_system *sys, int32_t *info6);
+/* the same six numbers for rank r of world without creating anything (host only): how a lattice would be cut, or why it cannot */
+MCG_API int mcg_slab_plan(const mcg_lattice_desc *desc, int precision, int rank, int world, int32_t *info6);
+MCG_API int mcg_slab_sync(mcg_system *sys);
+
 /* Philox stream layout of the Metropolis sweeps (csrc/rng.cuh), for checkers that restate the trajectory:
  * stride = 0: one block per site (table-built systems, scalar structured pass); stride = S, group = V: the V sites
  * id = base + m*S of one vector item share their blocks. */

@@ -61,6 +61,10 @@ SIGNATURES = {
     "mcg_rng_layout": (_i, [_vp, _vp, _vp]),
     "mcg_set_params": (_i, [_vp, _vp, _vp]),
     "mcg_recycle": (_i, [_vp, _vp, _vp, _u64, _i]),
+    "mcg_create_lattice_slab": (_i, [C.POINTER(LatticeDesc), C.POINTER(Config), _i, _i, _vp, C.POINTER(_vp)]),
+    "mcg_slab_info": (_i, [_vp, _vp]),
+    "mcg_slab_plan": (_i, [C.POINTER(LatticeDesc), _i, _i, _i, _vp]),
+    "mcg_slab_sync": (_i, [_vp]),
     "mcg_init_spins": (_i, [_vp, _d]),
     "mcg_set_spins": (_i, [_vp, _i, _vp]),
     "mcg_get_spins": (_i, [_vp, _i, _vp]),

@@ -424,7 +424,7 @@ static void measure(mcg_system *s) {
     launch_measure_sums(s, -1, nullptr, nullptr);
     launch_extras(s);
     s->launches++;
-    k_finalize_sweep<<<(s->R + 63) / 64, 64, 0, s->stream>>>(s->model, s->R, s->N, s->nLat, s->d_sums, s->d_acc, s->d_slot, s->d_last);
+    k_finalize_sweep<<<(s->R + 63) / 64, 64, 0, s->stream>>>(s->model, s->R, s->normN(), s->normLat(), s->d_sums, s->d_acc, s->d_slot, s->d_last);
     MCG_CUDA(cudaGetLastError());
 }
 
@@ -679,8 +679,9 @@ static void run(mcg_system *s, int algorithm, int64_t nthermal, int64_t nsweep, 
     int64_t nsub = 1;
     double pAtt = 1.0;
     if (algorithm == MCG_METROPOLIS) {
-        if (ninterval >= s->N) nsub = (ninterval + s->N / 2) / s->N;
-        else if (ninterval > 0) pAtt = (double)ninterval / (double)s->N;
+        const int64_t Nw = s->normN();     // sites of the whole lattice (a slab holds a part of it plus ghosts)
+        if (ninterval >= Nw) nsub = (ninterval + Nw / 2) / Nw;
+        else if (ninterval > 0) pAtt = (double)ninterval / (double)Nw;
         else nsub = 0;
     }
     if (!s->structured && !s->profilePasses) {
@@ -707,7 +708,7 @@ static void run(mcg_system *s, int algorithm, int64_t nthermal, int64_t nsweep, 
         }
         if (fused) {
             s->launches++;
-            k_finalize_sweep<<<(s->R + 63) / 64, 64, 0, s->stream>>>(s->model, s->R, s->N, s->nLat, s->d_sums, s->d_acc, s->d_slot, s->d_last);
+            k_finalize_sweep<<<(s->R + 63) / 64, 64, 0, s->stream>>>(s->model, s->R, s->normN(), s->normLat(), s->d_sums, s->d_acc, s->d_slot, s->d_last);
             MCG_CUDA(cudaGetLastError());
         } else measure(s);
         if ((i & 255) == 255) MCG_CUDA(cudaStreamSynchronize(s->stream));   // bound the launch queue
@@ -728,7 +729,7 @@ void results_from(mcg_system *s, const double *accBase, const double *gaccBase, 
     if (s->model == MCG_ISING) {   // isingLib.c:435-446
         out[0] = A[ACC_SI] / ns; out[1] = A[ACC_SJ] / ns; out[2] = A[ACC_SIJ] / ns; out[3] = autoCorr;
         out[4] = A[ACC_E] / ns; out[5] = A[ACC_E2] / ns; out[6] = A[ACC_ER] / ns; out[7] = A[ACC_E2R] / ns;
-        out[8] = U4; out[9] = A[ACC_STOT] / ns / s->nLat;
+        out[8] = U4; out[9] = A[ACC_STOT] / ns / s->normLat();
         return;
     }
     for (int c = 0; c < 3; c++) { out[c] = A[ACC_SI + c] / ns; out[3 + c] = A[ACC_SJ + c] / ns; }
@@ -756,7 +757,7 @@ void measured_sweep(mcg_system *s, double pAtt) {
         s->wolffPrimed = false;
         structured_sweeps(s, 1, pAtt, true);
         s->launches++;
-        k_finalize_sweep<<<(s->R + 63) / 64, 64, 0, s->stream>>>(s->model, s->R, s->N, s->nLat, s->d_sums, s->d_acc, s->d_slot, s->d_last);
+        k_finalize_sweep<<<(s->R + 63) / 64, 64, 0, s->stream>>>(s->model, s->R, s->normN(), s->normLat(), s->d_sums, s->d_acc, s->d_slot, s->d_last);
     } else {
         metropolis_sweeps(s, 1, pAtt);
         measure(s);
@@ -841,6 +842,32 @@ MCG_API int mcg_create_lattice(const mcg_lattice_desc *d, const mcg_config *cfg,
     });
 }
 
+// One lattice cut into `world` slabs along its first axis, one rank per GPU (structured.cu, last section): desc describes the
+// WHOLE lattice, the created system holds this rank's planes plus ghost planes.  Sweeps exchange the boundary planes after every
+// colour pass and all-reduce the raw measurement sums, so every rank accumulates the whole lattice's observables; the
+// trajectory is the undivided lattice's, bit for bit.
+MCG_API int mcg_create_lattice_slab(const mcg_lattice_desc *d, const mcg_config *cfg, int rank, int world, const char *comm_id, mcg_system **out) {
+    return guarded([&] {
+        MCG_REQUIRE(out, "out is NULL");
+        MCG_REQUIRE(d && cfg, "descriptor/config is NULL");
+        MCG_REQUIRE(cfg->precision == 32 || cfg->precision == 64, "slab decomposition: precision 32 or 64");
+        MCG_REQUIRE(cfg->nReplica >= 1, "nReplica must be >= 1");
+        std::unique_ptr<mcg_system> sys(new mcg_system());
+        select_device(cfg, sys.get());
+        sys->prec = cfg->precision; sys->R = cfg->nReplica; sys->seed = cfg->seed; sys->replica0 = (uint32_t)cfg->replica_offset;
+        structured_create_slab(sys.get(), d, rank, world, comm_id);
+        alloc_replica_state(sys.get(), cfg);
+        if (sys->nG > 0) {
+            size_t n = (size_t)(sys->nG + 2) * (sys->nG + 1);
+            sys->d_gacc = dalloc<double>((size_t)sys->R * n);
+            MCG_CUDA(cudaMemset(sys->d_gacc, 0, sizeof(double) * sys->R * n));
+        }
+        MCG_CUDA(cudaStreamCreateWithFlags(&sys->stream, cudaStreamNonBlocking));
+        MCG_CUDA(cudaDeviceSynchronize());
+        *out = sys.release();
+    });
+}
+
 MCG_API int mcg_jit_check(const mcg_lattice_desc *d, int precision, int *ncompiled, char *report, int report_len) {
     return guarded([&] {
         MCG_REQUIRE(d && ncompiled, "NULL argument");
@@ -913,6 +940,27 @@ MCG_API int mcg_recycle(mcg_system *sys, const double *beta, const double *field
         MCG_CUDA(cudaMemcpyAsync(sys->d_beta, sys->beta_host.data(), sizeof(double) * sys->R, cudaMemcpyHostToDevice, sys->stream));
         MCG_CUDA(cudaMemcpyAsync(sys->d_field, sys->field_host.data(), sizeof(double) * sys->R, cudaMemcpyHostToDevice, sys->stream));
         reset_measurements_async(sys);
+        MCG_CUDA(cudaStreamSynchronize(sys->stream));
+    });
+}
+
+MCG_API int mcg_slab_plan(const mcg_lattice_desc *d, int precision, int rank, int world, int32_t *info6) {
+    return guarded([&] {
+        MCG_REQUIRE(d && info6, "NULL argument");
+        structured_slab_plan(d, precision, rank, world, info6);
+    });
+}
+MCG_API int mcg_slab_info(const mcg_system *sys, int32_t *info6) {
+    return guarded([&] {
+        MCG_REQUIRE(sys && info6, "NULL argument");
+        MCG_REQUIRE(sys->structured && structured_is_slab(sys), "not a slab of a decomposed lattice");
+        structured_slab_info(sys, info6);
+    });
+}
+MCG_API int mcg_slab_sync(mcg_system *sys) {
+    SYS_GUARD({
+        MCG_REQUIRE(sys->structured && structured_is_slab(sys), "not a slab of a decomposed lattice");
+        structured_slab_exchange_all(sys);
         MCG_CUDA(cudaStreamSynchronize(sys->stream));
     });
 }

@@ -45,6 +45,10 @@ struct StructArgs {
     double *classSums;
     RngKey key;
     uint32_t replica0;
+    // slab decomposition along X (slab.cu): only the rows [rowLo, rowHi) are updated and measured - the coarse planes outside are
+    // ghosts, copies of the neighbouring ranks' boundary planes - and the reference site ids behind the Philox counters are those
+    // of the GLOBAL lattice: local x + xoff.  Whole lattice on one GPU: rowLo = 0, rowHi = nrows, xoff = 0.
+    int rowLo, rowHi, xoff;
 };
 
 template <typename real, int V> struct Vec;
@@ -456,8 +460,9 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
     };
     int natt = 0, nacc = 0;
 
-    const int rowEnd = min(nrows, (rb + 1) * rowsPerBlock);
-    for (int row = rb * rowsPerBlock + threadIdx.y; row < rowEnd; row += blockDim.y) {
+    const int rowLo = MCG_DIM(a, rowLo), rowHi = MCG_DIM(a, rowHi), xoff = MCG_DIM(a, xoff);
+    const int rowEnd = min(rowHi, rowLo + (rb + 1) * rowsPerBlock);
+    for (int row = rowLo + rb * rowsPerBlock + threadIdx.y; row < rowEnd; row += blockDim.y) {
         const int X = row / Yd, Y = row - X * Yd;
         const int rowBase = ((q * Xd + X) * Yd + Y) * Zd;
         const int wxp = X == Xd - 1 ? -planeX : 0, wxm = X == 0 ? planeX : 0;
@@ -494,7 +499,7 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
             }
         }
 #endif
-        const int xy = ((X * px + cls.ca()) * Ly + (Y * py + cls.cb())) * Lz;
+        const int xy = ((X * px + cls.ca() + xoff) * Ly + (Y * py + cls.cb())) * Lz;
         for (int zc = threadIdx.x; zc < Zc; zc += blockDim.x) {
             const int Z0 = zc * V;
 #ifndef MCG_NO_F32X2

@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "structured.hpp"
+#include "nccl_dl.hpp"
 #include "struct_pass.cuh"
 #include "ising8.cuh"
 #include "topo_pass.cuh"
@@ -81,6 +82,13 @@ struct StructuredSystem {
     int *d_rgNent = nullptr, *d_rgPerm = nullptr;
     double *d_rgJ = nullptr, *d_rgSD = nullptr, *d_ms = nullptr, *d_rsums = nullptr;
     double *d_stage = nullptr;           // [3N] host<->device staging, allocated on demand
+    // slab decomposition along X (slab.cu): rows [rowLo, rowHi) are this rank's own, the coarse planes X = 0 and X = Xd - 1 are
+    // ghosts; xoff = global x of local x = 0; LxGlobal = extent of the whole lattice.  Not decomposed: 0, nrows, 0, L[0].
+    int rowLo = 0, rowHi = 0, xoff = 0, LxGlobal = 0;
+    int slabRank = 0, slabWorld = 0;     // slabWorld == 0: not decomposed
+    void *slabComm = nullptr;            // ncclComm_t of the slab ring (world > 1)
+    void *d_slabBuf = nullptr;           // [4][max elements of one boundary plane set]: send left/right, receive right/left
+    size_t slabBufElems = 0;
 };
 
 __device__ __forceinline__ void split_period(int v, int p, int ps, int &rem, int &quo) {
@@ -103,6 +111,18 @@ __device__ __forceinline__ int struct_site_id(const StructArgs &a, int p) {
     return ((x * a.Ly + y) * a.Lz + z) * a.norb + c.o;
 }
 
+
+// reference id of storage position p in the GLOBAL lattice: a slab's local x is shifted by xoff and wrapped (ghost planes of
+// the first and last slab are periodic images); equal to struct_site_id when the lattice is not decomposed
+__device__ __forceinline__ int struct_site_gid(const StructArgs &a, int p, int LxGlobal) {
+    int q = p / a.ncellc, cell = p - q * a.ncellc;
+    int Z = cell % a.Zd, Y = (cell / a.Zd) % a.Yd, X = cell / (a.Zd * a.Yd);
+    const SClassD &c = a.classes[q];
+    int x = X * a.px + c.a + a.xoff, y = Y * a.py + c.b, z = Z * a.pz + c.c;
+    if (x < 0) x += LxGlobal;
+    if (x >= LxGlobal) x -= LxGlobal;
+    return ((x * a.Ly + y) * a.Lz + z) * a.norb + c.o;
+}
 
 // ---- topology of the structured path for the Wolff kernels (kernels_wolff.cuh) ----
 template <int NC, typename real> struct StructTopo {
@@ -194,11 +214,11 @@ __global__ void __launch_bounds__(256) k_struct(StructArgs a, int q0, int nqc, i
     real accM[3] = {0, 0, 0}, accE = 0;
     int natt = 0, nacc = 0;
 
-    const int rowEnd = min(a.nrows, (rb + 1) * rowsPerBlock);
-    for (int row = rb * rowsPerBlock + threadIdx.y; row < rowEnd; row += blockDim.y) {
+    const int rowEnd = min(a.rowHi, a.rowLo + (rb + 1) * rowsPerBlock);
+    for (int row = a.rowLo + rb * rowsPerBlock + threadIdx.y; row < rowEnd; row += blockDim.y) {
         const int X = row / a.Yd, Y = row - X * a.Yd;
         const int rowBase = ((q * a.Xd + X) * a.Yd + Y) * a.Zd;
-        const int x = X * a.px + sc.a, y = Y * a.py + sc.b;
+        const int x = X * a.px + sc.a + a.xoff, y = Y * a.py + sc.b;   // x: of the global lattice (slab decomposition), for the RNG only
         for (int zc = threadIdx.x; zc < a.Zc; zc += blockDim.x) {
             const int Z0 = zc * V;
             real s[3][V], H[3][V], Hl[3][V];
@@ -638,7 +658,7 @@ __global__ void __launch_bounds__(128) k_struct_rg_sums(StructArgs a, RgS g, int
 }
 
 template <int NC, typename real>
-__global__ void __launch_bounds__(256) k_struct_init(StructArgs a, double flunc) {
+__global__ void __launch_bounds__(256) k_struct_init(StructArgs a, double flunc, int LxGlobal) {
     int r = blockIdx.y;
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.N) return;
@@ -654,7 +674,7 @@ __global__ void __launch_bounds__(256) k_struct_init(StructArgs a, double flunc)
         return;
     }
     uint32_t w[4];
-    rng4(a.key, a.replica0 + r, STREAM_INIT, 0, 0, (uint32_t)struct_site_id(a, p), w);
+    rng4(a.key, a.replica0 + r, STREAM_INIT, 0, 0, (uint32_t)struct_site_gid(a, p, LxGlobal), w);
     double n[3];
     if (sizeof(real) == 4) { float nf[3]; random_dir<NC, float>(w[0], w[1], nf); n[0] = nf[0]; n[1] = nf[1]; n[2] = nf[2]; }
     else random_dir<NC, double>(w[0], w[1], n);
@@ -820,6 +840,7 @@ std::string jit_prologue(const mcg_system *s, int colour, bool partial) {
       << st->Zd / st->V << "\n#define JIT_N " << s->N << "\n#define JIT_px " << st->p[0] << "\n#define JIT_py " << st->p[1]
       << "\n#define JIT_pz " << st->p[2] << "\n#define JIT_norb " << st->norb << "\n#define JIT_Ly " << st->L[1]
       << "\n#define JIT_Lz " << st->L[2] << "\n#define JIT_nrows " << st->nrows << "\n#define JIT_nclass " << st->nclass << "\n";
+    o << "#define JIT_rowLo " << st->rowLo << "\n#define JIT_rowHi " << st->rowHi << "\n#define JIT_xoff " << st->xoff << "\n";
     o << "namespace mcg {\ntemplate <int J, int K> struct CtLinkData;\ntemplate <int J> struct CtClassData;\n";
     for (int j = 0; j < nqc; j++) {
         const SClassD &cl = st->classes[q0 + j];
@@ -1117,10 +1138,16 @@ static StructArgs struct_args(const mcg_system *s) {
     a.spin = s->d_spin; a.beta = s->d_beta; a.field = s->d_field; a.cnt = s->d_cnt; a.classSums = st->d_classSums;
     a.key = make_rng_key(s->seed);
     a.replica0 = s->replica0;
+    a.rowLo = st->rowLo; a.rowHi = st->rowHi; a.xoff = st->xoff;
     return a;
 }
 
-static void structured_build_host(mcg_system *s, const mcg_lattice_desc *d, std::vector<SLinkD> &links, std::vector<double> &Jt) {
+// plan of a slab decomposition along X: the descriptor handed to structured_build_host is the LOCAL lattice (own planes plus one
+// ghost coarse cell on either side), coloured with the period of the whole lattice
+struct SlabPlan { int rank, world, period[3], LxGlobal; };
+
+static void structured_build_host(mcg_system *s, const mcg_lattice_desc *d, std::vector<SLinkD> &links, std::vector<double> &Jt,
+                                  const SlabPlan *plan = nullptr) {
     MCG_REQUIRE(d->model >= 1 && d->model <= 3, "model must be 1, 2 or 3");
     MCG_REQUIRE(d->norb >= 1 && d->S, "norb/S invalid");
     for (int k = 0; k < 3; k++) MCG_REQUIRE(d->L[k] >= 1, "supercell dims must be >= 1");
@@ -1192,8 +1219,9 @@ static void structured_build_host(mcg_system *s, const mcg_lattice_desc *d, std:
     }
 
     // ---- colouring period search ----
-    auto candidates = [&](int Ld) {
+    auto candidates = [&](int Ld, int ax) {
         std::vector<int> c;
+        if (plan) { c.push_back(plan->period[ax]); return c; }   // a slab is coloured like the whole lattice
         if (Ld == 1) { c.push_back(1); return c; }
         for (int p = 1; p <= 6; p++) if (Ld % p == 0) c.push_back(p);
         if (Ld > 6 && Ld <= 16) c.push_back(Ld);
@@ -1201,7 +1229,8 @@ static void structured_build_host(mcg_system *s, const mcg_lattice_desc *d, std:
     };
     int best[3] = {0, 0, 0}, bestC = 1 << 30, bestN = 1 << 30;
     std::vector<int> bestColour;
-    for (int px : candidates(L[0])) for (int py : candidates(L[1])) for (int pz : candidates(L[2])) {
+    const std::vector<int> candX = candidates(L[0], 0), candY = candidates(L[1], 1), candZ = candidates(L[2], 2);
+    for (int px : candX) for (int py : candY) for (int pz : candZ) {
         int ncls = px * py * pz * no;
         if (ncls > 1024) continue;
         auto cid = [&](int a, int b, int c, int o) { return ((a * py + b) * pz + c) * no + o; };
@@ -1238,6 +1267,14 @@ static void structured_build_host(mcg_system *s, const mcg_lattice_desc *d, std:
     st->Xd = L[0] / px; st->Yd = L[1] / py; st->Zd = L[2] / pz;
     st->ncellc = st->Xd * st->Yd * st->Zd;
     st->nrows = st->Xd * st->Yd;
+    st->rowLo = 0; st->rowHi = st->nrows; st->xoff = 0; st->LxGlobal = L[0];
+    if (plan) {
+        MCG_REQUIRE(st->Xd >= 4, "slab too thin: a rank needs at least two coarse planes of its own");
+        st->rowLo = st->Yd; st->rowHi = (st->Xd - 1) * st->Yd;
+        st->LxGlobal = plan->LxGlobal;
+        st->xoff = plan->rank * (plan->LxGlobal / plan->world) - px;
+        st->slabRank = plan->rank; st->slabWorld = plan->world;
+    }
     int Vmax = s->prec == 32 ? 4 : 2;
     st->V = (st->Zd % Vmax == 0) ? Vmax : 1;
     if (s->prec == 8) {   // int8 Ising items: 16 sites (one 16-byte load) or 4 (one word)
@@ -1544,10 +1581,10 @@ static void structured_build_host(mcg_system *s, const mcg_lattice_desc *d, std:
     s->st = stp.release();
 }
 
-void structured_create(mcg_system *s, const mcg_lattice_desc *d) {
+static void structured_create_impl(mcg_system *s, const mcg_lattice_desc *d, const SlabPlan *plan) {
     std::vector<SLinkD> links;
     std::vector<double> Jt;
-    structured_build_host(s, d, links, Jt);
+    structured_build_host(s, d, links, Jt, plan);
     StructuredSystem *st = s->st;
     // ---- upload ----
     auto up = [&](const void *src, size_t bytes) { void *p = pool_alloc(std::max<size_t>(bytes, 16)); if (bytes) MCG_CUDA(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice)); return p; };
@@ -1595,6 +1632,8 @@ void structured_create(mcg_system *s, const mcg_lattice_desc *d) {
     MCG_CUDA(cudaMemset(st->d_classSums, 0, cs));
     s->d_spin = pool_alloc((size_t)s->R * s->NC * s->N * s->real_size());
 }
+
+void structured_create(mcg_system *s, const mcg_lattice_desc *d) { structured_create_impl(s, d, nullptr); }
 
 // host-only check used by the CPU tests: build the class tables of a descriptor and compile the
 // specialised pass kernels of every colour with NVRTC (no device needed up to the cubin)
@@ -1647,8 +1686,13 @@ void structured_destroy(StructuredSystem *st) {
     if (!st) return;
     void *bufs[] = {st->d_classes, st->d_links, st->d_J, st->d_classOf, st->d_circuits, st->d_classSums, st->d_stage, st->d_tverts, st->d_ttris, st->d_gmask, st->d_rgEnt, st->d_rgNent, st->d_rgPerm, st->d_rgJ, st->d_rgSD, st->d_ms, st->d_rsums, st->d_asTab};
     for (void *b : bufs) pool_free(b);
+    pool_free(st->d_slabBuf);
+    if (st->slabComm && nccl_api().ok) nccl_api().commDestroy((ncclComm_t)st->slabComm);
     delete st;
 }
+
+static void slab_exchange_classes(mcg_system *s, int q0, int nqc);
+static void slab_allreduce_sums(mcg_system *s);
 
 template <typename F> static void sdispatch(const mcg_system *s, F &&f) {
     bool d = s->prec == 64, fj = s->fullJ;
@@ -1669,7 +1713,7 @@ void structured_init_spins(mcg_system *s, double flunc) {
     dim3 g((s->N + 255) / 256, s->R);
     s->launches++;
     if (s->prec == 8) k_i8_init<<<g, 256, 0, s->stream>>>(a);
-    else sdispatch(s, [&]<int NC, typename real, bool FJ>() { k_struct_init<NC, real><<<g, 256, 0, s->stream>>>(a, flunc); });
+    else sdispatch(s, [&]<int NC, typename real, bool FJ>() { k_struct_init<NC, real><<<g, 256, 0, s->stream>>>(a, flunc, s->st->LxGlobal); });
     MCG_CUDA(cudaGetLastError());
 }
 
@@ -1688,6 +1732,8 @@ void structured_set_spins(mcg_system *s, int r, const double *spins) {
     else sdispatch(s, [&]<int NC, typename real, bool FJ>() { k_struct_frame<NC, real, false><<<(s->N + 255) / 256, 256, 0, s->stream>>>(a, r, buf); });
     MCG_CUDA(cudaGetLastError());
     MCG_CUDA(cudaStreamSynchronize(s->stream));
+    // a slab takes its local planes, ghosts included, as given: mcg_slab_sync() brings the ghosts up to date once every rank has
+    // set every replica (it is collective)
 }
 
 void structured_get_spins(mcg_system *s, int r, double *spins) {
@@ -1731,10 +1777,11 @@ template <int MODE> static void launch_pass(mcg_system *s, int colour, uint64_t 
     while (bx < bxTarget && bx < 64) bx <<= 1;
     int by = 256 / bx;
     int iters = 8;
-    auto nblocks = [&](int it) { return (long long)s->R * nqc * ((st->nrows + by * it - 1) / (by * it)); };
+    const int nrowsOwn = st->rowHi - st->rowLo;      // all rows, or this rank's slab of them
+    auto nblocks = [&](int it) { return (long long)s->R * nqc * ((nrowsOwn + by * it - 1) / (by * it)); };
     while (iters > 1 && nblocks(iters) < 2368) iters >>= 1;   // >= 16 blocks per SM on 148 SMs when the lattice allows
     int rowsPerBlock = by * iters;
-    int nrb = (st->nrows + rowsPerBlock - 1) / rowsPerBlock;
+    int nrb = (nrowsOwn + rowsPerBlock - 1) / rowsPerBlock;
     dim3 block(bx, by), grid((unsigned)(s->R * nrb * nqc));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     const bool prof = s->profilePasses && MODE != 2;
@@ -1826,8 +1873,11 @@ static void fold_and_extras(mcg_system *s) {
     StructuredSystem *st = s->st;
     StructArgs a = struct_args(s);
     s->launches++;
-    k_struct_fold<<<s->R, 32, 0, s->stream>>>(a, s->R, s->NC, s->prec, st->pair_s, st->pair_t, st->selfPairs ? 1 : 0, (double)s->nLat, s->d_sums,
+    // a slab folds the sums of its own planes; the all-reduce below makes them the whole lattice's on every rank
+    const double nLatOwn = st->slabWorld ? (double)s->nLatGlobal / st->slabWorld : (double)s->nLat;
+    k_struct_fold<<<s->R, 32, 0, s->stream>>>(a, s->R, s->NC, s->prec, st->pair_s, st->pair_t, st->selfPairs ? 1 : 0, nLatOwn, s->d_sums,
                                                           s->nG, st->d_gmask, st->groupInSC ? 1 : 0, s->d_gacc, s->d_slot);
+    slab_allreduce_sums(s);
     if (!st->selfPairs) {
         dim3 g((s->nLat + 255) / 256, s->R);
         s->launches++;
@@ -1861,6 +1911,7 @@ static void fold_and_extras(mcg_system *s) {
 
 int structured_wolff_step(mcg_system *s, const WolffArgs &w, bool primed, bool needResidual, int force) {
     MCG_REQUIRE(s->prec != 8, "Wolff updates run on fp32/fp64 state: create the system with precision 32");
+    MCG_REQUIRE(!s->st->slabWorld, "Wolff updates are not decomposed over slabs: run them on one GPU");
     StructArgs a = struct_args(s);
     int launches = 0;
     sdispatch(s, [&]<int NC, typename real, bool FJ>() {
@@ -1888,6 +1939,8 @@ void structured_sweeps(mcg_system *s, int64_t n, double pAtt, bool fusedMeasure)
         for (int c = 0; c < s->C; c++) {
             if (last && fuse) launch_pass<1>(s, c, s->sweepCtr, pAtt);
             else launch_pass<0>(s, c, s->sweepCtr, pAtt);
+            // slab decomposition: the neighbours' ghosts of the classes just written, before any other colour reads them
+            if (s->st->slabWorld) slab_exchange_classes(s, s->st->colourClassStart[c], s->st->colourClassStart[c + 1] - s->st->colourClassStart[c]);
         }
         s->sweepCtr++;
     }
@@ -1895,6 +1948,165 @@ void structured_sweeps(mcg_system *s, int64_t n, double pAtt, bool fusedMeasure)
     if (fusedMeasure) {
         if (fuse) fold_and_extras(s);
         else structured_measure_sums(s);
+    }
+}
+
+
+// =============================================================================================
+// Slab decomposition of ONE lattice along X over the ranks of a node (SURVEY 8e "largest lattice", optional in the reference's
+// terms: it has no decomposition at all, README.md:99).  Every rank holds Lx/world planes of its own plus one ghost coarse cell
+// (px planes) on either side; a colour pass updates the own rows only, then the two boundary coarse planes of the classes it
+// just wrote travel to the neighbours' ghosts (ncclSend/ncclRecv on the compute stream, one message per direction; one rank:
+// the periodic images are copied in place).  The Philox counters are keyed by the GLOBAL reference site ids, so the slabs
+// together perform - bit for bit - the trajectory the undivided lattice performs on one GPU (tests/test_gpu_slab.py).  The raw
+// measurement sums are all-reduced before the non-linear fold, so every rank accumulates the observables of the whole lattice.
+// =============================================================================================
+template <typename real>
+static __global__ void __launch_bounds__(256) k_slab_pack(const real *__restrict__ spin, real *__restrict__ toLeft, real *__restrict__ toRight, int R, int NC,
+                                                          size_t N, int q0, int nqc, int Xd, int plane) {
+    const size_t total = (size_t)R * NC * nqc * plane;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e % plane);
+        size_t t = e / plane;
+        const int j = (int)(t % nqc); t /= nqc;
+        const int c = (int)(t % NC), r = (int)(t / NC);
+        const real *base = spin + ((size_t)r * NC + c) * N + (size_t)(q0 + j) * Xd * plane;
+        toLeft[e] = base[(size_t)plane + i];                  // first own coarse plane
+        toRight[e] = base[(size_t)(Xd - 2) * plane + i];      // last own coarse plane
+    }
+}
+// fromRight: the right neighbour's first own plane -> ghost X = Xd-1;  fromLeft: the left neighbour's last own plane -> ghost X = 0.
+// SELF (one rank): both neighbours are this rank, the periodic images are read straight from the own planes.
+template <typename real, bool SELF>
+static __global__ void __launch_bounds__(256) k_slab_unpack(real *__restrict__ spin, const real *__restrict__ fromRight, const real *__restrict__ fromLeft, int R,
+                                                            int NC, size_t N, int q0, int nqc, int Xd, int plane) {
+    const size_t total = (size_t)R * NC * nqc * plane;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e % plane);
+        size_t t = e / plane;
+        const int j = (int)(t % nqc); t /= nqc;
+        const int c = (int)(t % NC), r = (int)(t / NC);
+        real *base = spin + ((size_t)r * NC + c) * N + (size_t)(q0 + j) * Xd * plane;
+        base[(size_t)(Xd - 1) * plane + i] = SELF ? base[(size_t)plane + i] : fromRight[e];
+        base[i] = SELF ? base[(size_t)(Xd - 2) * plane + i] : fromLeft[e];
+    }
+}
+
+// ghost planes of the classes [q0, q0 + nqc) - one colour, or all classes - brought up to date; stream-ordered, no host sync
+static void slab_exchange_classes(mcg_system *s, int q0, int nqc) {
+    StructuredSystem *st = s->st;
+    if (!st->slabWorld || nqc == 0) return;
+    const int plane = st->Yd * st->Zd;
+    const size_t total = (size_t)s->R * s->NC * nqc * plane;
+    const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+    const size_t rs = s->real_size();
+    s->launches++;
+    if (st->slabWorld == 1) {
+        if (s->prec == 32) k_slab_unpack<float, true><<<grid, 256, 0, s->stream>>>((float *)s->d_spin, nullptr, nullptr, s->R, s->NC, (size_t)s->N, q0, nqc, st->Xd, plane);
+        else k_slab_unpack<double, true><<<grid, 256, 0, s->stream>>>((double *)s->d_spin, nullptr, nullptr, s->R, s->NC, (size_t)s->N, q0, nqc, st->Xd, plane);
+        MCG_CUDA(cudaGetLastError());
+        return;
+    }
+    MCG_REQUIRE(total <= st->slabBufElems, "slab exchange buffer too small");
+    char *buf = (char *)st->d_slabBuf;
+    void *toLeft = buf, *toRight = buf + st->slabBufElems * rs, *fromRight = buf + 2 * st->slabBufElems * rs, *fromLeft = buf + 3 * st->slabBufElems * rs;
+    if (s->prec == 32) k_slab_pack<float><<<grid, 256, 0, s->stream>>>((const float *)s->d_spin, (float *)toLeft, (float *)toRight, s->R, s->NC, (size_t)s->N, q0, nqc, st->Xd, plane);
+    else k_slab_pack<double><<<grid, 256, 0, s->stream>>>((const double *)s->d_spin, (double *)toLeft, (double *)toRight, s->R, s->NC, (size_t)s->N, q0, nqc, st->Xd, plane);
+    NcclApi &api = nccl_api();
+    ncclComm_t comm = (ncclComm_t)st->slabComm;
+    const int W = st->slabWorld, left = (st->slabRank + W - 1) % W, right = (st->slabRank + 1) % W;
+    // a pair of ranks matches its messages in order: with two ranks the neighbour's "to its left" arrives first, which is this
+    // rank's right ghost - hence receive-from-right before receive-from-left
+    MCG_NCCL(api.groupStart());
+    MCG_NCCL(api.send(toLeft, total * rs, ncclChar, left, comm, s->stream));
+    MCG_NCCL(api.send(toRight, total * rs, ncclChar, right, comm, s->stream));
+    MCG_NCCL(api.recv(fromRight, total * rs, ncclChar, right, comm, s->stream));
+    MCG_NCCL(api.recv(fromLeft, total * rs, ncclChar, left, comm, s->stream));
+    MCG_NCCL(api.groupEnd());
+    s->launches++;
+    if (s->prec == 32) k_slab_unpack<float, false><<<grid, 256, 0, s->stream>>>((float *)s->d_spin, (const float *)fromRight, (const float *)fromLeft, s->R, s->NC, (size_t)s->N, q0, nqc, st->Xd, plane);
+    else k_slab_unpack<double, false><<<grid, 256, 0, s->stream>>>((double *)s->d_spin, (const double *)fromRight, (const double *)fromLeft, s->R, s->NC, (size_t)s->N, q0, nqc, st->Xd, plane);
+    MCG_CUDA(cudaGetLastError());
+}
+
+void structured_slab_exchange_all(mcg_system *s) { slab_exchange_classes(s, 0, s->st->nclass); }
+bool structured_is_slab(const mcg_system *s) { return s->st && s->st->slabWorld > 0; }
+void structured_slab_info(const mcg_system *s, int32_t *info) {
+    const StructuredSystem *st = s->st;
+    const int px = st->p[0];
+    info[0] = st->slabRank; info[1] = st->slabWorld; info[2] = st->xoff + px;   // first own global x
+    info[3] = (st->Xd - 2) * px;                                                 // own planes
+    info[4] = px;                                                                // ghost planes on either side
+    info[5] = st->LxGlobal;
+}
+
+// raw per-sweep sums of the own rows -> sums of the whole lattice on every rank
+static void slab_allreduce_sums(mcg_system *s) {
+    StructuredSystem *st = s->st;
+    if (st->slabWorld <= 1) return;
+    MCG_NCCL(nccl_api().allReduce(s->d_sums, s->d_sums, (size_t)s->R * NSUM, ncclDouble, ncclSum, (ncclComm_t)st->slabComm, s->stream));
+}
+
+// host-only: how the whole lattice is cut (no device needed): {rank, world, first own x, own planes, ghost planes per side, L[0]}
+static SlabPlan slab_plan(const mcg_lattice_desc *global, int precision, int device, int rank, int world);
+void structured_slab_plan(const mcg_lattice_desc *global, int precision, int rank, int world, int32_t *info) {
+    const SlabPlan p = slab_plan(global, precision, 0, rank, world);
+    const int own = p.LxGlobal / world;
+    info[0] = rank; info[1] = world; info[2] = rank * own; info[3] = own; info[4] = p.period[0]; info[5] = p.LxGlobal;
+}
+
+static SlabPlan slab_plan(const mcg_lattice_desc *global, int precision, int device, int rank, int world) {
+    MCG_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad slab rank/world");
+    MCG_REQUIRE(precision == 32 || precision == 64, "slab decomposition: fp32 or fp64 state");
+    MCG_REQUIRE(global->L[0] > 1 && global->L[1] > 1 && global->L[2] > 1, "slab decomposition is for three-dimensional supercells (it cuts the first axis)");
+    MCG_REQUIRE(global->ncircuit == 0 && !global->block_spin, "slab decomposition: topological charge and block-spin statistics are not decomposed - run them on one GPU");
+    MCG_REQUIRE(global->pair_s == global->pair_t && global->pair_d[0] == 0 && global->pair_d[1] == 0 && global->pair_d[2] == 0,
+                "slab decomposition: the correlated pair must be a site with itself (the default)");
+    // period of the whole lattice: the slabs must be coloured exactly like it
+    SlabPlan plan;
+    {
+        mcg_system tmp;
+        tmp.prec = precision; tmp.R = 1;
+        tmp.device = device;          // its destructor selects its device
+        std::vector<SLinkD> l; std::vector<double> j;
+        structured_build_host(&tmp, global, l, j);
+        for (int k = 0; k < 3; k++) plan.period[k] = tmp.st->p[k];
+        MCG_REQUIRE(tmp.st->V > 1, "slab decomposition needs vector items (innermost coarse dimension a multiple of 4, fp64: 2)");
+        for (int c = 0; c < tmp.C; c++) MCG_REQUIRE(tmp.st->fastOK[c], "slab decomposition needs bonds that reach at most one colouring period along every axis");
+    }
+    const int px = plan.period[0], Lx = global->L[0];
+    MCG_REQUIRE(Lx % world == 0 && (Lx / world) % px == 0 && Lx / world >= 2 * px, "the first supercell dimension must split into equal slabs of whole colouring periods, two or more per rank");
+    plan.rank = rank; plan.world = world; plan.LxGlobal = Lx;
+    return plan;
+}
+
+void structured_create_slab(mcg_system *s, const mcg_lattice_desc *global, int rank, int world, const char *commId) {
+    const SlabPlan plan = slab_plan(global, s->prec, s->device, rank, world);
+    const int px = plan.period[0], Lx = global->L[0];
+    mcg_lattice_desc local = *global;
+    local.L[0] = Lx / world + 2 * px;
+    local.ngroup = 0;      // orbital-group statistics are products of sums: not decomposed
+    structured_create_impl(s, &local, &plan);
+    StructuredSystem *st = s->st;
+    MCG_REQUIRE(!st->hasSelf, "slab decomposition: bonds of a site with its own periodic image are not supported");
+    // observables are those of the whole lattice
+    s->nLatGlobal = s->nLat / (st->Xd * px) * Lx;
+    s->NGlobal = s->N / (st->Xd * px) * Lx;
+    if (world > 1) {
+        MCG_REQUIRE(commId, "slab decomposition over several ranks needs the communicator id (mcg_comm_unique_id on rank 0)");
+        NcclApi &api = nccl_api();
+        if (!api.ok) throw Error(MCG_ERR_NCCL, api.why);
+        ncclUniqueId u;
+        memcpy(&u, commId, sizeof u);
+        ncclComm_t comm = nullptr;
+        MCG_CUDA(cudaSetDevice(s->device));
+        MCG_NCCL(api.commInitRank(&comm, world, u, rank));
+        st->slabComm = comm;
+        int maxq = 0;
+        for (int c = 0; c < s->C; c++) maxq = std::max(maxq, st->colourClassStart[c + 1] - st->colourClassStart[c]);
+        maxq = std::max(maxq, st->nclass);      // the initial exchange moves every class at once
+        st->slabBufElems = (size_t)s->R * s->NC * maxq * st->Yd * st->Zd;
+        st->d_slabBuf = pool_alloc(4 * st->slabBufElems * s->real_size());
     }
 }
 

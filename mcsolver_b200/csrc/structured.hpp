@@ -17,4 +17,10 @@ struct WolffArgs;
 int structured_wolff_step(mcg_system *s, const WolffArgs &w, bool primed, bool needResidual, int force);   // returns kernels launched
 uint64_t structured_jit_key(const mcg_system *s, int colour);   // cache key (= cubin file name) of a colour's specialised module
 int structured_jit_check(const mcg_lattice_desc *d, int precision, std::string &report);
+// slab decomposition of one lattice along its first axis (structured.cu, last section)
+void structured_create_slab(mcg_system *s, const mcg_lattice_desc *global, int rank, int world, const char *commId);
+void structured_slab_plan(const mcg_lattice_desc *global, int precision, int rank, int world, int32_t *info);
+void structured_slab_exchange_all(mcg_system *s);
+bool structured_is_slab(const mcg_system *s);
+void structured_slab_info(const mcg_system *s, int32_t *info);
 }  // namespace mcg

@@ -59,6 +59,9 @@ struct mcg_system {
     std::vector<double> S_host;          // [N] signed S in reference order
     // measurement tables
     int nLat = 0, nTri = 0, nG = 0, maxG = 0, nR = 0, nC = 0;
+    int NGlobal = 0, nLatGlobal = 0;     // slab decomposition: sites / cells of the WHOLE lattice (0: this system is the whole lattice)
+    int normN() const { return NGlobal ? NGlobal : N; }
+    int normLat() const { return nLatGlobal ? nLatGlobal : nLat; }
     bool selfPairs = false;
     bool dupLinks = false;
     // device buffers (generic path)

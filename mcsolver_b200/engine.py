@@ -160,6 +160,37 @@ class System:
         check(_ffi.lib().mcg_create_lattice(C.byref(d), C.byref(cfg), C.byref(h)))
         return cls(h, int(model), spec.nsite, nReplica, len(spec.groups) if model != ISING else 0)
 
+    @classmethod
+    def from_spec_slab(cls, spec, model, rank, world, comm_id=None, precision=32, nReplica=1, beta=None, field=None, seed=1,
+                       replica_offset=0, device=-1):
+        """This rank's slab of ONE lattice cut along its first axis over `world` ranks (mcg_create_lattice_slab): spec is the
+        whole lattice, comm_id the bytes of mcsolver_b200.pt.comm_id(rank, world) (None for world == 1).  Sweeps, measurements
+        and energy() are collective; results() are the whole lattice's on every rank.  self.N counts the local planes, ghost
+        planes included (slab_info())."""
+        keep = []
+        d = cls._desc(spec, model, keep, False)
+        cfg = _config(precision, nReplica, beta, field, seed, replica_offset, device, keep)
+        h = C.c_void_p()
+        idbuf = C.create_string_buffer(comm_id, len(comm_id)) if comm_id else None
+        check(_ffi.lib().mcg_create_lattice_slab(C.byref(d), C.byref(cfg), int(rank), int(world), idbuf, C.byref(h)))
+        info = (C.c_int32 * 6)()
+        check(_ffi.lib().mcg_slab_info(h, info))
+        nloc = (info[3] + 2 * info[4]) * spec.L[1] * spec.L[2] * spec.norb
+        obj = cls(h, int(model), nloc, nReplica, len(spec.groups) if model != ISING else 0)
+        obj.slab = dict(rank=info[0], world=info[1], x0=info[2], nx=info[3], ghost=info[4], Lx=info[5], Ly=spec.L[1], Lz=spec.L[2], norb=spec.norb)
+        return obj
+
+    def slab_sync(self):
+        """collective: refresh the ghost planes from the neighbouring slabs (after set_spins)"""
+        check(_ffi.lib().mcg_slab_sync(self._h))
+
+    def own_spins(self, replica=0):
+        """a slab's own planes (ghosts stripped) in reference order: rows x0 .. x0+nx of the whole lattice's get_spins()"""
+        sl = self.slab
+        per_x = sl["Ly"] * sl["Lz"] * sl["norb"]
+        sp = self.get_spins(replica)
+        return sp[sl["ghost"] * per_x:(sl["ghost"] + sl["nx"]) * per_x]
+
     def close(self):
         if self._h is not None:
             _ffi.lib().mcg_destroy(self._h)
@@ -305,6 +336,16 @@ class System:
 # ---------------------------------------------------------------------------------------------
 # legacy one-shot calls: positional tuples in, reference-layout tuples out
 # ---------------------------------------------------------------------------------------------
+def slab_plan(spec, model, rank, world, precision=32):
+    """How mcg_create_lattice_slab would cut the lattice for rank `rank` of `world` (host only, no GPU): dict(x0, nx, ghost, Lx);
+    raises McgError when the lattice cannot be cut that way."""
+    keep = []
+    d = System._desc(spec, model, keep, False)
+    info = (C.c_int32 * 6)()
+    check(_ffi.lib().mcg_slab_plan(C.byref(d), int(precision), int(rank), int(world), info))
+    return dict(rank=info[0], world=info[1], x0=info[2], nx=info[3], ghost=info[4], Lx=info[5])
+
+
 def jit_check(spec, model, precision=32, block_spin=False):
     """Host-only: build the class tables of a lattice (incl. the block-spin tables when asked) and NVRTC-compile its
     specialised pass kernels; returns (n_modules, report)."""

@@ -1,0 +1,133 @@
+"""Slab decomposition of one lattice along its first axis (mcg_create_lattice_slab; SURVEY 8e, optional in the reference's terms -
+it has no decomposition, README.md:99).  The slabs' Philox counters are keyed by the global site ids and their ghost planes are
+refreshed after every colour pass, so together they must perform the undivided lattice's trajectory bit for bit, and every rank
+must accumulate the whole lattice's observables."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from tests.specs import spec_of
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CASES = [("cubic", (16, 8, 8), 3, 0.0, 64), ("cubic", (16, 8, 16), 3, 0.3, 32), ("cubic", (8, 8, 8), 2, 0.0, 64), ("aniso", (8, 6, 8), 3, 0.2, 64),
+         ("cubic", (32, 32, 64), 3, 0.0, 32), ("cubic", (16, 16, 16), 1, 0.1, 32)]
+IDS = ["%s-%s-m%d-fp%d" % (c[0], "x".join(map(str, c[1])), c[2], c[4]) for c in CASES]
+
+
+def _whole(spec, model, prec, T, H, flunc, nth, nsw):
+    from mcsolver_b200 import engine
+    R = len(T)
+    with engine.System.from_spec(spec, model, precision=prec, nReplica=R, beta=1 / T, field=H, seed=5) as s:
+        s.init_spins(flunc)
+        s.run(0, nth, nsw, spec.nsite)
+        return [s.get_spins(r) for r in range(R)], np.stack([s.results(r)[0] for r in range(R)]), [s.counters(r) for r in range(R)], s.energy(0)
+
+
+@pytest.mark.parametrize("case", CASES, ids=IDS)
+def test_one_rank_slab_with_ghost_planes_reproduces_the_whole_lattice(case, monkeypatch):
+    """world = 1: the slab owns every plane, its ghosts are its own periodic images - the row range, the ghost refresh after
+    every colour pass, the global-id Philox counters and the folded sums are all in play on one GPU.  JIT on: the specialised
+    kernels (literal row range and x offset) are the ones that run at size."""
+    from mcsolver_b200 import engine
+    name, L, model, h, prec = case
+    monkeypatch.setenv("MCG_JIT", "1")
+    spec = spec_of(name, L, circuits=[], pair=(0, 0, (0, 0, 0))) if name == "aniso" else spec_of(name, L)
+    T = np.array([0.8, 1.5, 3.0]) * (1.0 if model != 1 else 3.0)
+    H = np.full(3, h)
+    flunc = 0.0 if model == 1 else 0.6
+    sp, rows, cnt, E = _whole(spec, model, prec, T, H, flunc, 3, 6)
+    with engine.System.from_spec_slab(spec, model, 0, 1, precision=prec, nReplica=3, beta=1 / T, field=H, seed=5) as s:
+        assert s.slab["nx"] == L[0] and s.slab["x0"] == 0
+        s.init_spins(flunc)
+        s.run(0, 3, 6, spec.nsite)
+        for r in range(3):
+            assert np.array_equal(s.own_spins(r), sp[r]), r
+            assert s.counters(r) == cnt[r]
+        got = np.stack([s.results(r)[0] for r in range(3)])
+        assert np.max(np.abs(got - rows) / np.maximum(1.0, np.abs(rows))) < (1e-11 if prec == 64 else 2e-6)
+        assert abs(s.energy(0) - E) <= (1e-11 if prec == 64 else 2e-6) * abs(E)
+        if s.rng_layout()[1] > 1:
+            assert s.jit_launch_count() > 0
+
+
+def test_slab_refuses_what_is_not_decomposed():
+    from mcsolver_b200 import engine
+    with pytest.raises(engine.McgError):
+        engine.System.from_spec_slab(spec_of("square", (16, 16, 1)), 2, 0, 1)            # two-dimensional supercell
+    with pytest.raises(engine.McgError):
+        engine.System.from_spec_slab(spec_of("cubic", (6, 8, 8)), 3, 0, 4)               # 6 planes do not split over 4 ranks
+    with engine.System.from_spec_slab(spec_of("cubic", (8, 8, 8)), 3, 0, 1, precision=32) as s:
+        s.init_spins(0.0)
+        with pytest.raises(engine.McgError):
+            s.wolff_steps(1)
+
+
+WORKER = r'''
+import json, os, sys
+sys.path.insert(0, os.environ["MCG_ROOT"])
+import numpy as np
+from mcsolver_b200 import engine, pt
+from tests.specs import spec_of
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+prec = int(os.environ["MCG_PREC"])
+spec = spec_of("cubic", (32, 16, 32))
+T = np.array([0.9, 1.44, 2.5]); H = np.array([0.0, 0.1, 0.0])
+cid = pt.comm_id(rank, world)
+with engine.System.from_spec_slab(spec, 3, rank, world, comm_id=cid, precision=prec, nReplica=3, beta=1 / T, field=H, seed=5, device=rank) as s:
+    s.init_spins(0.5)
+    s.run(0, 4, 8, spec.nsite)
+    out = dict(info=s.slab, rows=[s.results(r)[0].tolist() for r in range(3)], counters=[s.counters(r) for r in range(3)],
+               E=s.energy(1), torch_loaded="torch" in sys.modules)
+    np.save(os.environ["MCG_OUT"] + ".%d.npy" % rank, np.stack([s.own_spins(r) for r in range(3)]))
+json.dump(out, open(os.environ["MCG_OUT"] + ".%d.json" % rank, "w"))
+'''
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("prec", [64, 32])
+def test_two_slabs_on_two_gpus_reproduce_the_whole_lattice(prec, tmp_path):
+    """One process per GPU, halo planes over NCCL send/recv after every colour pass, raw sums all-reduced: the two halves,
+    put together, are the single-GPU configuration bit for bit; both ranks report the whole lattice's observables."""
+    from mcsolver_b200 import engine
+    if engine.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    spec = spec_of("cubic", (32, 16, 32))
+    T = np.array([0.9, 1.44, 2.5]); H = np.array([0.0, 0.1, 0.0])
+    sp, rows, cnt, _ = _whole(spec, 3, prec, T, H, 0.5, 4, 8)
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    out = str(tmp_path / "out")
+    port = _free_port()
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, MCG_ROOT=ROOT, MCG_OUT=out, MCG_PREC=str(prec), RANK=str(rank), WORLD_SIZE="2", LOCAL_RANK=str(rank),
+                   MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        o, _ = p.communicate(timeout=600)
+        assert p.returncode == 0, o[-3000:]
+    res = [json.load(open(out + ".%d.json" % r)) for r in range(2)]
+    halves = [np.load(out + ".%d.npy" % r) for r in range(2)]
+    assert not res[0]["torch_loaded"]
+    assert [res[r]["info"]["x0"] for r in range(2)] == [0, 16]
+    for r in range(3):
+        assert np.array_equal(np.concatenate([halves[0][r], halves[1][r]]), sp[r]), r
+        assert tuple(np.add(res[0]["counters"][r], res[1]["counters"][r])) == cnt[r]
+    assert res[0]["rows"] == res[1]["rows"]
+    got = np.array(res[0]["rows"])
+    assert np.max(np.abs(got - rows) / np.maximum(1.0, np.abs(rows))) < (1e-11 if prec == 64 else 2e-6)
+    assert res[0]["E"] == res[1]["E"]

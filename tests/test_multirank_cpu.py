@@ -7,6 +7,7 @@ import subprocess
 import sys
 
 import numpy as np
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -121,3 +122,28 @@ def test_communicator_id_reaches_every_rank_without_torch(tmp_path):
         assert p.returncode == 0, o[-2000:]
     ids = [open(out + ".%d" % r).read() for r in range(world)]
     assert len(set(ids)) == 1 and len(ids[0]) == 64
+
+
+def test_slab_plan_tiles_the_first_axis_for_every_world_size():
+    """Host half of the slab decomposition (mcg_slab_plan, no GPU): for every rank count the slabs tile [0, Lx) without gap or
+    overlap, the ghost width is the colouring period of the WHOLE lattice (the same on every rank), and lattices that cannot be
+    cut into whole periods are refused with a message instead of being cut wrongly."""
+    from mcsolver_b200 import engine
+    from tests.specs import spec_of
+    for name, L, model, prec in (("cubic", (64, 32, 32), 3, 32), ("cubic", (48, 8, 8), 2, 64), ("aniso", (16, 6, 8), 3, 64)):
+        spec = spec_of(name, L, circuits=[], pair=(0, 0, (0, 0, 0)))
+        period = engine.slab_plan(spec, model, 0, 1, precision=prec)["ghost"]
+        for world in (1, 2, 4, 8):
+            if L[0] % world or (L[0] // world) % period or L[0] // world < 2 * period:
+                with pytest.raises(engine.McgError):
+                    engine.slab_plan(spec, model, 0, world, precision=prec)
+                continue
+            plans = [engine.slab_plan(spec, model, r, world, precision=prec) for r in range(world)]
+            assert [p["x0"] for p in plans] == [r * L[0] // world for r in range(world)]
+            assert sum(p["nx"] for p in plans) == L[0] and len({p["ghost"] for p in plans}) == 1
+            assert all(p["nx"] % p["ghost"] == 0 and p["nx"] >= 2 * p["ghost"] for p in plans)
+    for bad, world in (((6, 8, 8), 4), ((16, 16, 1), 2), ((10, 8, 8), 4)):
+        with pytest.raises(engine.McgError):
+            engine.slab_plan(spec_of("cubic" if bad[2] > 1 else "square", bad), 3, 0, world)
+    with pytest.raises(engine.McgError):      # topological charge is not decomposed
+        engine.slab_plan(spec_of("aniso", (16, 6, 8)), 3, 0, 2)
