@@ -1,4 +1,5 @@
-"""Builds libmcsolver_b200.so in-tree with nvcc for sm_100a (no PyTorch, no JIT cache).
+"""Builds libmcsolver_b200.so in-tree with nvcc for sm_100a (no PyTorch).  The NVRTC-specialised modules the library compiles at
+run time are cached as cubins under mcsolver_b200/build/jitcache (pre-filled by __graft_entry__.build()).
 
     python -m mcsolver_b200.build [--force] [--verbose]
 
