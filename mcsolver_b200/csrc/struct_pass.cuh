@@ -460,7 +460,7 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
     };
     int natt = 0, nacc = 0;
 
-    const int rowLo = MCG_DIM(a, rowLo), rowHi = MCG_DIM(a, rowHi), xoff = MCG_DIM(a, xoff);
+    const int rowLo = a.rowLo, rowHi = a.rowHi, xoff = MCG_DIM(a, xoff);   // the row range is a launch argument in both builds
     const int rowEnd = min(rowHi, rowLo + (rb + 1) * rowsPerBlock);
     for (int row = rowLo + rb * rowsPerBlock + threadIdx.y; row < rowEnd; row += blockDim.y) {
         const int X = row / Yd, Y = row - X * Yd;

@@ -87,6 +87,8 @@ struct StructuredSystem {
     int rowLo = 0, rowHi = 0, xoff = 0, LxGlobal = 0;
     int slabRank = 0, slabWorld = 0;     // slabWorld == 0: not decomposed
     void *slabComm = nullptr;            // ncclComm_t of the slab ring (world > 1)
+    cudaStream_t slabStream = nullptr;   // the exchange of a colour's boundary planes runs here, behind the interior rows
+    cudaEvent_t slabEvA = nullptr, slabEvB = nullptr;
     void *d_slabBuf = nullptr;           // [4][max elements of one boundary plane set]: send left/right, receive right/left
     size_t slabBufElems = 0;
 };
@@ -840,7 +842,7 @@ std::string jit_prologue(const mcg_system *s, int colour, bool partial) {
       << st->Zd / st->V << "\n#define JIT_N " << s->N << "\n#define JIT_px " << st->p[0] << "\n#define JIT_py " << st->p[1]
       << "\n#define JIT_pz " << st->p[2] << "\n#define JIT_norb " << st->norb << "\n#define JIT_Ly " << st->L[1]
       << "\n#define JIT_Lz " << st->L[2] << "\n#define JIT_nrows " << st->nrows << "\n#define JIT_nclass " << st->nclass << "\n";
-    o << "#define JIT_rowLo " << st->rowLo << "\n#define JIT_rowHi " << st->rowHi << "\n#define JIT_xoff " << st->xoff << "\n";
+    o << "#define JIT_xoff " << st->xoff << "\n";      // the row range [rowLo, rowHi) is read from the kernel arguments
     o << "namespace mcg {\ntemplate <int J, int K> struct CtLinkData;\ntemplate <int J> struct CtClassData;\n";
     for (int j = 0; j < nqc; j++) {
         const SClassD &cl = st->classes[q0 + j];
@@ -1687,6 +1689,9 @@ void structured_destroy(StructuredSystem *st) {
     void *bufs[] = {st->d_classes, st->d_links, st->d_J, st->d_classOf, st->d_circuits, st->d_classSums, st->d_stage, st->d_tverts, st->d_ttris, st->d_gmask, st->d_rgEnt, st->d_rgNent, st->d_rgPerm, st->d_rgJ, st->d_rgSD, st->d_ms, st->d_rsums, st->d_asTab};
     for (void *b : bufs) pool_free(b);
     pool_free(st->d_slabBuf);
+    if (st->slabStream) { cudaStreamSynchronize(st->slabStream); cudaStreamDestroy(st->slabStream); }
+    if (st->slabEvA) cudaEventDestroy(st->slabEvA);
+    if (st->slabEvB) cudaEventDestroy(st->slabEvB);
     if (st->slabComm && nccl_api().ok) nccl_api().commDestroy((ncclComm_t)st->slabComm);
     delete st;
 }
@@ -1765,9 +1770,12 @@ void structured_colour_order(const mcg_system *s, int32_t *order) {
     }
 }
 
-template <int MODE> static void launch_pass(mcg_system *s, int colour, uint64_t sweep, double pAtt) {
+// rowFrom/rowTo: update only these rows (a slab launches its two boundary planes ahead of its interior); -1 = all own rows
+template <int MODE> static void launch_pass(mcg_system *s, int colour, uint64_t sweep, double pAtt, int rowFrom = -1, int rowTo = -1) {
     StructuredSystem *st = s->st;
     StructArgs a = struct_args(s);
+    if (rowFrom >= 0) { a.rowLo = rowFrom; a.rowHi = rowTo; }
+    if (a.rowHi <= a.rowLo) return;
     int q0 = st->colourClassStart[colour], nqc = st->colourClassStart[colour + 1] - q0;
     if (nqc == 0) return;
     int Zc = st->Zd / st->V;
@@ -1777,7 +1785,7 @@ template <int MODE> static void launch_pass(mcg_system *s, int colour, uint64_t 
     while (bx < bxTarget && bx < 64) bx <<= 1;
     int by = 256 / bx;
     int iters = 8;
-    const int nrowsOwn = st->rowHi - st->rowLo;      // all rows, or this rank's slab of them
+    const int nrowsOwn = a.rowHi - a.rowLo;          // all rows, this rank's slab of them, or a part of the slab
     auto nblocks = [&](int it) { return (long long)s->R * nqc * ((nrowsOwn + by * it - 1) / (by * it)); };
     while (iters > 1 && nblocks(iters) < 2368) iters >>= 1;   // >= 16 blocks per SM on 148 SMs when the lattice allows
     int rowsPerBlock = by * iters;
@@ -1937,10 +1945,33 @@ void structured_sweeps(mcg_system *s, int64_t n, double pAtt, bool fusedMeasure)
     for (int64_t it = 0; it < n; it++) {
         bool last = it == n - 1;
         for (int c = 0; c < s->C; c++) {
-            if (last && fuse) launch_pass<1>(s, c, s->sweepCtr, pAtt);
-            else launch_pass<0>(s, c, s->sweepCtr, pAtt);
-            // slab decomposition: the neighbours' ghosts of the classes just written, before any other colour reads them
-            if (s->st->slabWorld) slab_exchange_classes(s, s->st->colourClassStart[c], s->st->colourClassStart[c + 1] - s->st->colourClassStart[c]);
+            StructuredSystem *st = s->st;
+            const int q0c = st->colourClassStart[c], nqcc = st->colourClassStart[c + 1] - q0c;
+            auto pass = [&](int from, int to) {
+                if (last && fuse) launch_pass<1>(s, c, s->sweepCtr, pAtt, from, to);
+                else launch_pass<0>(s, c, s->sweepCtr, pAtt, from, to);
+            };
+            if (st->slabWorld > 1 && st->Xd >= 6 && !getenv("MCG_SLAB_NO_OVERLAP")) {
+                // slab over several ranks: the two boundary coarse planes first, then their way to the neighbours' ghosts (pack,
+                // ncclSend/ncclRecv, unpack on the side stream) runs behind the interior rows.  No hazard: the interior reads
+                // other colours' planes 1 .. Xd-2 and writes this colour's planes 2 .. Xd-3; the exchange reads this colour's
+                // planes 1 and Xd-2 and writes its ghost planes 0 and Xd-1.
+                pass(st->rowLo, st->rowLo + st->Yd);
+                pass(st->rowHi - st->Yd, st->rowHi);
+                MCG_CUDA(cudaEventRecord(st->slabEvA, s->stream));
+                MCG_CUDA(cudaStreamWaitEvent(st->slabStream, st->slabEvA, 0));
+                cudaStream_t main = s->stream;
+                s->stream = st->slabStream;
+                slab_exchange_classes(s, q0c, nqcc);
+                s->stream = main;
+                MCG_CUDA(cudaEventRecord(st->slabEvB, st->slabStream));
+                pass(st->rowLo + st->Yd, st->rowHi - st->Yd);
+                MCG_CUDA(cudaStreamWaitEvent(s->stream, st->slabEvB, 0));
+            } else {
+                pass(-1, -1);
+                // the neighbours' ghosts of the classes just written, before any other colour reads them
+                if (st->slabWorld) slab_exchange_classes(s, q0c, nqcc);
+            }
         }
         s->sweepCtr++;
     }
@@ -2107,6 +2138,9 @@ void structured_create_slab(mcg_system *s, const mcg_lattice_desc *global, int r
         maxq = std::max(maxq, st->nclass);      // the initial exchange moves every class at once
         st->slabBufElems = (size_t)s->R * s->NC * maxq * st->Yd * st->Zd;
         st->d_slabBuf = pool_alloc(4 * st->slabBufElems * s->real_size());
+        MCG_CUDA(cudaStreamCreateWithFlags(&st->slabStream, cudaStreamNonBlocking));
+        MCG_CUDA(cudaEventCreateWithFlags(&st->slabEvA, cudaEventDisableTiming));
+        MCG_CUDA(cudaEventCreateWithFlags(&st->slabEvB, cudaEventDisableTiming));
     }
 }
 
