@@ -98,13 +98,15 @@ def _free_port():
     return p
 
 
+@pytest.mark.parametrize("world", [2, 4])
 @pytest.mark.parametrize("prec", [64, 32])
-def test_two_slabs_on_two_gpus_reproduce_the_whole_lattice(prec, tmp_path):
-    """One process per GPU, halo planes over NCCL send/recv after every colour pass, raw sums all-reduced: the two halves,
-    put together, are the single-GPU configuration bit for bit; both ranks report the whole lattice's observables."""
+def test_slabs_on_several_gpus_reproduce_the_whole_lattice(prec, world, tmp_path):
+    """One process per GPU, halo planes over NCCL send/recv after every colour pass (two ranks: both neighbours are the same
+    rank; four: distinct left and right neighbours), raw sums all-reduced: the slabs, put together, are the single-GPU
+    configuration bit for bit; every rank reports the whole lattice's observables."""
     from mcsolver_b200 import engine
-    if engine.device_count() < 2:
-        pytest.skip("needs two GPUs")
+    if engine.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
     spec = spec_of("cubic", (32, 16, 32))
     T = np.array([0.9, 1.44, 2.5]); H = np.array([0.0, 0.1, 0.0])
     sp, rows, cnt, _ = _whole(spec, 3, prec, T, H, 0.5, 4, 8)
@@ -113,21 +115,20 @@ def test_two_slabs_on_two_gpus_reproduce_the_whole_lattice(prec, tmp_path):
     out = str(tmp_path / "out")
     port = _free_port()
     procs = []
-    for rank in range(2):
-        env = dict(os.environ, MCG_ROOT=ROOT, MCG_OUT=out, MCG_PREC=str(prec), RANK=str(rank), WORLD_SIZE="2", LOCAL_RANK=str(rank),
+    for rank in range(world):
+        env = dict(os.environ, MCG_ROOT=ROOT, MCG_OUT=out, MCG_PREC=str(prec), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
                    MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
         procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     for p in procs:
         o, _ = p.communicate(timeout=600)
         assert p.returncode == 0, o[-3000:]
-    res = [json.load(open(out + ".%d.json" % r)) for r in range(2)]
-    halves = [np.load(out + ".%d.npy" % r) for r in range(2)]
+    res = [json.load(open(out + ".%d.json" % r)) for r in range(world)]
+    parts = [np.load(out + ".%d.npy" % r) for r in range(world)]
     assert not res[0]["torch_loaded"]
-    assert [res[r]["info"]["x0"] for r in range(2)] == [0, 16]
+    assert [res[r]["info"]["x0"] for r in range(world)] == [r * 32 // world for r in range(world)]
     for r in range(3):
-        assert np.array_equal(np.concatenate([halves[0][r], halves[1][r]]), sp[r]), r
-        assert tuple(np.add(res[0]["counters"][r], res[1]["counters"][r])) == cnt[r]
-    assert res[0]["rows"] == res[1]["rows"]
+        assert np.array_equal(np.concatenate([p[r] for p in parts]), sp[r]), r
+        assert tuple(np.sum([res[k]["counters"][r] for k in range(world)], axis=0)) == cnt[r]
+    assert all(res[k]["rows"] == res[0]["rows"] and res[k]["E"] == res[0]["E"] for k in range(world))
     got = np.array(res[0]["rows"])
     assert np.max(np.abs(got - rows) / np.maximum(1.0, np.abs(rows))) < (1e-11 if prec == 64 else 2e-6)
-    assert res[0]["E"] == res[1]["E"]
