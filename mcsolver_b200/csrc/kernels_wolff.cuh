@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(WF_THREADS) k_wolff_frontier(TOPO topo, WolffA
 }
 
 static __global__ void __launch_bounds__(256) k_wolff_identity(int32_t *parent, size_t n) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) parent[i] = (int32_t)(i % 2147483647);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) parent[i] = (int32_t)i;   // positions are replica-local: n = N < 2^31
 }
 
 // launch sequence of one cluster update, shared by both paths.  primed: the forest/projection buffers of this
