@@ -57,6 +57,26 @@ def test_one_rank_slab_with_ghost_planes_reproduces_the_whole_lattice(case, monk
             assert s.jit_launch_count() > 0
 
 
+@pytest.mark.parametrize("prec", [32, 64])
+def test_one_rank_slab_of_the_dipole_stencil_lattice(prec, monkeypatch):
+    """BASELINE config 5's Hamiltonian (sc + dipole stencil r <= 2: 32 full-tensor links, period 4, 16 colours) as a slab: the ghost
+    is a whole period (4 planes) wide, fp32 runs the asynchronous link pipeline (k_struct_async) over the slab's row range."""
+    from mcsolver_b200 import engine
+    from mcsolver_b200.lattice import add_dipole_stencil
+    spec = add_dipole_stencil(spec_of("cubic", (16, 8, 16)), 0.1, 2.0)
+    T, H = np.array([0.9, 1.6]), np.array([0.0, 0.2])
+    sp, rows, cnt, E = _whole(spec, 3, prec, T, H, 0.5, 2, 4)
+    with engine.System.from_spec_slab(spec, 3, 0, 1, precision=prec, nReplica=2, beta=1 / T, field=H, seed=5) as s:
+        assert s.slab["ghost"] == 4 and s.num_colours() == 16
+        s.init_spins(0.5)
+        s.run(0, 2, 4, spec.nsite)
+        for r in range(2):
+            assert np.array_equal(s.own_spins(r), sp[r]), r
+            assert s.counters(r) == cnt[r]
+        got = np.stack([s.results(r)[0] for r in range(2)])
+        assert np.max(np.abs(got - rows) / np.maximum(1.0, np.abs(rows))) < (1e-11 if prec == 64 else 2e-6)
+
+
 def test_slab_refuses_what_is_not_decomposed():
     from mcsolver_b200 import engine
     with pytest.raises(engine.McgError):
