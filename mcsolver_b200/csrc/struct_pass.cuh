@@ -432,7 +432,7 @@ __device__ __forceinline__ void pass_body(const StructArgs &a, const CLS cls, in
 #endif
     const int Xd = MCG_DIM(a, Xd), Yd = MCG_DIM(a, Yd), Zd = MCG_DIM(a, Zd), Zc = MCG_DIM(a, Zc), N = MCG_DIM(a, N);
     const int px = MCG_DIM(a, px), py = MCG_DIM(a, py), pz = MCG_DIM(a, pz), norb = MCG_DIM(a, norb);
-    const int Ly = MCG_DIM(a, Ly), Lz = MCG_DIM(a, Lz), nrows = MCG_DIM(a, nrows), nclass = MCG_DIM(a, nclass);
+    const int Ly = MCG_DIM(a, Ly), Lz = MCG_DIM(a, Lz), nclass = MCG_DIM(a, nclass);
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     const int lowmode = cls.lowmode();
     const real S = cls.S();

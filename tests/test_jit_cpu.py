@@ -26,7 +26,7 @@ def test_specialised_kernels_compile_for_sm100a(name, L, model, prec, ncol, tmp_
     if ncol is not None:
         assert n == ncol, report
     topo = 1 if (name == "skyrmion" and model == 3) else 0       # + the specialised topological-charge kernel
-    assert ("topological charge: cubin" in report) == bool(topo), report
+    assert ("topological charge: module" in report) == bool(topo), report
     assert n >= 2 and len(os.listdir(tmp_path)) == n + topo     # one cached cubin per colour
 
 
