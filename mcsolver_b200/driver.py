@@ -28,11 +28,43 @@ def _write_out_line(f, model, T, h, r, extra=None):
                 r[17], np.dot(sir, sjr), Er, E2r, r[26]))
 
 
-def loadMC(rpath, precision=None, seed=None, rank=0, world=1, device=-1, workdir=".", table_limit=200000, quiet=False, dipole_rcut=2.0):
+def _gather_rows(workdir, tag, rank, world, payload, timeout=3600.0):
+    """Result rows of all ranks on rank 0, through files in `workdir` (the product has no PyTorch and the grid points are
+    independent: nothing else ever crosses between the ranks of a scan).  Other ranks return None."""
+    mine = os.path.join(workdir, ".mcg_%s_rank%d_of%d.npz" % (tag, rank, world))
+    np.savez(mine + ".tmp.npz", **{k: v for k, v in payload.items() if v is not None})
+    os.replace(mine + ".tmp.npz", mine)
+    if rank != 0:
+        return None
+    parts, t0 = [], time.time()
+    for r in range(world):
+        f = os.path.join(workdir, ".mcg_%s_rank%d_of%d.npz" % (tag, r, world))
+        while not os.path.exists(f):
+            if time.time() - t0 > timeout:
+                raise TimeoutError("rank %d never delivered its rows (%s)" % (r, f))
+            time.sleep(0.05)
+        with np.load(f) as z:
+            parts.append({k: z[k] for k in z.files})
+        os.remove(f)
+    out = {}
+    for k in payload:
+        have = [p[k] for p in parts if k in p]
+        out[k] = np.concatenate(have) if have and len(have) == world else None
+    return out
+
+
+def loadMC(rpath, precision=None, seed=None, rank=None, world=None, device=None, workdir=".", table_limit=200000, quiet=False, dipole_rcut=2.0):
     """Run the simulation described by a reference parameter file.  Returns the result table
-    (dict of columns, as written to result.txt).  With world > 1 each rank runs its share of the
-    grid and returns only its rows; rank 0 should gather and write (see scripts/)."""
+    (dict of columns, as written to result.txt).
+    Several GPUs: start one process per GPU under any launcher that sets RANK / WORLD_SIZE / LOCAL_RANK (torchrun does); each
+    rank runs its contiguous share of the (H,T) grid - the reference's process-pool axis, win.py:90-91 - on GPU LOCAL_RANK, rank 0
+    collects the rows and writes the files; the files are byte for byte those of a one-GPU run (the Philox streams follow the grid
+    point, not the rank)."""
     t0 = time.time()
+    rank = int(os.environ.get("RANK", "0")) if rank is None else rank
+    world = int(os.environ.get("WORLD_SIZE", "1")) if world is None else world
+    if device is None:
+        device = int(os.environ["LOCAL_RANK"]) % max(1, engine.device_count()) if (world > 1 and "LOCAL_RANK" in os.environ) else -1
     p = paramfile.parse(rpath)
     if p.algorithm not in ("Metropolis", "Wolff"):
         raise ValueError("only Metropolis and Wolff algorithm is supported")
@@ -55,6 +87,13 @@ def loadMC(rpath, precision=None, seed=None, rank=0, world=1, device=-1, workdir
                                         seed=sd, rank=rank, world=world, device=device, spin_frames=p.spinFrame, tables=use_tables,
                                         want_groups=True, block_spin=block_spin)
     rows, groups = rows
+    if world > 1:
+        import zlib
+        tag = "%08x" % zlib.crc32(("%s|%d|%d|%d" % (os.path.abspath(rpath), p.nthermal, p.nsweep, len(T))).encode())
+        allr = _gather_rows(workdir, tag, rank, world, dict(idx=idx, rows=rows, groups=groups, frames=frames))
+        if rank != 0:
+            return dict(T=Tf[idx], H=H[idx], rows=rows, **scan.observables(rows, Tf[idx], spec.nsite, model))
+        idx, rows, groups, frames = allr["idx"], allr["rows"], allr["groups"], allr["frames"]
     obs = scan.observables(rows, Tf[idx], spec.nsite, model)
     if rank == 0:
         with open(os.path.join(workdir, "out"), "w") as f:

@@ -92,3 +92,30 @@ def test_field_sweep_carries_the_configuration_and_shows_hysteresis():
     # loop opens around H = 0: the descending branch stays magnetised where the ascending one is not yet
     k0 = 6
     assert m_down[k0] - m_up[k0] > 0.5
+
+
+def test_loadmc_sharded_over_ranks_writes_the_one_gpu_files(tmp_path):
+    """One process per rank (RANK / WORLD_SIZE / LOCAL_RANK as a launcher sets them; the GPU index wraps, so a one-GPU box runs both
+    ranks on its GPU): each rank runs its share of the field scan, rank 0 collects the rows through files and writes result.txt,
+    out, spinDotSpin.txt and the frames - byte for byte what a single process writes (streams follow the grid point, not the rank)."""
+    import os
+    import subprocess
+    import sys
+    import mcsolver_b200
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    f = tmp_path / "Skyrmion"
+    f.write_text(paramfiles.SKYRMION_HEX.format(L=12, H0=0.0, H1=0.6, nH=5, frames=1, nthermal=200, nsweep=400))
+    one, two = tmp_path / "one", tmp_path / "two"
+    one.mkdir(); two.mkdir()
+    mcsolver_b200.loadMC(str(f), workdir=str(one), precision=32, seed=1, quiet=True)
+    code = ("import sys; sys.path.insert(0, %r); import mcsolver_b200; mcsolver_b200.loadMC(%r, workdir=%r, precision=32, seed=1, quiet=True)"
+            % (root, str(f), str(two)))
+    procs = [subprocess.Popen([sys.executable, "-c", code], env=dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    for p in procs:
+        o, _ = p.communicate(timeout=600)
+        assert p.returncode == 0, o[-2000:]
+    names = sorted(p.name for p in one.iterdir())
+    assert names == sorted(p.name for p in two.iterdir()) and "result.txt" in names and len(names) == 3 + 5
+    for n in names:
+        assert (one / n).read_bytes() == (two / n).read_bytes(), n
