@@ -147,3 +147,26 @@ def test_slab_plan_tiles_the_first_axis_for_every_world_size():
             engine.slab_plan(spec_of("cubic" if bad[2] > 1 else "square", bad), 3, 0, world)
     with pytest.raises(engine.McgError):      # topological charge is not decomposed
         engine.slab_plan(spec_of("aniso", (16, 6, 8)), 3, 0, 2)
+
+
+def test_loadmc_row_gather_between_ranks(tmp_path):
+    """driver._gather_rows: the only thing that crosses between the ranks of a sharded loadMC scan - rank 0 receives every rank's
+    block of result rows in rank (= grid) order, optional parts that no rank produced stay None, the exchange files are removed."""
+    import threading
+    from mcsolver_b200 import driver
+    world, got = 3, {}
+
+    def work(rank):
+        rows = np.full((2, 4), float(rank))
+        payload = dict(idx=np.arange(2 * rank, 2 * rank + 2), rows=rows, groups=None, frames=None)
+        got[rank] = driver._gather_rows(str(tmp_path), "t", rank, world, payload, timeout=60.0)
+
+    th = [threading.Thread(target=work, args=(r,)) for r in (2, 0, 1)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert got[1] is None and got[2] is None
+    assert got[0]["idx"].tolist() == [0, 1, 2, 3, 4, 5] and got[0]["rows"][:, 0].tolist() == [0, 0, 1, 1, 2, 2]
+    assert got[0]["groups"] is None and got[0]["frames"] is None
+    assert list(tmp_path.iterdir()) == []
