@@ -372,6 +372,63 @@ def pt_leg(rank, world, local, barrier_max, peak, L=256, R=8, sweeps=40, sps=5):
     return out
 
 
+SHIM_JOB = ("cri3", (32, 32, 1), 40.0, 800, 6400)      # samples/CrI3With2NNCoupling at its own size, sweep counts / 100
+
+
+def _shim_ref_worker(_):
+    """the reference's compiled heisenberglib on the shim job, one host core (runs in a forked child before CUDA is initialised)"""
+    from oracle import refharness as rh
+    from mcsolver_b200.lattice import build_tables
+    from tests.specs import spec_of
+    name, L, T, nth, nsw = SHIM_JOB
+    t = build_tables(spec_of(name, L), T, 3)
+    args = t.on_args(0, nth // 10, nsw // 10, t.N, 0.0, 0.0, 0)     # a tenth of the job: ~0.5 s of CPU
+    t0 = time.time()
+    out = rh.run_ref_engine(3, args, seed=1)
+    return time.time() - t0, t.N * (nth // 10 + nsw // 10), out[8]
+
+
+def shim_ref_sample():
+    if not ref_kind() == "reference":
+        return None
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(processes=1, initializer=_quiet_stdout) as pool:
+        dt, att, e = pool.map(_shim_ref_worker, [0])[0]
+    return {"seconds": dt, "attempts": att, "attempts_per_s": att / dt, "e_per_site_over_kT": e}
+
+
+def shim_leg(ref):
+    """End to end through the reference-facing boundary itself: ONE heisenberglib.MCMainFunction(*args) call of the drop-in module
+    (mcsolver_b200/lib/heisenberglib.py) with the 23 positional arguments mcMain.py:239-248 builds - host tuples in, the 29-item
+    result tuple out, marshalling, upload and download inside the timed call - at the reference's own job size."""
+    from mcsolver_b200.lattice import build_tables
+    from tests.specs import spec_of
+    sys.path.insert(0, os.path.join(ROOT, "mcsolver_b200", "lib"))
+    import heisenberglib
+    name, L, T, nth, nsw = SHIM_JOB
+    t = build_tables(spec_of(name, L), T, 3)
+    args = t.on_args(0, nth, nsw, t.N, 0.0, 0.0, 0)
+    nbytes = sum(np.asarray(x).nbytes for x in args if isinstance(x, (tuple, list)))
+    heisenberglib.MCMainFunction(*t.on_args(0, 10, 20, t.N, 0.0, 0.0, 0))      # context, module load
+    times = []
+    for _ in range(3):
+        t0 = time.time()
+        out = heisenberglib.MCMainFunction(*args)
+        times.append(time.time() - t0)
+    dt = min(times)
+    att = t.N * (nth + nsw)
+    res = {"workload": "samples/CrI3With2NNCoupling: honeycomb 32x32x2 (z = 12, D), T = 40, %d + %d sweeps (the sample's counts / 100), one (T,H) point "
+                       "= one MCMainFunction call, fp64 state (the shim's default)" % (nth, nsw),
+           "seconds_per_call": dt, "value": att / dt, "unit": "attempts/s", "h2d_bytes_per_call": int(nbytes), "d2h_bytes_per_call": 29 * 8,
+           "result_tuple_items": len(out), "e_per_site_over_kT": float(out[8]),
+           "note": "one point occupies one thread block (resident kernel); a scan's points run concurrently on different SMs where the reference "
+                   "runs one process per core"}
+    if ref:
+        res["reference_one_core"] = ref
+        res["speedup_vs_reference_one_core"] = res["value"] / ref["attempts_per_s"]
+    return res
+
+
 def slab_leg(rank, world, local, barrier_max, a, peak, sweeps=40):
     """ONE lattice over all GPUs (SURVEY 8e "largest lattice"): Heisenberg sc (256 N) x 256 x 256 cut into N slabs along x, the same
     8 replicas and 256^3 sites per GPU as the headline.  After every colour pass the boundary planes go to the neighbours' ghost
@@ -481,6 +538,13 @@ def main():
         cpu = {"value": att / eng, "unit": "attempts/s", "cores": cores, "kind": ref_kind(),
                "sample": "reference C engine (oracle/_ref heisenberglib), sc %d^3, %d temperature points x (2+%d) sweeps, one "
                          "process per point, engine-call time %.1f s" % (a.ref_L, cores, a.ref_sweeps, eng)}
+
+    shim_ref = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        try:
+            shim_ref = shim_ref_sample()
+        except Exception:
+            shim_ref = None
 
     dist = None
     if world > 1:
@@ -592,6 +656,13 @@ def main():
         except Exception as e:
             ptres = {"error": str(e)[:300]}
 
+    shim = None
+    if rank == 0 and world == 1 and not a.no_wolff:
+        try:
+            shim = shim_leg(shim_ref)
+        except Exception as e:
+            shim = {"error": str(e)[:300]}
+
     slab = None
     if not a.no_slab:
         try:
@@ -604,7 +675,7 @@ def main():
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_max / a.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(a, world), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roof, "cpu_baseline": cpu, "wolff": wolff, "fp64_state": f64, "configs": configs, "pt": ptres, "slab": slab, "host_wall_s": wall,
+                "roofline": roof, "cpu_baseline": cpu, "wolff": wolff, "fp64_state": f64, "configs": configs, "pt": ptres, "slab": slab, "shim": shim, "host_wall_s": wall,
                 "check": {"replica0_T": float(Ts[0]), "e_per_site_over_kT": float(out0[8]), "U4": float(out0[10])}}
         emit(line)
     if dist is not None:
