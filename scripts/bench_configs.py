@@ -39,7 +39,7 @@ sq = lambda L: LatticeSpec(L=(L, L, 1), S=[1.0], bonds=[(0, 0, (1, 0, 0), J), (0
 cu = lambda L: LatticeSpec(L=(L, L, L), S=[1.0], bonds=[(0, 0, (1, 0, 0), J), (0, 0, (0, 1, 0), J), (0, 0, (0, 0, 1), J)])
 run("C1 XY square 4096^2 T-scan", lambda: sq(4096), 2, 8, np.linspace(0.9, 1.2, 8), z=4)
 run("C2 Ising square 4096^2 T-scan", lambda: sq(4096), 1, 16, np.linspace(2.0, 2.6, 16), z=4)
-run("C3 CrI3 honeycomb 512^2 (1NN+2NN+3NN, D)", lambda: spec_of("cri3", (512, 512, 1)), 3, 21, np.linspace(30, 50, 21), z=12)
+run("C3 CrI3 honeycomb 512^2 (1NN+2NN+3NN, D)", lambda: spec_of("cri3", (512, 512, 1)), 3, int(os.environ.get("C3_R", 64)), np.linspace(30, 50, int(os.environ.get("C3_R", 64))), z=12)
 run("C4 skyrmion hex 1024^2 (DMI, D, h, Q)", lambda: spec_of("skyrmion", (1024, 1024, 1)), 3, 16, np.full(16, 0.3), H=np.linspace(0, 0.7, 16), z=3)
 run("C5 Heisenberg sc 256^3 T-scan", lambda: cu(256), 3, 8, 0.8 * 1.443 * (1.3 / 0.8) ** (np.arange(8) / 7), z=6)
 run("C5 + dipole stencil r<=2 (32 links), 128^3", lambda: add_dipole_stencil(cu(128), 0.1, 2.0), 3, 8, np.linspace(1.2, 1.9, 8), z=32, nsw=4)
