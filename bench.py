@@ -280,10 +280,10 @@ def config_table():
     zero = lambda n: np.zeros(n)
     return [
         ("C1 XY square 4096^2 T-scan", lambda: square_spec(4096), 2, 32, 8, lin(0.9, 1.2), zero, 4, 20),
-        ("C2 Ising square 4096^2 T-scan, int8 state", lambda: square_spec(4096), 1, 8, 16, lin(2.0, 2.6), zero, 4, 20),
-        ("C2 Ising square 4096^2 T-scan, fp32 state", lambda: square_spec(4096), 1, 32, 16, lin(2.0, 2.6), zero, 4, 20),
+        ("C2 Ising square 4096^2 T-scan, int8 state", lambda: square_spec(4096), 1, 8, 32, lin(2.0, 2.6), zero, 4, 20),
+        ("C2 Ising square 4096^2 T-scan, fp32 state", lambda: square_spec(4096), 1, 32, 32, lin(2.0, 2.6), zero, 4, 20),
         ("C3 CrI3 honeycomb 512^2 x 2 (1NN+2NN+3NN, D)", lambda: spec_of("cri3", (512, 512, 1)), 3, 32, 64, lin(30, 50), zero, 12, 40),
-        ("C4 skyrmion hex 1024^2 x 2 (DMI, D, h; Q every sweep)", lambda: spec_of("skyrmion", (1024, 1024, 1)), 3, 32, 16, lambda n: np.full(n, 0.3), lin(0, 0.7), 3, 40),
+        ("C4 skyrmion hex 1024^2 x 2 (DMI, D, h; Q every sweep)", lambda: spec_of("skyrmion", (1024, 1024, 1)), 3, 32, 32, lambda n: np.full(n, 0.3), lin(0, 0.7), 3, 40),
         ("C5 Heisenberg sc 256^3 T-scan, fp64 state", lambda: cubic_spec(256), 3, 64, 8, ladder, zero, 6, 10),
         ("C5 + dipole stencil r<=2 (32 full-tensor links) sc 256^3", lambda: add_dipole_stencil(cubic_spec(256), 0.1, 2.0), 3, 32, 8, ladder, zero, 32, 8),
     ]
