@@ -574,6 +574,7 @@ def main():
     s.profile_passes(True)
     module_key = s.jit_module_key(1) if s.jit_launch_count() > 0 else None     # identity of the kernel the roofline line is about
     l0 = s.launch_count()
+    j0 = s.jit_launch_count()
     clocks = ClockSampler(local)
     clocks.start()
     barrier_max(0.0)
@@ -585,6 +586,7 @@ def main():
     t_max = barrier_max(dev_ms / 1e3)
     clk = clocks.stop()
     launches = s.launch_count() - l0
+    jit_launches = s.jit_launch_count() - j0      # of those, launches of the NVRTC-specialised module (cuLaunchKernel of mcg_pass_m1)
     pass_ms, npass = s.profile_read()
     s.profile_passes(False)
     out0 = s.results(0)[0]
@@ -614,7 +616,7 @@ def main():
             "kernel": "mcg_pass_m1 = pass_body<NC=3,float,diagJ,MODE=1 (update + fused measurement),V=4>, NVRTC-specialised for the lattice (struct_pass.cuh)", "bytes_per_attempt": b_alg,
             "attempts_per_launch": attempts_per_launch, "avg_launch_ms": avg_launch_s * 1e3, "launches_timed": npass,
             "kernel_share_of_step": pass_ms / dev_ms, "peak_source": peak_src,
-            "module_key": module_key, "traffic_source": traffic_note,
+            "module_key": module_key, "specialised_kernel_launches_timed": int(jit_launches), "traffic_source": traffic_note,
             "algorithmic_bytes_per_launch": attempts_per_launch * b_alg}
 
     # ---- e2e: whole jobs through the public API, host descriptors in, host result rows out.  The first job creates the system
