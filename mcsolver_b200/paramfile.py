@@ -15,7 +15,6 @@ import numpy as np
 from .lattice import LatticeSpec
 
 VERSION = "3.0"
-_NUM = r"[0-9\.\-]+"
 
 
 @dataclass
@@ -67,56 +66,100 @@ class Params:
         return T, H
 
 
+# ---- the grammar as data -------------------------------------------------------------------------------------------------
+# A section is the LAST line whose first alphabetic word is the key; its values sit on the lines after it (or on the header line
+# itself).  Fixed-shape sections are described here; the three repeated blocks (orbitals, bonds, circuits) and the group list have
+# their own readers below.
+_FLOATS, _INTS, _UNSIGNED, _WORD = r"[0-9\.\-]+", r"[0-9\-]+", r"[0-9]+", None
+_SCALARS = {
+    # attribute(s)                     section        line offset   token pattern   converters
+    ("T0", "T1", "nT"):               ("Temperature",  1,           r"[0-9\.]+",    (float, float, int)),
+    ("H0", "H1", "nH"):               ("Field",        1,           _FLOATS,        (float, float, int)),
+    ("dipoleAlpha",):                 ("Dipole",       1,           _FLOATS,        (float,)),
+    ("nthermal", "nsweep", "ninterval"): ("Sweeps",    1,           _FLOATS,        (int, int, int)),
+    ("spinFrame",):                   ("Distribution", 0,           _UNSIGNED,      (int,)),
+    ("xAxisType",):                   ("XAxis",        1,           _WORD,          (str,)),
+    ("modelType",):                   ("Model",        1,           _WORD,          (str,)),
+    ("algorithm",):                   ("Algorithm",    1,           _WORD,          (str,)),
+    ("ncores",):                      ("Ncores",       1,           _WORD,          (int,)),
+}
+_SECTIONS = ("Lattice", "Supercell", "Orbitals", "Bonds", "Measurement", "OrbGroup", "LocalCircuit") + tuple(v[0] for v in _SCALARS.values())
+
+
+class _Doc:
+    """The non-empty lines of a save file, addressed as (section key, offset)."""
+
+    def __init__(self, text):
+        self.lines = [ln for ln in text.split("\n") if ln]
+        found = re.findall(r"[0-9\.]+", self.lines[0]) if self.lines else []
+        if not found or found[0] != VERSION:
+            raise ValueError("unknown file or version (only support v%s)" % VERSION)
+        self.at = {}
+        for n, ln in enumerate(self.lines):
+            m = re.search(r"[a-zA-Z]+", ln)
+            if m:
+                self.at[m.group(0)] = n          # a later header of the same name wins, as in the reference
+        absent = [k for k in _SECTIONS if not self.at.get(k)]
+        if absent:
+            raise ValueError("cannot find some tags: %s" % ", ".join(absent))
+
+    def line(self, key, offset=0):
+        return self.lines[self.at[key] + offset]
+
+    def tokens(self, key, offset, pattern):
+        return re.findall(pattern, self.line(key, offset))
+
+    def count(self, key, offset):
+        return int(self.tokens(key, offset, _UNSIGNED)[0])
+
+
+def _orbitals(doc):
+    """'orb k: type t spin S pos [x y z] Dx a Dy b Dz c ...' - numbers are positional, the labels are decoration"""
+    S, pos, D = [], [], []
+    for k in range(doc.count("Orbitals", 1)):
+        v = [float(x) for x in doc.tokens("Orbitals", 3 + k, _FLOATS)]
+        S.append(v[2]); pos.append(v[3:6]); D.append(v[6:9])
+    return S, pos, D
+
+
+def _bonds(doc):
+    """'bond k: Jx .. (nine numbers) orb s to orb t over [a b c]' -> [s, t, [a, b, c], J0 .. J8]"""
+    out = []
+    for k in range(doc.count("Bonds", 1)):
+        v = doc.tokens("Bonds", 3 + k, _FLOATS)
+        out.append([int(v[10]), int(v[11]), [int(x) for x in v[12:15]]] + [float(x) for x in v[1:10]])
+    return out
+
+
+def _groups(doc):
+    """'OrbGroup:n' / Supergroup|... / 'groupk orbA-orbB' -> inclusive orbital ranges"""
+    ranges = []
+    for k in range(doc.count("OrbGroup", 0)):
+        _, lo, hi = doc.tokens("OrbGroup", 2 + k, _UNSIGNED)
+        ranges.append(list(range(int(lo), int(hi) + 1)))
+    return ranges, doc.line("OrbGroup", 1) == "Supergroup"
+
+
+def _circuits(doc):
+    """'LocalCircuit per cell: n' then n lines 'id o1 a b c o2 a b c o3 a b c'"""
+    out = []
+    for k in range(doc.count("LocalCircuit", 0)):
+        v = [int(x) for x in doc.tokens("LocalCircuit", 1 + k, _INTS)]
+        out.append([(v[1 + 4 * j], tuple(v[2 + 4 * j:5 + 4 * j])) for j in range(3)])
+    return out
+
+
 def parse(path) -> Params:
     with open(path, "r") as f:
-        data = [line for line in f.read().split("\n") if line]
-    version = re.findall(r"[0-9\.]+", data[0])[0]
-    if version != VERSION:
-        raise ValueError("unknown file or version (only support v%s)" % VERSION)
-    tags = {}
-    for i, line in enumerate(data):
-        kw = re.findall(r"[a-zA-Z]+", line)
-        if kw:
-            tags[kw[0]] = i          # later lines overwrite earlier ones, as in the reference
-    need = ["Lattice", "Supercell", "Orbitals", "Bonds", "Temperature", "Sweeps", "Model", "Algorithm", "Ncores", "Field", "Dipole",
-            "Distribution", "XAxis", "OrbGroup", "LocalCircuit", "Measurement"]
-    missing = [k for k in need if not tags.get(k)]
-    if missing:
-        raise ValueError("cannot find some tags: %s" % ", ".join(missing))
-    t = tags
-    LMatrix = [[float(x) for x in re.findall(_NUM, data[t["Lattice"] + 1 + i])] for i in range(3)]
-    LPack = [int(x) for x in re.findall(r"[0-9]+", data[t["Supercell"] + 1])]
-    norb = int(re.findall(r"[0-9]+", data[t["Orbitals"] + 1])[0])
-    pos, S, DList = [], [], []
-    for i in range(norb):
-        e = re.findall(_NUM, data[t["Orbitals"] + 3 + i])
-        S.append(float(e[2]))
-        pos.append([float(e[3]), float(e[4]), float(e[5])])
-        DList.append([float(e[6]), float(e[7]), float(e[8])])
-    nb = int(re.findall(r"[0-9]+", data[t["Bonds"] + 1])[0])
-    bondList = []
-    for i in range(nb):
-        e = re.findall(_NUM, data[t["Bonds"] + 3 + i])
-        bondList.append([int(e[10]), int(e[11]), [int(e[12]), int(e[13]), int(e[14])]] + [float(v) for v in e[1:10]])
-    s_, t_, v1, v2, v3 = [int(x) for x in re.findall(r"[0-9\-]+", data[t["Measurement"] + 1])]
-    nG = int(re.findall(r"[0-9]+", data[t["OrbGroup"]])[0])
-    groupInSC = data[t["OrbGroup"] + 1] == "Supergroup"
-    groups = []
-    for i in range(nG):
-        _, a, b = re.findall(r"[0-9]+", data[t["OrbGroup"] + i + 2])
-        groups.append(list(range(int(a), int(b) + 1)))
-    nC = int(re.findall(r"[0-9]+", data[t["LocalCircuit"]])[0])
-    circuits = []
-    for i in range(nC):
-        e = [int(x) for x in re.findall(r"[0-9\-]+", data[t["LocalCircuit"] + 1 + i])]
-        circuits.append([(e[1], (e[2], e[3], e[4])), (e[5], (e[6], e[7], e[8])), (e[9], (e[10], e[11], e[12]))])
-    Tp = re.findall(r"[0-9\.]+", data[t["Temperature"] + 1])
-    Hp = re.findall(_NUM, data[t["Field"] + 1])
-    sw = [int(x) for x in re.findall(_NUM, data[t["Sweeps"] + 1])]
-    return Params(LMatrix=LMatrix, LPack=LPack, pos=pos, S=S, DList=DList, bondList=bondList, T0=float(Tp[0]), T1=float(Tp[1]),
-                  nT=int(Tp[2]), H0=float(Hp[0]), H1=float(Hp[1]), nH=int(Hp[2]),
-                  dipoleAlpha=float(re.findall(_NUM, data[t["Dipole"] + 1])[0]), nthermal=sw[0], nsweep=sw[1], ninterval=sw[2],
-                  xAxisType=data[t["XAxis"] + 1], modelType=data[t["Model"] + 1], algorithm=data[t["Algorithm"] + 1],
-                  GcOrb=[[s_, t_], [v1, v2, v3]], ncores=int(data[t["Ncores"] + 1]),
-                  spinFrame=int(re.findall(r"[0-9]+", data[t["Distribution"]])[0]), orbGroupList=groups, groupInSC=groupInSC,
-                  localCircuitList=circuits)
+        doc = _Doc(f.read())
+    kw = {}
+    for names, (key, offset, pattern, conv) in _SCALARS.items():
+        raw = [doc.line(key, offset)] if pattern is _WORD else doc.tokens(key, offset, pattern)
+        for name, fn, tok in zip(names, conv, raw):
+            kw[name] = fn(tok)
+    S, pos, D = _orbitals(doc)
+    groups, in_sc = _groups(doc)
+    corr = [int(x) for x in doc.tokens("Measurement", 1, _INTS)]      # orbS orbT over [a b c]
+    return Params(LMatrix=[[float(x) for x in doc.tokens("Lattice", 1 + k, _FLOATS)] for k in range(3)],
+                  LPack=[int(x) for x in doc.tokens("Supercell", 1, _UNSIGNED)], pos=pos, S=S, DList=D, bondList=_bonds(doc),
+                  GcOrb=[corr[0:2], corr[2:5]], orbGroupList=groups, groupInSC=in_sc, localCircuitList=_circuits(doc), **kw)
