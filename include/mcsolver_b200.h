@@ -209,8 +209,9 @@ MCG_API int mcg_profile_read(mcg_system *sys, double *total_ms, int64_t *nlaunch
 
 /* ---- the whole MCMainFunction loop on the resident system ----
  * thermalise nthermal intervals, then nsweep x (ninterval updates + measurement).
- * Metropolis: ninterval >= N -> round(ninterval/N) sweeps per interval, else one sweep with
- * attempt probability ninterval/N.  Wolff: ninterval cluster updates per interval.
+ * Metropolis: an interval of ninterval single-site attempts (heisenbergLib.c:614-620) = floor(ninterval/N) whole colour sweeps
+ * plus, for a remainder, one sweep in which every site attempts with probability (ninterval mod N)/N.
+ * Wolff: ninterval cluster updates per interval.
  * frames: NULL or [nReplica][spinFrame][N*3] (Ising [N]) host buffer (slot 27 / 10). */
 MCG_API int mcg_run(mcg_system *sys, int algorithm, int64_t nthermal, int64_t nsweep, int64_t ninterval, int spinFrame,
             double *frames);

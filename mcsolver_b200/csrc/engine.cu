@@ -676,22 +676,32 @@ static void run(mcg_system *s, int algorithm, int64_t nthermal, int64_t nsweep, 
     MCG_REQUIRE(algorithm == MCG_METROPOLIS || algorithm == MCG_WOLFF, "algorithm must be 0 (Metropolis) or 1 (Wolff)");
     MCG_REQUIRE(nthermal >= 0 && nsweep >= 1 && ninterval >= 0, "need nthermal>=0, nsweep>=1, ninterval>=0");
     MCG_REQUIRE(spinFrame >= 0 && (spinFrame == 0 || frames), "frames buffer is NULL");
-    int64_t nsub = 1;
+    // Metropolis: `ninterval` single-site attempts between two measurements (heisenbergLib.c:614-620) = floor(ninterval / N) whole
+    // colour sweeps plus, for the remainder, one sweep in which every site attempts with probability (ninterval mod N) / N.
+    // nsub sweeps per interval, the last of them with attempt probability pAtt.
+    int64_t nsub = 1, nfull = 0;
     double pAtt = 1.0;
     if (algorithm == MCG_METROPOLIS) {
         const int64_t Nw = s->normN();     // sites of the whole lattice (a slab holds a part of it plus ghosts)
-        if (ninterval >= Nw) nsub = (ninterval + Nw / 2) / Nw;
-        else if (ninterval > 0) pAtt = (double)ninterval / (double)Nw;
-        else nsub = 0;
+        nfull = ninterval / Nw;
+        const int64_t rem = ninterval % Nw;
+        if (rem > 0) pAtt = (double)rem / (double)Nw;
+        nsub = nfull + (rem > 0 ? 1 : 0);
     }
+    const bool partialLast = pAtt < 1.0;
     if (!s->structured && !s->profilePasses) {
         const int64_t per = algorithm == MCG_METROPOLIS ? nsub : ninterval;
         if (s->N <= resident_max_sites()) { run_resident(s, algorithm, nthermal * per, per, pAtt, nsweep, spinFrame, frames, 0); return; }
         if (const int B = coop_blocks_per_replica(s)) { run_resident(s, algorithm, nthermal * per, per, pAtt, nsweep, spinFrame, frames, B); return; }
     }
     auto updates = [&](int64_t intervals) {
-        if (algorithm == MCG_METROPOLIS) { if (nsub > 0) metropolis_sweeps(s, intervals * nsub, pAtt); }
-        else wolff_steps(s, intervals * ninterval);
+        if (algorithm != MCG_METROPOLIS) { wolff_steps(s, intervals * ninterval); return; }
+        if (nsub == 0) return;
+        if (!partialLast) { metropolis_sweeps(s, intervals * nfull, 1.0); return; }
+        for (int64_t i = 0; i < intervals; i++) {
+            if (nfull > 0) metropolis_sweeps(s, nfull, 1.0);
+            metropolis_sweeps(s, 1, pAtt);
+        }
     };
     // structured Metropolis: the measurement sums are produced by the last sweep of the interval itself
     const bool fused = s->structured && algorithm == MCG_METROPOLIS && nsub > 0;
@@ -700,7 +710,14 @@ static void run(mcg_system *s, int algorithm, int64_t nthermal, int64_t nsweep, 
     if (spinFrame > 0) per = std::max<int64_t>(1, nsweep / spinFrame);
     size_t fsz = (size_t)s->N * (s->NC == 1 ? 1 : 3);
     for (int64_t i = 0; i < nsweep; i++) {
-        if (fused) { s->wolffPrimed = false; structured_sweeps(s, nsub, pAtt, true); }
+        if (fused) {
+            s->wolffPrimed = false;
+            if (!partialLast) structured_sweeps(s, nfull, 1.0, true);
+            else {
+                if (nfull > 0) structured_sweeps(s, nfull, 1.0, false);
+                structured_sweeps(s, 1, pAtt, true);
+            }
+        }
         else updates(1);
         if (spinFrame > 0 && i % per == 0 && iFrame < spinFrame) {   // heisenbergLib.c:664-675, capped
             for (int r = 0; r < s->R; r++) capture_frame(s, r, frames + ((size_t)r * spinFrame + iFrame) * fsz);

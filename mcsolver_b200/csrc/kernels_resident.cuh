@@ -67,11 +67,11 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_resident(GenArgs a, RgArgs g
     if (tid < NRS) srs[tid] = 0.0;
     __syncthreads();
 
-    auto metro_sweep = [&]() {
+    auto metro_sweep = [&](double pAttThis) {
         int att = 0, acc = 0;
         for (int c = 0; c < P.C; c++) {
             const int cb = P.colourStart[c], ce = P.colourStart[c + 1];
-            for (int p = cb + tid; p < ce; p += nt) metro_site<NC, real, FULLJ>(a, sp, r, p, sweep, (real)P.pAtt, beta, hf, att, acc);
+            for (int p = cb + tid; p < ce; p += nt) metro_site<NC, real, FULLJ>(a, sp, r, p, sweep, (real)pAttThis, beta, hf, att, acc);
             __syncthreads();
         }
         sweep++;
@@ -158,17 +158,19 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_resident(GenArgs a, RgArgs g
         __syncthreads();
     };
 
-    auto update = [&]() {
-        if (P.algorithm == MCG_METROPOLIS) metro_sweep();
+    // u: index of the update inside its measurement interval - only the LAST sweep of an interval carries the attempt probability
+    // P.pAtt (the remainder of ninterval / N), the others are whole sweeps
+    auto update = [&](long long u) {
+        if (P.algorithm == MCG_METROPOLIS) metro_sweep(u == P.perSweep - 1 ? P.pAtt : 1.0);
         else wolff_step();
     };
 
-    for (long long u = 0; u < P.thermal; u++) update();
+    for (long long u = 0; u < P.thermal; u++) update(P.perSweep > 0 ? u % P.perSweep : 0);
     long long iFrame = P.spinFrame > 0 ? (P.i0 + P.per - 1) / P.per : 0;
     if (iFrame > P.spinFrame) iFrame = P.spinFrame;
     const size_t fsz = (size_t)N * (NC == 1 ? 1 : 3);
     for (long long i = 0; i < P.nsweep; i++) {
-        for (long long u = 0; u < P.perSweep; u++) update();
+        for (long long u = 0; u < P.perSweep; u++) update(u);
         if (P.spinFrame > 0 && (P.i0 + i) % P.per == 0 && iFrame < P.spinFrame) {   // heisenbergLib.c:664-675, capped
             double *dst = P.frames + ((size_t)r * P.spinFrame + iFrame) * fsz;
             for (int p = tid; p < N; p += nt) {
@@ -219,11 +221,11 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_resident_coop(GenArgs a, RgA
     const size_t RN = (size_t)w.R * N;
     const bool leader = bq == 0 && threadIdx.x == 0;
 
-    auto metro_sweep = [&]() {
+    auto metro_sweep = [&](double pAttThis) {
         int att = 0, acc = 0;
         for (int c = 0; c < P.C; c++) {
             const int cb = P.colourStart[c], ce = P.colourStart[c + 1];
-            for (int p = cb + tid; p < ce; p += nt) metro_site<NC, real, FULLJ>(a, sp, r, p, sweep, (real)P.pAtt, beta, hf, att, acc);
+            for (int p = cb + tid; p < ce; p += nt) metro_site<NC, real, FULLJ>(a, sp, r, p, sweep, (real)pAttThis, beta, hf, att, acc);
             grid.sync();
         }
         sweep++;
@@ -327,17 +329,19 @@ __global__ void __launch_bounds__(RES_THREADS, 1) k_resident_coop(GenArgs a, RgA
         grid.sync();   // the cleared sums must be in place before the next measurement adds to them
     };
 
-    auto update = [&]() {
-        if (P.algorithm == MCG_METROPOLIS) metro_sweep();
+    // u: index of the update inside its measurement interval - only the LAST sweep of an interval carries the attempt probability
+    // P.pAtt (the remainder of ninterval / N), the others are whole sweeps
+    auto update = [&](long long u) {
+        if (P.algorithm == MCG_METROPOLIS) metro_sweep(u == P.perSweep - 1 ? P.pAtt : 1.0);
         else wolff_step();
     };
 
-    for (long long u = 0; u < P.thermal; u++) update();
+    for (long long u = 0; u < P.thermal; u++) update(P.perSweep > 0 ? u % P.perSweep : 0);
     long long iFrame = P.spinFrame > 0 ? (P.i0 + P.per - 1) / P.per : 0;
     if (iFrame > P.spinFrame) iFrame = P.spinFrame;
     const size_t fsz = (size_t)N * (NC == 1 ? 1 : 3);
     for (long long i = 0; i < P.nsweep; i++) {
-        for (long long u = 0; u < P.perSweep; u++) update();
+        for (long long u = 0; u < P.perSweep; u++) update(u);
         if (P.spinFrame > 0 && (P.i0 + i) % P.per == 0 && iFrame < P.spinFrame) {   // heisenbergLib.c:664-675, capped
             double *dst = P.frames + ((size_t)r * P.spinFrame + iFrame) * fsz;
             for (int p = tid; p < N; p += nt) {

@@ -584,13 +584,13 @@ int orc_run(const orc_sys *s, int update_mode, long nthermal, long nsweep, long 
     memset(&st, 0, sizeof st);
     recompute_state(s, sp, &st);
     uint64_t sweepCtr = 0;
-    /* mapping of (ninterval single-site attempts) onto colour sweeps, engine convention:
-     * ninterval >= N -> round(ninterval/N) full sweeps; < N -> one pass, attempt prob ninterval/N */
-    long nsub = 1;
-    double pAtt = 1.0;
+    /* mapping of (ninterval single-site attempts) onto colour sweeps, engine convention: floor(ninterval/N) whole sweeps, then -
+     * for a remainder - one sweep in which every site attempts with probability (ninterval mod N)/N */
+    long nfull = 0;
+    double pPart = 0.0;
     if (update_mode == 2) {
-        if (ninterval >= N) nsub = (long)((ninterval + N / 2) / N);
-        else pAtt = (double)ninterval / (double)N;
+        nfull = (long)(ninterval / N);
+        pPart = (double)(ninterval % N) / (double)N;
     }
 #define DO_UPDATES(count)                                                                                   \
     for (long long q_ = 0; q_ < (count); q_++) {                                                            \
@@ -598,19 +598,24 @@ int orc_run(const orc_sys *s, int update_mode, long nthermal, long nsweep, long 
         else if (update_mode == 1) on_block_update(s, sp, &st, 0, 0, 0, 0, 0, scr_i, scr_d);                \
         else if (update_mode == 3) { on_block_update(s, sp, &st, 1, seed, replica, sweepCtr, f32, scr_i, scr_d); sweepCtr++; } \
     }
-#define DO_SWEEPS(count)                                                                                    \
+#define DO_SWEEPS(count, pa)                                                                                \
     for (long long q_ = 0; q_ < (count); q_++) {                                                            \
         for (int p_ = 0; p_ < N; p_++) {                                                                    \
             int i_ = order[p_];                                                                             \
             uint32_t r_[4];                                                                                 \
-            site_words(s, seed, replica, sweepCtr, (uint32_t)i_, pAtt < 1.0, r_);                           \
-            on_attempt_philox(s, sp, i_, r_, f32, pAtt, &st);                                               \
+            site_words(s, seed, replica, sweepCtr, (uint32_t)i_, (pa) < 1.0, r_);                           \
+            on_attempt_philox(s, sp, i_, r_, f32, (pa), &st);                                               \
         }                                                                                                   \
         sweepCtr++;                                                                                         \
     }
+#define DO_INTERVALS(count)                                                                                 \
+    for (long long v_ = 0; v_ < (count); v_++) {                                                            \
+        DO_SWEEPS(nfull, 1.0);                                                                              \
+        if (pPart > 0.0) DO_SWEEPS(1, pPart);                                                               \
+    }
     if (update_mode == 2) {
         /* thermalisation: nthermal measurement-intervals worth of updates */
-        DO_SWEEPS((long long)nthermal * nsub);
+        DO_INTERVALS(nthermal);
         recompute_state(s, sp, &st);
     } else {
         DO_UPDATES((long long)ninterval * (long long)nthermal); /* heisenbergLib.c:614-620 */
@@ -628,7 +633,7 @@ int orc_run(const orc_sys *s, int update_mode, long nthermal, long nsweep, long 
     if (spinFrame > 0) per = nsweep / spinFrame;
     if (per < 1) per = 1;
     for (long isweep = 0; isweep < nsweep; isweep++) {
-        if (update_mode == 2) { DO_SWEEPS(nsub); recompute_state(s, sp, &st); }
+        if (update_mode == 2) { DO_INTERVALS(1); recompute_state(s, sp, &st); }
         else { DO_UPDATES(ninterval); if (update_mode == 3) recompute_state(s, sp, &st); }
         if (spinFrame > 0 && isweep % per == 0 && iFrame < spinFrame) { /* :664-675 (+cap) */
             memcpy(frames + (size_t)iFrame * N * 3, sp, sizeof(double) * 3 * (size_t)N);
@@ -753,11 +758,9 @@ int orc_run_ising(const orc_sys *s, int update_mode, long nthermal, long nsweep,
     orc_state st;
     memset(&st, 0, sizeof st);
     uint64_t sweepCtr = 0;
-    long nsub = 1;
-    double pAtt = 1.0;
-    if (update_mode == 2) {
-        if (ninterval >= N) nsub = (long)((ninterval + N / 2) / N); else pAtt = (double)ninterval / (double)N;
-    }
+    long nfull = 0;
+    double pPart = 0.0;
+    if (update_mode == 2) { nfull = (long)(ninterval / N); pPart = (double)(ninterval % N) / (double)N; }   /* as in orc_run */
     if (update_mode <= 1) {
         /* isingLib.c:348-350: energy starts at 0 (relative!), totSpin sums `ninterval` entries */
         long lim = ninterval < N ? ninterval : N;
@@ -772,17 +775,22 @@ int orc_run_ising(const orc_sys *s, int update_mode, long nthermal, long nsweep,
         else if (update_mode == 1) ising_block_update(s, sp, &st, 0, 0, 0, 0, 0, scr);                       \
         else if (update_mode == 3) { ising_block_update(s, sp, &st, 1, seed, replica, sweepCtr, f32, scr); sweepCtr++; } \
     }
-#define I_SWEEPS(count)                                                                                      \
+#define I_SWEEPS(count, pa)                                                                                  \
     for (long long q_ = 0; q_ < (count); q_++) {                                                             \
         for (int p_ = 0; p_ < N; p_++) {                                                                     \
             int i_ = order[p_];                                                                              \
             uint32_t r_[4];                                                                                  \
-            site_words(s, seed, replica, sweepCtr, (uint32_t)i_, pAtt < 1.0, r_);                            \
-            ising_attempt_philox(s, sp, i_, r_[2], r_[3], f32, pAtt, &st);                                   \
+            site_words(s, seed, replica, sweepCtr, (uint32_t)i_, (pa) < 1.0, r_);                            \
+            ising_attempt_philox(s, sp, i_, r_[2], r_[3], f32, (pa), &st);                                   \
         }                                                                                                    \
         sweepCtr++;                                                                                          \
     }
-    if (update_mode == 2) { I_SWEEPS((long long)nthermal * nsub); }
+#define I_INTERVALS(count)                                                                                   \
+    for (long long v_ = 0; v_ < (count); v_++) {                                                             \
+        I_SWEEPS(nfull, 1.0);                                                                                \
+        if (pPart > 0.0) I_SWEEPS(1, pPart);                                                                 \
+    }
+    if (update_mode == 2) { I_INTERVALS(nthermal); }
     else { I_UPDATES((long long)((int)nthermal * (int)ninterval)); } /* :352 int product */
     double spin_i = 0, spin_j = 0, spin_ij = 0, totE = 0, totEr = 0, E2 = 0, E2r = 0;
     if (update_mode <= 1) st.energy = 0; /* :359 */
@@ -793,7 +801,7 @@ int orc_run_ising(const orc_sys *s, int update_mode, long nthermal, long nsweep,
     if (per < 1) per = 1;
     double nLat = (double)s->nLat;
     for (long isw = 0; isw < nsweep; isw++) {
-        if (update_mode == 2) { I_SWEEPS(nsub); }
+        if (update_mode == 2) { I_INTERVALS(1); }
         else { I_UPDATES(ninterval); }
         if (update_mode >= 2) {
             st.energy = orc_total_energy(s, sp);

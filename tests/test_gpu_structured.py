@@ -100,6 +100,28 @@ def test_structured_whole_run_fused_measurement_matches_oracle(case, jit_mode):
     assert np.max(np.abs(fr[0] - r["frames"])) < 1e-9
 
 
+@pytest.mark.parametrize("case", [CASES[1], CASES[8], CASES[11]], ids=[IDS[1], IDS[8], IDS[11]])
+def test_structured_whole_run_with_a_fractional_interval_matches_oracle(case, jit_mode):
+    """ninterval = 1.5 N on the structured path: one whole sweep, then a half sweep that carries the fused measurement."""
+    eng = _eng()
+    name, L, T, model, h = case
+    spec = spec_of(name, L)
+    t = util.tables_for(dict(spec=name, L=L, T=T, model=model))
+    o = util.oracle_system(t, h / T)
+    nint = t.N + t.N // 2
+    with eng.System.from_spec(spec, model, precision=64, beta=[1.0 / T], field=[h], seed=17) as s:
+        order = s.colour_order()
+        o.rng_layout = s.rng_layout()
+        s.init_spins(0.3)
+        s.run(0, 3, 10, nint)
+        out, _ = s.results()
+        _check_jit_ran(s, jit_mode)
+    r = o.run(2, 3, 10, nint, flunc=0.3, order=order, seed=17)
+    slots = [0, 2, 4, 5, 8] if model == 1 else util.ON_CORE_SLOTS + [7]
+    for k in slots:
+        assert abs(out[k] - r["out"][k]) <= 1e-9 * max(1.0, abs(r["out"][k])), (k, out[k], r["out"][k])
+
+
 def test_structured_replicas_are_independent_points_of_a_scan():
     """A batch of replicas = the reference's (T,H) grid: replica r of a batch gives exactly what a
     single-replica system with replica_offset=r gives (GPU-count independent streams)."""
