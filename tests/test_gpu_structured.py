@@ -259,3 +259,28 @@ def test_structured_block_spin_rejects_supercells_the_descriptor_cannot_express(
     for L in [(4, 6, 8), (5, 5, 1)]:
         with pytest.raises(eng.McgError, match="block_spin"):
             eng.System.from_spec(spec_of("cubic" if L[2] > 1 else "square", L), 3 if L[2] > 1 else 2, precision=64, block_spin=True)
+
+
+@pytest.mark.parametrize("flunc", [0.3, 3.0], ids=["smooth", "rough"])
+def test_packed_fp32_topological_charge_equals_the_fp64_evaluation(flunc, monkeypatch):
+    """The fp32 specialised topological-charge kernel works on two cells at a time with packed arithmetic and a hand-written
+    2 atan(im/re) (topo_pass.cuh: topo_cell_pair); the fp64 engine keeps the reference's double arithmetic (calcSignedArea,
+    heisenbergLib.c:114-127; <= 1e-12 against the reference's known answers).  Same configuration in both: Q must agree to the
+    fp32 rounding of the inputs, for smooth textures (small solid angles: relative accuracy) and rough ones (all quadrants)."""
+    eng = _eng()
+    monkeypatch.setenv("MCG_JIT", "1")
+    spec = spec_of("skyrmion", (96, 64, 1))
+    with eng.System.from_spec(spec, 3, precision=64, beta=[1 / 0.3], field=[0.2], seed=4) as d:
+        d.init_spins(flunc)
+        d.metropolis_sweeps(2)
+        sp = d.get_spins()
+        d.measure()
+        q64 = d.results()[0][26]
+    with eng.System.from_spec(spec, 3, precision=32, beta=[1 / 0.3], field=[0.2], seed=4) as s:
+        s.set_spins(sp)
+        s.measure()
+        q32 = s.results()[0][26]
+        assert s.jit_launch_count() > 0
+    ntri = 4 * 96 * 64
+    assert abs(q32 - q64) < 2e-6 * np.sqrt(ntri) + 1e-6 * abs(q64), (q32, q64)
+    assert abs(q64) > 1e-3 or flunc < 1.0
