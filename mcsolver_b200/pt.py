@@ -98,34 +98,6 @@ def local_allgather(x):
     return np.asarray(x)
 
 
-def torch_allgather(device=None):
-    """allgather over torch.distributed: NCCL (NVLink/NVSwitch) when `device` is a CUDA device, gloo on CPU."""
-    import torch
-    import torch.distributed as dist
-
-    def ag(x):
-        t = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64))
-        if device is not None:
-            t = t.to(device)
-        out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
-        dist.all_gather(out, t)
-        return torch.cat(out).cpu().numpy()
-    return ag
-
-
-def torch_allreduce_sum(device=None):
-    import torch
-    import torch.distributed as dist
-
-    def ar(x):
-        t = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64))
-        if device is not None:
-            t = t.to(device)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return t.cpu().numpy()
-    return ar
-
-
 class Ladder:
     """Bookkeeping of which replica carries which label; independent of the engine (CPU-testable)."""
 

@@ -4,6 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch, torch.distributed as dist
 from mcsolver_b200 import pt
+from tests import dist_util
 from mcsolver_b200.lattice import LatticeSpec, add_dipole_stencil
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -20,7 +21,7 @@ NTH, NSW, SPS = int(os.environ.get("NTHERMAL", "200")), int(os.environ.get("NSWE
 n = 8 * world
 T = 0.8 * 1.443 * (1.3 / 0.8) ** (np.arange(n) / (n - 1))
 p = pt.ParallelTempering(spec, 3, T, precision=32, seed=3, rank=rank, world=world, device=local,
-                         allgather=pt.torch_allgather(dev), allreduce_sum=pt.torch_allreduce_sum(dev))
+                         allgather=dist_util.torch_allgather(dev), allreduce_sum=dist_util.torch_allreduce_sum(dev))
 p.sys.timed_sweeps(1, with_measure=True)   # first launch of each specialised kernel (NVRTC compile or cubin load) stays untimed
 p.sys.reset_measurements()
 dist.barrier(); torch.cuda.synchronize()

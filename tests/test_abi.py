@@ -86,6 +86,8 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(root, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
                 assert "liboracle" not in src and "refharness" not in src, f
+                # north_star: no PyTorch, Triton or other backends in the product - the multi-GPU paths talk to NCCL themselves
+                assert not re.search(r"^\s*(from|import)\s+(torch|triton|jax|cupy)\b", src, re.M), f
 
 
 def test_engine_errors_survive_the_process_pool_of_the_reference_host():

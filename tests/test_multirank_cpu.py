@@ -17,12 +17,13 @@ import numpy as np
 sys.path.insert(0, os.environ["MCG_ROOT"])
 import torch.distributed as dist
 from mcsolver_b200 import pt, scan
+from tests import dist_util
 dist.init_process_group(backend="gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 n = 16
 T = np.linspace(1.0, 2.5, n)
 lad = pt.Ladder(1.0 / T, np.zeros(n), rank=rank, world=world, seed=7)
-ag = pt.torch_allgather(None)
+ag = dist_util.torch_allgather(None)
 rng = np.random.RandomState(100 + rank)
 lo, hi = lad.lo, lad.hi
 hist = []
